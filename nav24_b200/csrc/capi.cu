@@ -1,0 +1,694 @@
+// capi.cu — C ABI (include/nav24_orb.h) on top of the sm_100a kernels: context, device workspace,
+// stream orchestration.  Host-side set-up math (scale tables, quotas, level sizes, cell grids,
+// resize coefficient tables) restates the reference's float/double arithmetic exactly:
+//   ctor / setNumFeatures   core/operators/objDetection/OP_FtDtOrbSlam.cpp:441-500, :962-976
+//   level sizes             :940        cell grid  :735-768      quadtree roots  :505-527
+// There is no CPU compute path: every entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "orb_internal.cuh"
+
+using namespace nav24;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return ctx->fail(NAV24_E_CUDA, #call, e_);                          \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; bytes = 0;
+        size_t want = need + need / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct nav24_orb {
+    int device = 0;
+    nav24_orb_params prm{};
+    int nIniFeatures = 0;
+    double scaleFactorD = 1.2;
+    std::vector<float> scale, invScale;
+    std::vector<int> quota;
+    std::string err;
+    cudaStream_t stream = nullptr, copyStream = nullptr;
+    cudaEvent_t ev[6]{};
+    long long launches = 0;
+
+    // workspace keyed on (w, h, nFeatures); batch capacity grows on demand
+    int wsW = 0, wsH = 0, wsB = 0, wsFeat = -1;
+    FrameGeom g{};
+    DevPtrs p{};
+    std::vector<ResizeTab> tabs;
+    DevBuf bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
+        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs;
+    // matcher scratch
+    DevBuf mK1, mK2, mU1, mU2, mD1, mD2, mN1, mN2, mCellOf, mCellStart, mCellFill, mCellItems, mCand, mCandCnt, mDist2,
+        mM21, mBins, mMatches, mNMatches, mPairs, mI0, mI1, mF0, mF1, mPass;
+    int lastB = 0;            // frames of the last detect call
+    bool lastValid = false;
+    int l0Pitch = 0;
+
+    int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+        err = what;
+        if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
+        return code;
+    }
+
+    void compute_quota(int n) {
+        prm.n_features = n;
+        const int nl = prm.n_levels;
+        float factor = 1.0f / scaleFactorD;
+        float per = n * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; ++l) {
+            quota[l] = (int)lrintf(per);
+            sum += quota[l];
+            per *= factor;
+        }
+        quota[nl - 1] = std::max(n - sum, 0);
+    }
+};
+
+namespace {
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Builds the frame geometry for (w,h). Returns NAV24_OK or NAV24_E_GEOMETRY.
+int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
+    memset(&g, 0, sizeof(g));
+    const int nl = ctx->prm.n_levels;
+    g.nlevels = nl;
+    const int rawPerKpx = ctx->prm.raw_keys_per_kpx > 0 ? ctx->prm.raw_keys_per_kpx : 125;
+    long long off = 0, boff = 0;
+    int cellBase = 0, rawOff = 0, nodeOff = 0, kpOff = 0;
+    for (int l = 0; l < nl; ++l) {
+        LevelGeom& L = g.lv[l];
+        L.w = (int)lrintf((float)w * ctx->invScale[l]);
+        L.h = (int)lrintf((float)h * ctx->invScale[l]);
+        if (L.w >= 8192 || L.h >= 8192) return ctx->fail(NAV24_E_GEOMETRY, "image larger than 8191 px not supported");
+        L.pitch = align_up(L.w, 128);
+        L.off = off;
+        if (l > 0) off += (long long)L.pitch * L.h;
+        L.boff = boff;
+        boff += (long long)L.pitch * L.h;
+        const int minBX = kMinBorder, minBY = kMinBorder;
+        L.maxBX = L.w - kEdge + 3;
+        L.maxBY = L.h - kEdge + 3;
+        const float width = (float)(L.maxBX - minBX), height = (float)(L.maxBY - minBY);
+        if (width < 35.f || height < 35.f) return ctx->fail(NAV24_E_GEOMETRY, "pyramid level smaller than one 35-px FAST cell");
+        L.nCols = (int)(width / 35.f);
+        L.nRows = (int)(height / 35.f);
+        L.wCell = (int)std::ceil(width / L.nCols);
+        L.hCell = (int)std::ceil(height / L.nRows);
+        if (L.wCell + 6 > kMaxCellTile || L.hCell + 6 > kMaxCellTile) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
+        L.cellBase = cellBase;
+        cellBase += L.nCols * L.nRows;
+        long long cap = ((long long)L.w * L.h * rawPerKpx + 999) / 1000 + 64;
+        if (cap >= (1 << 19)) cap = (1 << 19) - 1;      // sort key packs count into 19 bits
+        L.rawCap = (int)cap;
+        L.rawOff = rawOff;
+        rawOff += align_up(L.rawCap, 4);
+        L.quota = ctx->quota[l];
+        L.nIni = (int)std::round((float)(L.maxBX - minBX) / (L.maxBY - minBY));
+        if (L.nIni < 1) return ctx->fail(NAV24_E_GEOMETRY, "image taller than 2:1, the quadtree has no root node");
+        L.hX = (float)(L.maxBX - minBX) / (float)L.nIni;
+        L.nodeCap = align_up(std::max(4 * L.nIni, L.quota + 3) + 4, 4);
+        L.nodeOff = nodeOff;
+        nodeOff += L.nodeCap;
+        L.kpOff = kpOff;
+        L.kpCap = L.nodeCap;
+        kpOff += L.kpCap;
+        L.scale = ctx->scale[l];
+        L.patch = (float)(int)(31 * ctx->scale[l]);
+    }
+    g.totalCells = cellBase;
+    g.rawPerFrame = rawOff;
+    g.nodesPerFrame = nodeOff;
+    g.kpPerFrame = kpOff;
+    g.outCap = kpOff;
+    g.blurFrameBytes = (boff + 255) / 256 * 256;
+    g.pyrFrameBytes = (off + 255) / 256 * 256;
+    return NAV24_OK;
+}
+
+// cv::resize coefficient tables, computed exactly like OpenCV does on the host.
+void build_resize_table(int ssize, int dsize, std::vector<int>& ofs, std::vector<short2>& ab) {
+    ofs.resize(dsize); ab.resize(dsize);
+    const double inv = (double)dsize / ssize, scale = 1.0 / inv;
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        ofs[d] = s;
+        ab[d].x = (short)lrintf((1.f - f) * 2048.f);
+        ab[d].y = (short)lrintf(f * 2048.f);
+    }
+}
+
+int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
+    cudaSetDevice(ctx->device);
+    const bool shapeChanged = (w != ctx->wsW || h != ctx->wsH || ctx->prm.n_features != ctx->wsFeat);
+    if (shapeChanged) {
+        FrameGeom g;
+        int rc = build_geometry(ctx, w, h, g);
+        if (rc != NAV24_OK) return rc;
+        ctx->g = g;
+        // resize tables
+        const int nl = g.nlevels;
+        std::vector<int> allOfs; std::vector<short2> allAb;
+        std::vector<size_t> oX(nl), oY(nl);
+        for (int l = 1; l < nl; ++l) {
+            std::vector<int> o; std::vector<short2> a;
+            build_resize_table(g.lv[l - 1].w, g.lv[l].w, o, a);
+            oX[l] = allOfs.size(); allOfs.insert(allOfs.end(), o.begin(), o.end()); allAb.insert(allAb.end(), a.begin(), a.end());
+            build_resize_table(g.lv[l - 1].h, g.lv[l].h, o, a);
+            oY[l] = allOfs.size(); allOfs.insert(allOfs.end(), o.begin(), o.end()); allAb.insert(allAb.end(), a.begin(), a.end());
+        }
+        const size_t nT = allOfs.size();
+        CK(ctx->bTabs.ensure(nT * 8 + 16));
+        int* dOfs = (int*)ctx->bTabs.ptr;
+        short2* dAb = (short2*)((char*)ctx->bTabs.ptr + nT * 4);
+        if (nT) {
+            CK(cudaMemcpyAsync(dOfs, allOfs.data(), nT * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(dAb, allAb.data(), nT * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->tabs.assign(nl, ResizeTab{});
+        for (int l = 1; l < nl; ++l) ctx->tabs[l] = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l]};
+        ctx->wsW = w; ctx->wsH = h; ctx->wsFeat = ctx->prm.n_features; ctx->wsB = 0;
+        ctx->lastValid = false;
+    }
+    if (B > ctx->wsB || shapeChanged) {
+        const FrameGeom& g = ctx->g;
+        const size_t b = (size_t)std::max(B, ctx->wsB);
+        ctx->l0Pitch = align_up(w, 128);
+        CK(ctx->bL0.ensure(b * (size_t)ctx->l0Pitch * h));
+        CK(ctx->bPyr.ensure(b * (size_t)g.pyrFrameBytes + 256));
+        CK(ctx->bBlur.ensure(b * (size_t)g.blurFrameBytes));
+        CK(ctx->bCell.ensure(b * g.totalCells * sizeof(uint2)));
+        CK(ctx->bCellDst.ensure(b * g.totalCells * sizeof(int)));
+        CK(ctx->bRawCount.ensure(b * g.nlevels * sizeof(int)));
+        CK(ctx->bRaw.ensure(b * g.rawPerFrame * sizeof(RawRec)));
+        CK(ctx->bKeys.ensure(b * g.rawPerFrame * sizeof(RawRec)));
+        CK(ctx->bNodeOfKey.ensure(b * g.rawPerFrame * sizeof(int)));
+        CK(ctx->bNodesA.ensure(b * g.nodesPerFrame * sizeof(QNode)));
+        CK(ctx->bNodesB.ensure(b * g.nodesPerFrame * sizeof(QNode)));
+        CK(ctx->bChild.ensure(b * g.nodesPerFrame * 4 * sizeof(int)));
+        CK(ctx->bAux.ensure(b * g.nodesPerFrame * sizeof(int)));
+        CK(ctx->bBest.ensure(b * g.nodesPerFrame * sizeof(unsigned long long)));
+        CK(ctx->bSort.ensure(b * g.nodesPerFrame * sizeof(unsigned long long)));
+        CK(ctx->bLkp.ensure(b * g.kpPerFrame * sizeof(LevelKp)));
+        CK(ctx->bLevelCount.ensure(b * g.nlevels * sizeof(int)));
+        CK(ctx->bRawTotal.ensure(b * g.nlevels * sizeof(int)));
+        CK(ctx->bOutKp.ensure(b * g.outCap * sizeof(nav24_kp)));
+        CK(ctx->bOutDesc.ensure(b * g.outCap * 32));
+        CK(ctx->bNOut.ensure(b * sizeof(int)));
+        CK(ctx->bMono.ensure(b * sizeof(int)));
+        CK(ctx->bErr.ensure(sizeof(int) * 4));
+        ctx->wsB = (int)b;
+        DevPtrs& p = ctx->p;
+        p.pyr = (uint8_t*)ctx->bPyr.ptr; p.blur = (uint8_t*)ctx->bBlur.ptr;
+        p.cellInfo = (uint2*)ctx->bCell.ptr; p.cellDst = (int*)ctx->bCellDst.ptr; p.rawCount = (int*)ctx->bRawCount.ptr;
+        p.raw = (RawRec*)ctx->bRaw.ptr; p.keys = (RawRec*)ctx->bKeys.ptr; p.nodeOfKey = (int*)ctx->bNodeOfKey.ptr;
+        p.nodesA = (QNode*)ctx->bNodesA.ptr; p.nodesB = (QNode*)ctx->bNodesB.ptr; p.childCnt = (int*)ctx->bChild.ptr;
+        p.nodeAux = (int*)ctx->bAux.ptr; p.best = (unsigned long long*)ctx->bBest.ptr;
+        p.sortRec = (unsigned long long*)ctx->bSort.ptr; p.lkp = (LevelKp*)ctx->bLkp.ptr;
+        p.levelCount = (int*)ctx->bLevelCount.ptr; p.rawTotal = (int*)ctx->bRawTotal.ptr;
+        p.outKp = (nav24_kp*)ctx->bOutKp.ptr; p.outDesc = (uint8_t*)ctx->bOutDesc.ptr;
+        p.nOut = (int*)ctx->bNOut.ptr; p.monoOut = (int*)ctx->bMono.ptr; p.err = (int*)ctx->bErr.ptr;
+        ctx->lastValid = false;
+    }
+    return NAV24_OK;
+}
+
+// enqueue the whole per-frame chain on ctx->stream; no host synchronisation
+int run_pipeline(nav24_orb* ctx, int B) {
+    const FrameGeom& g = ctx->g;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), s));
+    CK(cudaEventRecord(ctx->ev[0], s));
+    ctx->launches += launch_pyramid(g, ctx->p, ctx->tabs.data(), B, s);
+    CK(cudaEventRecord(ctx->ev[1], s));
+    ctx->launches += launch_fast(g, ctx->p, B, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);
+    CK(cudaEventRecord(ctx->ev[2], s));
+    ctx->launches += launch_quadtree(g, ctx->p, B, s);
+    CK(cudaEventRecord(ctx->ev[3], s));
+    ctx->launches += launch_describe(g, ctx->p, B, s);
+    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaGetLastError());
+    ctx->lastB = B;
+    ctx->lastValid = true;
+    return NAV24_OK;
+}
+
+int check_device_error(nav24_orb* ctx) {
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (e & ERR_RAW_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "raw FAST corner buffer overflow (raise raw_keys_per_kpx)");
+    if (e & ERR_ROOT_RANGE) return ctx->fail(NAV24_E_GEOMETRY, "keypoint outside the quadtree roots");
+    if (e & ERR_NODE_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "quadtree node buffer overflow");
+    if (e & ERR_CELL_SIZE) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
+    if (e & ERR_KP_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "output keypoint buffer overflow");
+    return NAV24_OK;
+}
+
+int fetch_results(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
+    if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results to fetch");
+    const int B = ctx->lastB;
+    const FrameGeom& g = ctx->g;
+    std::vector<int> n(B), m(B);
+    CK(cudaMemcpyAsync(n.data(), ctx->p.nOut, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(m.data(), ctx->p.monoOut, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    const int ccap = std::min(cap, g.outCap);
+    if (kps && ccap > 0)
+        CK(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(nav24_kp), ctx->p.outKp, (size_t)g.outCap * sizeof(nav24_kp),
+                             (size_t)ccap * sizeof(nav24_kp), B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc && ccap > 0)
+        CK(cudaMemcpy2DAsync(desc, (size_t)cap * 32, ctx->p.outDesc, (size_t)g.outCap * 32, (size_t)ccap * 32, B,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = check_device_error(ctx);   // synchronises the stream
+    if (rc != NAV24_OK) return rc;
+    bool small = false;
+    for (int f = 0; f < B; ++f) {
+        if (n_out) n_out[f] = n[f];
+        if (mono_out) mono_out[f] = m[f];
+        if ((kps || desc) && n[f] > cap) small = true;
+    }
+    if (small) return ctx->fail(NAV24_E_CAPACITY, "output capacity too small");
+    return NAV24_OK;
+}
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+int nav24_abi_version(void) { return NAV24_ABI_VERSION; }
+
+int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out) {
+    if (!params || !out) return NAV24_E_BADARG;
+    *out = nullptr;
+    if (params->n_levels < 1 || params->n_levels > kMaxLevels || params->n_features < 0 || params->ini_th_fast < 1 ||
+        params->min_th_fast < 1 || !(params->scale_factor > 1.0f))
+        return NAV24_E_BADARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return NAV24_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return NAV24_E_CUDA;
+    nav24_orb* ctx = new nav24_orb();
+    ctx->device = device;
+    ctx->prm = *params;
+    ctx->nIniFeatures = params->n_features;
+    ctx->scaleFactorD = (double)params->scale_factor;      // the reference stores it in a double member
+    const int nl = params->n_levels;
+    ctx->scale.resize(nl); ctx->invScale.resize(nl); ctx->quota.resize(nl);
+    ctx->scale[0] = 1.0f;
+    for (int i = 1; i < nl; ++i) ctx->scale[i] = ctx->scale[i - 1] * ctx->scaleFactorD;
+    for (int i = 0; i < nl; ++i) ctx->invScale[i] = 1.0f / ctx->scale[i];
+    ctx->compute_quota(params->n_features);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return NAV24_E_CUDA;
+    }
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    *out = ctx;
+    return NAV24_OK;
+}
+
+void nav24_orb_destroy(nav24_orb* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&ctx->bL0, &ctx->bPyr, &ctx->bBlur, &ctx->bCell, &ctx->bCellDst, &ctx->bRawCount, &ctx->bRaw, &ctx->bKeys,
+                      &ctx->bNodeOfKey, &ctx->bNodesA, &ctx->bNodesB, &ctx->bChild, &ctx->bAux, &ctx->bBest, &ctx->bSort,
+                      &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
+                      &ctx->bErr, &ctx->bTabs, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
+                      &ctx->mN2, &ctx->mCellOf, &ctx->mCellStart, &ctx->mCellFill, &ctx->mCellItems, &ctx->mCand, &ctx->mCandCnt,
+                      &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mI0, &ctx->mI1,
+                      &ctx->mF0, &ctx->mF1, &ctx->mPass};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    delete ctx;
+}
+
+int nav24_orb_set_num_features(nav24_orb* ctx, int n) {
+    if (!ctx || n < 0) return NAV24_E_BADARG;
+    ctx->compute_quota(n);
+    return NAV24_OK;
+}
+int nav24_orb_get_num_features(const nav24_orb* ctx) { return ctx ? ctx->prm.n_features : NAV24_E_BADARG; }
+
+int nav24_orb_get_tables(const nav24_orb* ctx, float* scale, float* inv_scale, int32_t* fpl) {
+    if (!ctx) return NAV24_E_BADARG;
+    for (int l = 0; l < ctx->prm.n_levels; ++l) {
+        if (scale) scale[l] = ctx->scale[l];
+        if (inv_scale) inv_scale[l] = ctx->invScale[l];
+        if (fpl) fpl[l] = ctx->quota[l];
+    }
+    return NAV24_OK;
+}
+
+const char* nav24_last_error_string(const nav24_orb* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nav24_orb_max_keypoints(const nav24_orb* ctx) {
+    if (!ctx) return NAV24_E_BADARG;
+    // quota + 3 per level is the quadtree bound; wide images can start with 4*nIni > quota nodes
+    int n = 0;
+    for (int l = 0; l < ctx->prm.n_levels; ++l) n += std::max(ctx->quota[l] + 3, 64) + 4 + 4;
+    if (ctx->wsFeat == ctx->prm.n_features && ctx->wsW > 0) n = std::max(n, ctx->g.outCap);
+    return n;
+}
+
+int nav24_orb_detect_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames, int w, int h, size_t stride,
+                            size_t frame_stride) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!d_gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+    int rc = ensure_workspace(ctx, w, h, n_frames);
+    if (rc != NAV24_OK) return rc;
+    const bool aligned = (((uintptr_t)d_gray | stride | frame_stride) & 15) == 0;
+    if (aligned) {
+        ctx->p.l0 = d_gray; ctx->p.l0Pitch = (long long)stride; ctx->p.l0Frame = (long long)frame_stride;
+    } else {
+        for (int f = 0; f < n_frames; ++f)
+            CK(cudaMemcpy2DAsync((uint8_t*)ctx->bL0.ptr + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch,
+                                 d_gray + (size_t)f * frame_stride, stride, w, h, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->p.l0 = (const uint8_t*)ctx->bL0.ptr; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
+    }
+    return run_pipeline(ctx, n_frames);
+}
+
+int nav24_orb_fetch(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
+    if (!ctx) return NAV24_E_BADARG;
+    cudaSetDevice(ctx->device);
+    return fetch_results(ctx, kps, desc, cap, n_out, mono_out);
+}
+
+int nav24_orb_sync(nav24_orb* ctx) {
+    if (!ctx) return NAV24_E_BADARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NAV24_OK;
+}
+
+int nav24_orb_detect_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int w, int h, size_t stride,
+                           size_t frame_stride, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+    int rc = ensure_workspace(ctx, w, h, n_frames);
+    if (rc != NAV24_OK) return rc;
+    uint8_t* l0 = (uint8_t*)ctx->bL0.ptr;
+    if (frame_stride == stride * (size_t)h) {
+        CK(cudaMemcpy2DAsync(l0, ctx->l0Pitch, gray, stride, w, (size_t)h * n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (int f = 0; f < n_frames; ++f)
+            CK(cudaMemcpy2DAsync(l0 + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch, gray + (size_t)f * frame_stride, stride, w,
+                                 h, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->p.l0 = l0; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
+    rc = run_pipeline(ctx, n_frames);
+    if (rc != NAV24_OK) return rc;
+    return fetch_results(ctx, kps, desc, cap, n_out, mono_out);
+}
+
+int nav24_orb_detect(nav24_orb* ctx, const uint8_t* gray, int w, int h, size_t stride, nav24_kp* kps, uint8_t* desc,
+                     int cap, int* n_out) {
+    int mono = 0, n = 0;
+    int rc = nav24_orb_detect_batch(ctx, gray, 1, w, h, stride, stride * (size_t)(h > 0 ? h : 0), kps, desc, cap, &n, &mono);
+    if (n_out) *n_out = n;
+    return rc < 0 ? rc : mono;
+}
+
+int nav24_orb_get_level(nav24_orb* ctx, int frame, int level, int which, uint8_t* dst, size_t dst_stride, int* w, int* h) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
+        return ctx->fail(NAV24_E_BADARG, "bad frame/level");
+    cudaSetDevice(ctx->device);
+    const LevelGeom& L = ctx->g.lv[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!dst) return NAV24_OK;
+    const uint8_t* src; size_t pitch;
+    if (which == 1) { src = ctx->p.blur + (size_t)frame * ctx->g.blurFrameBytes + L.boff; pitch = L.pitch; }
+    else if (level == 0) { src = ctx->p.l0 + (size_t)frame * ctx->p.l0Frame; pitch = (size_t)ctx->p.l0Pitch; }
+    else { src = ctx->p.pyr + (size_t)frame * ctx->g.pyrFrameBytes + L.off; pitch = L.pitch; }
+    CK(cudaMemcpy2DAsync(dst, dst_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NAV24_OK;
+}
+
+int nav24_orb_get_raw_keys(nav24_orb* ctx, int frame, int level, float* xyr, int cap) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
+        return ctx->fail(NAV24_E_BADARG, "bad frame/level");
+    cudaSetDevice(ctx->device);
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->p.rawTotal + frame * ctx->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!xyr || n == 0) return n;
+    std::vector<RawRec> r(n);
+    CK(cudaMemcpyAsync(r.data(), ctx->p.keys + (size_t)frame * ctx->g.rawPerFrame + ctx->g.lv[level].rawOff, n * sizeof(RawRec),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n && i < cap; ++i) { xyr[3 * i] = r[i].x; xyr[3 * i + 1] = r[i].y; xyr[3 * i + 2] = r[i].score; }
+    return n;
+}
+
+int nav24_orb_get_level_keypoints(nav24_orb* ctx, int frame, int level, nav24_kp* kps, int cap) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
+        return ctx->fail(NAV24_E_BADARG, "bad frame/level");
+    cudaSetDevice(ctx->device);
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->p.levelCount + frame * ctx->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!kps || n == 0) return n;
+    std::vector<LevelKp> r(n);
+    const LevelGeom& L = ctx->g.lv[level];
+    CK(cudaMemcpyAsync(r.data(), ctx->p.lkp + (size_t)frame * ctx->g.kpPerFrame + L.kpOff, n * sizeof(LevelKp),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n && i < cap; ++i) {
+        kps[i].x = r[i].x; kps[i].y = r[i].y; kps[i].size = L.patch; kps[i].angle = r[i].angle;
+        kps[i].response = r[i].score; kps[i].octave = level; kps[i].class_id = -1;
+    }
+    return n;
+}
+
+int nav24_orb_stage_ms(nav24_orb* ctx, float* ms5) {
+    if (!ctx || !ms5) return NAV24_E_BADARG;
+    if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect call yet");
+    cudaSetDevice(ctx->device);
+    CK(cudaEventSynchronize(ctx->ev[4]));
+    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms5[i], ctx->ev[i], ctx->ev[i + 1]));
+    CK(cudaEventElapsedTime(&ms5[4], ctx->ev[0], ctx->ev[4]));
+    return NAV24_OK;
+}
+
+long long nav24_orb_launch_count(const nav24_orb* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// ---- matchers ---------------------------------------------------------------------------------
+namespace {
+
+int ensure_match_scratch(nav24_orb* ctx, int P, int cap, const nav24_grid_cfg* grid) {
+    const size_t nCells = (size_t)grid->cols * grid->rows;
+    const size_t pc = (size_t)P * cap;
+    CK(ctx->mCellOf.ensure(pc * 4));
+    CK(ctx->mCellStart.ensure((size_t)P * (nCells + 1) * 4));
+    CK(ctx->mCellFill.ensure((size_t)P * nCells * 4));
+    CK(ctx->mCellItems.ensure(pc * 4));
+    CK(ctx->mCand.ensure(pc * 32 * 4));
+    CK(ctx->mCandCnt.ensure(pc * 4));
+    CK(ctx->mDist2.ensure(pc * 4));
+    CK(ctx->mM21.ensure(pc * 4));
+    CK(ctx->mBins.ensure(pc * 4));
+    CK(ctx->mMatches.ensure(pc * 4));
+    CK(ctx->mNMatches.ensure((size_t)P * 4));
+    return NAV24_OK;
+}
+
+void fill_match_args(nav24_orb* ctx, MatchArgs& a, const nav24_grid_cfg* grid, float window, float nnratio, int th_low,
+                     int check_ori, int cap) {
+    a.grid = *grid;
+    a.invW = (float)grid->cols / (grid->max_x - grid->min_x);      // FeatureGrid.cpp:110-111
+    a.invH = (float)grid->rows / (grid->max_y - grid->min_y);
+    a.window = window; a.nnratio = nnratio; a.thLow = th_low; a.checkOri = check_ori; a.cap = cap;
+    a.cellOf = (int*)ctx->mCellOf.ptr; a.cellStart = (int*)ctx->mCellStart.ptr; a.cellFill = (int*)ctx->mCellFill.ptr;
+    a.cellItems = (int*)ctx->mCellItems.ptr; a.cand = (int*)ctx->mCand.ptr; a.candCnt = (int*)ctx->mCandCnt.ptr; a.candCap = 32;
+    a.dist2 = (int*)ctx->mDist2.ptr; a.m21 = (int*)ctx->mM21.ptr; a.bins = (int*)ctx->mBins.ptr;
+    a.matches12 = (int*)ctx->mMatches.ptr; a.nMatches = (int*)ctx->mNMatches.ptr;
+}
+
+bool grid_ok(const nav24_grid_cfg* g) {
+    return g && g->cols > 0 && g->rows > 0 && g->max_x > g->min_x && g->max_y > g->min_y;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nav24_match_window_batch(nav24_orb* ctx, int P, int cap, const nav24_kp* k1, const float* ud1, const uint8_t* d1,
+                             const int* n1, const nav24_kp* k2, const float* ud2, const uint8_t* d2, const int* n2,
+                             const nav24_grid_cfg* grid, float window, float nnratio, int th_low, int check_ori,
+                             int32_t* matches12, int* n_matches) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (P <= 0 || cap <= 0 || !k1 || !k2 || !ud1 || !ud2 || !d1 || !d2 || !n1 || !n2 || !matches12 || !grid_ok(grid))
+        return ctx->fail(NAV24_E_BADARG, "bad matcher argument");
+    for (int p = 0; p < P; ++p)
+        if (n1[p] < 0 || n1[p] > cap || n2[p] < 0 || n2[p] > cap) return ctx->fail(NAV24_E_BADARG, "n1/n2 exceed cap");
+    cudaSetDevice(ctx->device);
+    int rc = ensure_match_scratch(ctx, P, cap, grid);
+    if (rc != NAV24_OK) return rc;
+    const size_t pc = (size_t)P * cap;
+    CK(ctx->mK1.ensure(pc * sizeof(nav24_kp))); CK(ctx->mK2.ensure(pc * sizeof(nav24_kp)));
+    CK(ctx->mU1.ensure(pc * 8)); CK(ctx->mU2.ensure(pc * 8));
+    CK(ctx->mD1.ensure(pc * 32)); CK(ctx->mD2.ensure(pc * 32));
+    CK(ctx->mN1.ensure((size_t)P * 4)); CK(ctx->mN2.ensure((size_t)P * 4));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->mK1.ptr, k1, pc * sizeof(nav24_kp), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->mK2.ptr, k2, pc * sizeof(nav24_kp), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->mU1.ptr, ud1, pc * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->mU2.ptr, ud2, pc * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->mD1.ptr, d1, pc * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->mD2.ptr, d2, pc * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->mN1.ptr, n1, (size_t)P * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->mN2.ptr, n2, (size_t)P * 4, cudaMemcpyHostToDevice, s));
+    MatchArgs a{};
+    fill_match_args(ctx, a, grid, window, nnratio, th_low, check_ori, cap);
+    a.k1 = (const nav24_kp*)ctx->mK1.ptr; a.k2 = (const nav24_kp*)ctx->mK2.ptr;
+    a.ud1 = (const float*)ctx->mU1.ptr; a.ud2 = (const float*)ctx->mU2.ptr;
+    a.d1 = (const uint8_t*)ctx->mD1.ptr; a.d2 = (const uint8_t*)ctx->mD2.ptr;
+    a.n1 = (const int*)ctx->mN1.ptr; a.n2 = (const int*)ctx->mN2.ptr;
+    a.stride1 = cap; a.stride2 = cap; a.pairs = nullptr;
+    ctx->launches += launch_match_window(a, P, s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(matches12, a.matches12, pc * 4, cudaMemcpyDeviceToHost, s));
+    std::vector<int> nm(P);
+    CK(cudaMemcpyAsync(nm.data(), a.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int total = 0;
+    for (int p = 0; p < P; ++p) { if (n_matches) n_matches[p] = nm[p]; total += nm[p]; }
+    return total;
+}
+
+int nav24_match_window(nav24_orb* ctx, const nav24_kp* k1, const float* ud1, const uint8_t* d1, int n1, const nav24_kp* k2,
+                       const float* ud2, const uint8_t* d2, int n2, const nav24_grid_cfg* grid, float window, float nnratio,
+                       int th_low, int check_ori, int32_t* matches12) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (n1 < 0 || n2 < 0) return ctx->fail(NAV24_E_BADARG, "negative count");
+    if (n1 == 0) return 0;
+    const int cap = std::max(std::max(n1, n2), 1);
+    // pad both sides to a common capacity so that the batched entry point can be reused
+    std::vector<nav24_kp> K1(cap), K2(cap);
+    std::vector<float> U1(2 * (size_t)cap), U2(2 * (size_t)cap);
+    std::vector<uint8_t> D1(32 * (size_t)cap), D2(32 * (size_t)cap);
+    std::vector<int32_t> M(cap, -1);
+    if (!k1 || !ud1 || !d1 || !matches12 || (n2 > 0 && (!k2 || !ud2 || !d2))) return ctx->fail(NAV24_E_BADARG, "null pointer");
+    memcpy(K1.data(), k1, (size_t)n1 * sizeof(nav24_kp)); memcpy(U1.data(), ud1, (size_t)n1 * 8); memcpy(D1.data(), d1, (size_t)n1 * 32);
+    if (n2) { memcpy(K2.data(), k2, (size_t)n2 * sizeof(nav24_kp)); memcpy(U2.data(), ud2, (size_t)n2 * 8); memcpy(D2.data(), d2, (size_t)n2 * 32); }
+    int nm = 0;
+    int rc = nav24_match_window_batch(ctx, 1, cap, K1.data(), U1.data(), D1.data(), &n1, K2.data(), U2.data(), D2.data(), &n2,
+                                      grid, window, nnratio, th_low, check_ori, M.data(), &nm);
+    if (rc < 0) return rc;
+    memcpy(matches12, M.data(), (size_t)n1 * 4);
+    return nm;
+}
+
+int nav24_match_window_frames(nav24_orb* ctx, int P, const int* pairs_ab, const nav24_grid_cfg* grid, float window,
+                              float nnratio, int th_low, int check_ori, int32_t* matches12, int cap, int* n_matches) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results on the device");
+    if (P <= 0 || !pairs_ab || !grid_ok(grid)) return ctx->fail(NAV24_E_BADARG, "bad matcher argument");
+    const int oc = ctx->g.outCap;
+    if (matches12 && cap < oc) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
+    for (int p = 0; p < 2 * P; ++p)
+        if (pairs_ab[p] < 0 || pairs_ab[p] >= ctx->lastB) return ctx->fail(NAV24_E_BADARG, "frame index out of range");
+    cudaSetDevice(ctx->device);
+    int rc = ensure_match_scratch(ctx, P, oc, grid);
+    if (rc != NAV24_OK) return rc;
+    CK(ctx->mPairs.ensure((size_t)P * 8));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->mPairs.ptr, pairs_ab, (size_t)P * 8, cudaMemcpyHostToDevice, s));
+    MatchArgs a{};
+    fill_match_args(ctx, a, grid, window, nnratio, th_low, check_ori, oc);
+    a.k1 = a.k2 = ctx->p.outKp; a.ud1 = a.ud2 = nullptr; a.d1 = a.d2 = ctx->p.outDesc;
+    a.n1 = a.n2 = ctx->p.nOut; a.stride1 = a.stride2 = oc; a.pairs = (const int*)ctx->mPairs.ptr;
+    ctx->launches += launch_match_window(a, P, s);
+    CK(cudaGetLastError());
+    if (matches12)
+        CK(cudaMemcpy2DAsync(matches12, (size_t)cap * 4, a.matches12, (size_t)oc * 4, (size_t)oc * 4, P, cudaMemcpyDeviceToHost, s));
+    std::vector<int> nm(P);
+    CK(cudaMemcpyAsync(nm.data(), a.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int total = 0;
+    for (int p = 0; p < P; ++p) { if (n_matches) n_matches[p] = nm[p]; total += nm[p]; }
+    return total;
+}
+
+int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio,
+                        int32_t* idx0, int32_t* idx1, float* dist0, float* dist1, uint8_t* pass) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (n1 < 0 || n2 < 0 || (norm != NAV24_NORM_HAMMING && norm != NAV24_NORM_L2_U8)) return ctx->fail(NAV24_E_BADARG, "bad argument");
+    if (n1 == 0) return 0;
+    if (!d1 || (n2 > 0 && !d2) || !idx0 || !idx1 || !dist0 || !dist1 || !pass) return ctx->fail(NAV24_E_BADARG, "null pointer");
+    cudaSetDevice(ctx->device);
+    CK(ctx->mD1.ensure((size_t)n1 * 32)); CK(ctx->mD2.ensure((size_t)std::max(n2, 1) * 32));
+    CK(ctx->mI0.ensure((size_t)n1 * 4)); CK(ctx->mI1.ensure((size_t)n1 * 4));
+    CK(ctx->mF0.ensure((size_t)n1 * 4)); CK(ctx->mF1.ensure((size_t)n1 * 4)); CK(ctx->mPass.ensure((size_t)n1));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->mD1.ptr, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    if (n2) CK(cudaMemcpyAsync(ctx->mD2.ptr, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    ctx->launches += launch_bf_knn2((const uint8_t*)ctx->mD1.ptr, n1, (const uint8_t*)ctx->mD2.ptr, n2, norm, ratio,
+                                    (int*)ctx->mI0.ptr, (int*)ctx->mI1.ptr, (float*)ctx->mF0.ptr, (float*)ctx->mF1.ptr,
+                                    (uint8_t*)ctx->mPass.ptr, s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(idx0, ctx->mI0.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(idx1, ctx->mI1.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(dist0, ctx->mF0.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(dist1, ctx->mF1.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(pass, ctx->mPass.ptr, (size_t)n1, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int np = 0;
+    for (int i = 0; i < n1; ++i) np += pass[i];
+    return np;
+}
+
+int nav24_host_alloc(size_t bytes, void** out) {
+    if (!out) return NAV24_E_BADARG;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? NAV24_OK : NAV24_E_NOMEM;
+}
+int nav24_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? NAV24_OK : NAV24_E_CUDA; }
+int nav24_device_alloc(size_t bytes, void** out) {
+    if (!out) return NAV24_E_BADARG;
+    return cudaMalloc(out, bytes) == cudaSuccess ? NAV24_OK : NAV24_E_NOMEM;
+}
+int nav24_device_free(void* p) { return cudaFree(p) == cudaSuccess ? NAV24_OK : NAV24_E_CUDA; }
+int nav24_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? NAV24_OK : NAV24_E_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// match_kernels.cu — sm_100a kernels of the descriptor matchers (integer popc / warp-min; no
+// tensor cores: Hamming matching is not a dense floating-point contraction).
+//   window matcher  : FtAssocOrbSlam::matchV  core/operators/objAssoc/OP_FtAssocOrbSlam.cpp:91-223
+//                     + FeatureGrid           core/sensorData/observation/FeatureGrid.cpp:20-152
+//   brute force     : intended semantics of FtAssocOCV::match  core/operators/objAssoc/OP_FtAssoc.cpp:63-99
+#include "orb_internal.cuh"
+
+namespace nav24 {
+namespace {
+
+constexpr int kCandCap = 32;       // pruned candidates kept per query (one warp round); more -> exact slow path
+constexpr int kHisto = 30;         // HISTO_LENGTH (:15)
+
+__device__ __forceinline__ int block_excl_scan_m(int v, int* total, int* s_warp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < nw) s_warp[lane] = wi - w;
+        if (lane == nw - 1) s_warp[32] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[wid] + incl - v;
+}
+
+__device__ __forceinline__ int hamming256(const uint4* a, const uint4* b) {
+    const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+struct PairView {
+    const nav24_kp* k1; const float* ud1; const uint4* d1; int n1;
+    const nav24_kp* k2; const float* ud2; const uint4* d2; int n2;
+};
+
+__device__ __forceinline__ float2 ud_of(const nav24_kp* k, const float* ud, int i) {
+    return ud ? make_float2(ud[2 * i], ud[2 * i + 1]) : make_float2(k[i].x, k[i].y);
+}
+
+// Candidate cell range of FeatureGrid::getFeaturesInArea (FeatureGrid.cpp:38-60). false = empty.
+__device__ __forceinline__ bool cell_range(const MatchArgs& a, float x, float y, int& cx0, int& cx1, int& cy0, int& cy1) {
+    const float r = a.window;
+    cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, a.grid.min_x), r), a.invW)));
+    if (cx0 >= a.grid.cols) return false;
+    cx1 = min(a.grid.cols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.grid.min_x), r), a.invW)));
+    if (cx1 < 0) return false;
+    cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.grid.min_y), r), a.invH)));
+    if (cy0 >= a.grid.rows) return false;
+    cy1 = min(a.grid.rows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.grid.min_y), r), a.invH)));
+    if (cy1 < 0) return false;
+    return true;
+}
+
+// One CTA per frame pair.
+__global__ void __launch_bounds__(256) match_window_kernel(const MatchArgs a) {
+    __shared__ int s_scan[33];
+    __shared__ int s_hist[kHisto];
+    __shared__ int s_ind[3];
+    __shared__ int s_nm;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
+    const int pr = blockIdx.x;
+    PairView v;
+    {
+        long long o1, o2;
+        if (a.pairs) { o1 = (long long)a.pairs[2 * pr] * a.stride1; o2 = (long long)a.pairs[2 * pr + 1] * a.stride2; }
+        else { o1 = (long long)pr * a.stride1; o2 = (long long)pr * a.stride2; }
+        v.k1 = a.k1 + o1; v.k2 = a.k2 + o2;
+        v.ud1 = a.ud1 ? a.ud1 + 2 * o1 : nullptr; v.ud2 = a.ud2 ? a.ud2 + 2 * o2 : nullptr;
+        v.d1 = reinterpret_cast<const uint4*>(a.d1 + 32 * o1); v.d2 = reinterpret_cast<const uint4*>(a.d2 + 32 * o2);
+        v.n1 = a.pairs ? a.n1[a.pairs[2 * pr]] : a.n1[pr];
+        v.n2 = a.pairs ? a.n2[a.pairs[2 * pr + 1]] : a.n2[pr];
+    }
+    const int nCells = a.grid.cols * a.grid.rows;
+    int* cellOf = a.cellOf + (long long)pr * a.cap;
+    int* cellStart = a.cellStart + (long long)pr * (nCells + 1);
+    int* cellFill = a.cellFill + (long long)pr * nCells;
+    int* items = a.cellItems + (long long)pr * a.cap;
+    int* cand = a.cand + (long long)pr * a.cap * kCandCap;
+    int* candCnt = a.candCnt + (long long)pr * a.cap;
+    int* dist2 = a.dist2 + (long long)pr * a.cap;
+    int* m21 = a.m21 + (long long)pr * a.cap;
+    int* bins = a.bins + (long long)pr * a.cap;
+    int* m12 = a.matches12 + (long long)pr * a.cap;
+
+    // ---- FeatureGrid::assignFeaturesToGrid (:115-152) as CSR, cell id = ix*rows + iy ------------------
+    for (int c = tid; c < nCells; c += nth) cellFill[c] = 0;
+    for (int j = tid; j < v.n2; j += nth) { dist2[j] = 0x7fffffff; m21[j] = -1; }
+    for (int i = tid; i < v.n1; i += nth) { m12[i] = -1; bins[i] = -1; candCnt[i] = 0; }
+    if (tid < kHisto) s_hist[tid] = 0;
+    __syncthreads();
+    for (int j = tid; j < v.n2; j += nth) {
+        const float2 pt = ud_of(v.k2, v.ud2, j);
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(pt.x, a.grid.min_x), a.invW));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(pt.y, a.grid.min_y), a.invH));
+        int c = -1;
+        if (!(px < 0 || px >= a.grid.cols || py < 0 || py >= a.grid.rows)) { c = px * a.grid.rows + py; atomicAdd(&cellFill[c], 1); }
+        cellOf[j] = c;
+    }
+    __syncthreads();
+    int run = 0;
+    for (int base = 0; base < nCells; base += nth) {
+        const int c = base + tid;
+        const int cnt = c < nCells ? cellFill[c] : 0;
+        int tot;
+        const int ex = block_excl_scan_m(cnt, &tot, s_scan);
+        if (c < nCells) cellStart[c] = run + ex;
+        run += tot;
+    }
+    if (tid == 0) cellStart[nCells] = run;
+    __syncthreads();
+    for (int c = tid; c < nCells; c += nth) cellFill[c] = 0;
+    __syncthreads();
+    for (int j = tid; j < v.n2; j += nth) {
+        const int c = cellOf[j];
+        if (c >= 0) items[cellStart[c] + atomicAdd(&cellFill[c], 1)] = j;
+    }
+    __syncthreads();
+    for (int c = tid; c < nCells; c += nth) {           // insertion order inside a cell = index order
+        const int s = cellStart[c], e = cellStart[c + 1];
+        for (int i = s + 1; i < e; ++i) {
+            const int val = items[i];
+            int k = i - 1;
+            while (k >= s && items[k] > val) { items[k + 1] = items[k]; --k; }
+            items[k + 1] = val;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase A: per query, pruned candidate list in the grid's iteration order ------------------------
+    // A candidate whose distance can neither be an accepted best (dist > TH_LOW) nor fail the ratio
+    // test as second best ((float)dist*ratio > TH_LOW >= best) is equivalent to "no candidate".
+    const float thLowF = (float)a.thLow;
+    for (int i1 = wid; i1 < v.n1; i1 += nw) {
+        if (v.k1[i1].octave > 0) continue;                       // :120-122
+        const int level1 = v.k1[i1].octave;
+        const float2 q = ud_of(v.k1, v.ud1, i1);
+        int cx0, cx1, cy0, cy1;
+        if (!cell_range(a, q.x, q.y, cx0, cx1, cy0, cy1)) continue;
+        const uint4* dq = v.d1 + 2 * i1;
+        int cnt = 0;
+        for (int ix = cx0; ix <= cx1; ++ix) {
+            const int s = cellStart[ix * a.grid.rows + cy0], e = cellStart[ix * a.grid.rows + cy1 + 1];
+            for (int b = s; b < e; b += 32) {
+                const int idx = b + lane;
+                bool keep = false;
+                int packed = 0;
+                if (idx < e) {
+                    const int j = items[idx];
+                    const int oc = v.k2[j].octave;
+                    if (oc >= level1 && oc <= level1) {          // minLevel = maxLevel = level1 (:124)
+                        const float2 pt = ud_of(v.k2, v.ud2, j);
+                        if (fabsf(__fsub_rn(pt.x, q.x)) < a.window && fabsf(__fsub_rn(pt.y, q.y)) < a.window) {
+                            const int d = hamming256(dq, v.d2 + 2 * j);
+                            const bool prune = d > a.thLow && __fmul_rn((float)d, a.nnratio) > thLowF;
+                            keep = !prune;
+                            packed = (j << 9) | d;
+                        }
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < kCandCap) cand[(long long)i1 * kCandCap + pos] = packed;
+                }
+                cnt += __popc(bal);
+            }
+        }
+        if (lane == 0) candCnt[i1] = cnt;
+    }
+    __syncthreads();
+
+    // ---- phase B: the sequential accept / steal scan over i1 (:114-187), one warp ------------------------
+    if (wid == 0) {
+        for (int i1 = 0; i1 < v.n1; ++i1) {
+            const int cnt = candCnt[i1];
+            if (cnt == 0) continue;
+            int best = 0x7fffffff, best2 = 0x7fffffff, bestIdx = -1;
+            if (cnt <= kCandCap) {
+                int d = 0x7fffffff, j = -1;
+                if (lane < cnt) {
+                    const int pk = cand[(long long)i1 * kCandCap + lane];
+                    j = pk >> 9;
+                    const int dd = pk & 511;
+                    if (!(dist2[j] <= dd)) d = dd;               // :146
+                }
+                // first minimum in list order, then the second smallest of the multiset
+                int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
+                int kmin = key;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                if (kmin != 0x7fffffff) {
+                    const int bl = kmin & 31;
+                    best = kmin >> 5;
+                    bestIdx = __shfl_sync(0xffffffffu, j, bl);
+                    int d2 = (lane == bl) ? 0x7fffffff : d;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) d2 = min(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+                    best2 = d2;
+                }
+            } else {
+                // exact slow path: re-enumerate every candidate of this query in order
+                const int level1 = v.k1[i1].octave;
+                const float2 q = ud_of(v.k1, v.ud1, i1);
+                int cx0, cx1, cy0, cy1;
+                cell_range(a, q.x, q.y, cx0, cx1, cy0, cy1);
+                const uint4* dq = v.d1 + 2 * i1;
+                for (int ix = cx0; ix <= cx1; ++ix) {
+                    const int s = cellStart[ix * a.grid.rows + cy0], e = cellStart[ix * a.grid.rows + cy1 + 1];
+                    for (int b = s; b < e; b += 32) {
+                        const int idx = b + lane;
+                        int d = 0x7fffffff, j = -1;
+                        if (idx < e) {
+                            j = items[idx];
+                            const int oc = v.k2[j].octave;
+                            if (oc >= level1 && oc <= level1) {
+                                const float2 pt = ud_of(v.k2, v.ud2, j);
+                                if (fabsf(__fsub_rn(pt.x, q.x)) < a.window && fabsf(__fsub_rn(pt.y, q.y)) < a.window) {
+                                    const int dd = hamming256(dq, v.d2 + 2 * j);
+                                    if (!(dist2[j] <= dd)) d = dd;
+                                }
+                            }
+                        }
+                        int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
+                        int kmin = key;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                        if (kmin == 0x7fffffff) continue;
+                        const int bl = kmin & 31, cb = kmin >> 5;
+                        const int cj = __shfl_sync(0xffffffffu, j, bl);
+                        int d2 = (lane == bl) ? 0x7fffffff : d;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) d2 = min(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+                        if (cb < best) { best2 = min(best, d2); best = cb; bestIdx = cj; }
+                        else best2 = min(best2, cb);
+                    }
+                }
+            }
+            if (best <= a.thLow && (float)best < __fmul_rn((float)best2, a.nnratio)) {      // :161-163
+                if (lane == 0) {
+                    const int prev = m21[bestIdx];
+                    if (prev >= 0) m12[prev] = -1;
+                    m12[i1] = bestIdx;
+                    m21[bestIdx] = i1;
+                    dist2[bestIdx] = best;
+                    if (a.checkOri) {
+                        float rot = __fsub_rn(v.k1[i1].angle, v.k2[bestIdx].angle);
+                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                        int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHisto));
+                        if (bin == kHisto) bin = 0;
+                        if (bin >= 0 && bin < kHisto) { bins[i1] = bin; s_hist[bin] += 1; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ComputeThreeMaxima (:28-69)
+        if (lane == 0) {
+            int i1 = -1, i2 = -1, i3 = -1;
+            if (a.checkOri) {
+                int m1 = 0, m2 = 0, m3 = 0;
+                for (int i = 0; i < kHisto; ++i) {
+                    const int s = s_hist[i];
+                    if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+                    else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+                    else if (s > m3) { m3 = s; i3 = i; }
+                }
+                if ((float)m2 < __fmul_rn(0.1f, (float)m1)) { i2 = -1; i3 = -1; }
+                else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
+            }
+            s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3;
+            s_nm = 0;
+        }
+    }
+    __syncthreads();
+    int nm = 0;
+    for (int i = tid; i < v.n1; i += nth) {
+        int m = m12[i];
+        if (a.checkOri && m >= 0) {
+            const int b = bins[i];
+            if (b >= 0 && b != s_ind[0] && b != s_ind[1] && b != s_ind[2]) { m = -1; m12[i] = -1; }
+        }
+        nm += m >= 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, o);
+    if (lane == 0 && nm) atomicAdd(&s_nm, nm);
+    __syncthreads();
+    if (tid == 0) a.nMatches[pr] = s_nm;
+}
+
+// ------------------------------------------------------------------------------------------
+// brute-force kNN-2: one thread per query, train descriptors staged through shared memory in
+// tiles (every thread reads the same address -> broadcast).  Strict '<' keeps the lowest train
+// index on ties, like cv::BFMatcher.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bf_knn2_kernel(const uint4* __restrict__ d1, int n1, const uint4* __restrict__ d2,
+                                                      int n2, int norm, float ratio, int* idx0, int* idx1, float* dist0,
+                                                      float* dist1, uint8_t* pass) {
+    __shared__ uint4 s_t[128 * 2];
+    const int q = blockIdx.x * 128 + threadIdx.x;
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (q < n1) { qa = d1[2 * q]; qb = d1[2 * q + 1]; }
+    int b0 = 0x7fffffff, b1 = 0x7fffffff, j0 = -1, j1 = -1;
+    for (int base = 0; base < n2; base += 128) {
+        const int nt = min(128, n2 - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nt * 2; k += 128) s_t[k] = d2[2 * base + k];
+        __syncthreads();
+        for (int t = 0; t < nt; ++t) {
+            const uint4 ta = s_t[2 * t], tb = s_t[2 * t + 1];
+            int d;
+            if (norm == NAV24_NORM_HAMMING) {
+                d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                    __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            } else {
+                unsigned acc = 0, df;
+                df = __vabsdiffu4(qa.x, ta.x); acc = __dp4a(df, df, acc);
+                df = __vabsdiffu4(qa.y, ta.y); acc = __dp4a(df, df, acc);
+                df = __vabsdiffu4(qa.z, ta.z); acc = __dp4a(df, df, acc);
+                df = __vabsdiffu4(qa.w, ta.w); acc = __dp4a(df, df, acc);
+                df = __vabsdiffu4(qb.x, tb.x); acc = __dp4a(df, df, acc);
+                df = __vabsdiffu4(qb.y, tb.y); acc = __dp4a(df, df, acc);
+                df = __vabsdiffu4(qb.z, tb.z); acc = __dp4a(df, df, acc);
+                df = __vabsdiffu4(qb.w, tb.w); acc = __dp4a(df, df, acc);
+                d = (int)acc;
+            }
+            const int j = base + t;
+            if (d < b0) { b1 = b0; j1 = j0; b0 = d; j0 = j; }
+            else if (d < b1) { b1 = d; j1 = j; }
+        }
+    }
+    if (q < n1) {
+        idx0[q] = j0; idx1[q] = j1;
+        const float f0 = j0 < 0 ? 0.f : (norm == NAV24_NORM_HAMMING ? (float)b0 : __fsqrt_rn((float)b0));
+        const float f1 = j1 < 0 ? 0.f : (norm == NAV24_NORM_HAMMING ? (float)b1 : __fsqrt_rn((float)b1));
+        dist0[q] = f0; dist1[q] = f1;
+        pass[q] = (j0 >= 0 && j1 >= 0 && f0 < __fmul_rn(ratio, f1)) ? 1 : 0;
+    }
+}
+
+}  // namespace
+
+int launch_match_window(const MatchArgs& a, int P, cudaStream_t s) {
+    match_window_kernel<<<P, 256, 0, s>>>(a);
+    return 1;
+}
+
+int launch_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio, int* idx0, int* idx1,
+                   float* dist0, float* dist1, uint8_t* pass, cudaStream_t s) {
+    bf_knn2_kernel<<<(n1 + 127) / 128, 128, 0, s>>>(reinterpret_cast<const uint4*>(d1), n1, reinterpret_cast<const uint4*>(d2),
+                                                    n2, norm, ratio, idx0, idx1, dist0, dist1, pass);
+    return 1;
+}
+
+}  // namespace nav24

@@ -1,0 +1,124 @@
+// orb_internal.cuh — shared device-side layout of the B200 ORB front end (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nav24_orb.h"
+
+namespace nav24 {
+
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 19;           // EDGE_THRESHOLD (OP_FtDtOrbSlam.cpp:14)
+constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
+constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
+constexpr int kCellTilePitch = 80;
+
+// device error bits (ctx->d_err)
+enum : int { ERR_RAW_OVERFLOW = 1, ERR_ROOT_RANGE = 2, ERR_NODE_OVERFLOW = 4, ERR_CELL_SIZE = 8, ERR_KP_OVERFLOW = 16 };
+
+struct LevelGeom {
+    int w, h;
+    int pitch;               // row pitch in bytes of the level inside the pyramid / blurred buffers
+    long long off;           // byte offset of the level inside one frame's pyramid slab (level 0: unused)
+    long long boff;          // byte offset inside one frame's blurred slab
+    // FAST cell grid (OP_FtDtOrbSlam.cpp:735-768)
+    int nCols, nRows, wCell, hCell, maxBX, maxBY;
+    int cellBase;            // first cell id of this level inside the per-frame cell table
+    int rawCap;              // raw-corner capacity of this level (records)
+    int rawOff;              // record offset of the level inside one frame's raw slab
+    // quadtree (:502-725)
+    int quota;               // mnFeaturesPerLevel[level]
+    int nIni;                // number of root nodes
+    float hX;                // root width
+    int nodeCap;             // node capacity
+    int nodeOff;             // offset (in nodes) inside one frame's node slabs
+    int kpOff;               // offset of the level inside one frame's level-keypoint slab
+    int kpCap;               // quota + 3 ... (max(4*nIni, quota+3)+4 == nodeCap)
+    float scale;             // mvScaleFactor[level]
+    float patch;             // float(int(31*scale))
+};
+
+struct FrameGeom {
+    int nlevels;
+    int totalCells;
+    int rawPerFrame;         // records
+    int nodesPerFrame;
+    int kpPerFrame;          // level-keypoint slab size (sum of kpCap)
+    int outCap;              // output capacity per frame
+    long long pyrFrameBytes, blurFrameBytes;
+    LevelGeom lv[kMaxLevels];
+};
+
+struct RawRec {              // one FAST survivor, 8 bytes
+    unsigned short x, y;     // relative to (minBorderX, minBorderY)
+    unsigned short score;
+    unsigned short pad;
+};
+
+struct QNode {               // 12 bytes
+    short x0, y0, x1, y1;
+    int count;
+};
+
+struct LevelKp {             // keypoint in level coordinates, quadtree order (16 bytes)
+    unsigned short x, y;     // level pixel coordinates (border added)
+    unsigned short score;
+    unsigned short pad;
+    int dst;                 // index in the frame's final output order
+    float angle;
+};
+
+// all device pointers of one workspace, passed by value to kernels
+struct DevPtrs {
+    const uint8_t* l0; long long l0Pitch, l0Frame;   // level 0 (caller's buffer or staging copy)
+    uint8_t* pyr;            // levels >= 1
+    uint8_t* blur;           // blurred levels
+    uint2* cellInfo;         // [B][totalCells] (offset inside level raw slab, count)
+    int* cellDst;            // [B][totalCells] ordered start offset
+    int* rawCount;           // [B][nlevels] atomic append cursors
+    RawRec* raw;             // [B][rawPerFrame] append order
+    RawRec* keys;            // [B][rawPerFrame] reference order (vToDistributeKeys)
+    int* nodeOfKey;          // [B][rawPerFrame]
+    QNode* nodesA; QNode* nodesB;   // [B][nodesPerFrame]
+    int* childCnt;           // [B][4*nodesPerFrame]
+    int* nodeAux;            // [B][nodesPerFrame]
+    unsigned long long* best;       // [B][nodesPerFrame]
+    unsigned long long* sortRec;    // [B][nodesPerFrame]
+    LevelKp* lkp;            // [B][kpPerFrame]
+    int* levelCount;         // [B][nlevels] keypoints per level after the quadtree
+    int* rawTotal;           // [B][nlevels] raw keys per level
+    nav24_kp* outKp;         // [B][outCap]
+    uint8_t* outDesc;        // [B][outCap][32]
+    int* nOut; int* monoOut; // [B]
+    int* err;                // device error bits
+};
+
+struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
+    const int* xofs; const short2* xab; const int* yofs; const short2* yab;
+};
+
+// launchers (orb_kernels.cu); each returns the number of kernels launched
+int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, int B, cudaStream_t s);
+int launch_fast(const FrameGeom& g, const DevPtrs& p, int B, int iniTh, int minTh, cudaStream_t s);
+int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
+int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
+
+// matchers (match_kernels.cu)
+struct MatchArgs {
+    const nav24_kp* k1; const float* ud1; const uint8_t* d1; const int* n1;   // [P][cap]...
+    const nav24_kp* k2; const float* ud2; const uint8_t* d2; const int* n2;
+    long long stride1, stride2;    // element stride between pairs (keypoints); 0 with index lists
+    const int* pairs;              // optional [P][2] frame indices into k1/k2 (same arrays), else null
+    nav24_grid_cfg grid; float invW, invH;
+    float window, nnratio; int thLow, checkOri;
+    int cap;
+    int* cellOf; int* cellStart; int* cellFill; int* cellItems;  // grid scratch per pair
+    int* cand; int* candCnt; int candCap;                          // pruned candidate lists per query
+    int* dist2; int* m21; int* bins;                               // [P][cap]
+    int* matches12; int* nMatches;
+};
+int launch_match_window(const MatchArgs& a, int P, cudaStream_t s);
+int launch_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio, int* idx0, int* idx1,
+                   float* dist0, float* dist1, uint8_t* pass, cudaStream_t s);
+
+}  // namespace nav24

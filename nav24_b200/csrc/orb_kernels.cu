@@ -1,0 +1,754 @@
+// orb_kernels.cu — sm_100a kernels of the ORB detector (pyramid, FAST cells, quadtree, order,
+// blur, orientation + rBRIEF).  Each kernel cites the reference lines whose results it reproduces
+// (paths relative to /root/reference/core/operators/objDetection/).  Integer work is bit-exact;
+// float work uses explicit round-to-nearest intrinsics so that nvcc cannot contract mul+add
+// into FMA (the reference is built without contraction).
+#include "orb_internal.cuh"
+#include "stdsort.cuh"
+
+namespace nav24 {
+
+namespace {
+
+__device__ const signed char kPattern[1024] = {
+#include "pattern_31.inc"
+};
+
+__device__ __forceinline__ const uint8_t* level_ptr(const FrameGeom& g, const DevPtrs& p, int f, int l) {
+    return l == 0 ? p.l0 + (long long)f * p.l0Frame : p.pyr + (long long)f * g.pyrFrameBytes + g.lv[l].off;
+}
+__device__ __forceinline__ long long level_pitch(const FrameGeom& g, const DevPtrs& p, int l) {
+    return l == 0 ? p.l0Pitch : (long long)g.lv[l].pitch;
+}
+
+// exclusive block scan of one int per thread; returns the exclusive prefix, *total = block sum.
+// All threads of the block must call it. blockDim.x must be a multiple of 32, <= 1024.
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /* >= 33 ints */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();   // protect s_warp from the previous call's readers
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < nw) s_warp[lane] = wi - w;
+        if (lane == nw - 1) s_warp[32] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[wid] + incl - v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1  pyramid level l-1 -> l.  cv::resize(INTER_LINEAR) on CV_8UC1 = 11-bit fixed-point separable
+// bilinear; replaces ComputePyramid (OP_FtDtOrbSlam.cpp:936-960).
+// One thread produces 4 horizontally adjacent destination pixels (one 32-bit store).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_kernel(const uint8_t* __restrict__ src, long long sPitch, long long sFrame,
+                                                     int sw, int sh, uint8_t* __restrict__ dst, int dPitch,
+                                                     long long dFrame, int dw, int dh, ResizeTab t) {
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x4 >= dw || y >= dh) return;
+    const int f = blockIdx.z;
+    const int sy0 = t.yofs[y];
+    const int sy1 = min(sy0 + 1, sh - 1);
+    const short2 b = t.yab[y];
+    const uint8_t* r0 = src + (long long)f * sFrame + (long long)sy0 * sPitch;
+    const uint8_t* r1 = src + (long long)f * sFrame + (long long)sy1 * sPitch;
+    unsigned out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = min(x4 + k, dw - 1);
+        const int s0 = t.xofs[x];
+        const int s1 = min(s0 + 1, sw - 1);
+        const short2 a = t.xab[x];
+        const int h0 = (int)r0[s0] * a.x + (int)r0[s1] * a.y;
+        const int h1 = (int)r1[s0] * a.x + (int)r1[s1] * a.y;
+        const int v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+        out |= (unsigned)(v & 0xff) << (8 * k);
+    }
+    *reinterpret_cast<unsigned*>(dst + (long long)f * dFrame + (long long)y * dPitch + x4) = out;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2  FAST-9/16 per cell with threshold fallback.  One CTA per (cell, frame).
+// Reproduces the cell loop of ComputeKeyPointsOctTree (OP_FtDtOrbSlam.cpp:751-818) and
+// cv::FAST(cell, th, nms=true): the corner score is threshold independent, a
+// keypoint at threshold t is a strict 3x3 local maximum of the score map with score >= t, the
+// detection domain is the cell minus a 3-px rim, and a cell with no survivor at iniThFAST is
+// redone at minThFAST.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fast_score(const uint8_t* c, int pitch) {
+    // packed (d, -d) as s16x2; window-9 minima by doubling; max over the 16 arcs
+    const int cv = c[0];
+    unsigned v[16];
+    const int ofs[16] = {3 * pitch, 3 * pitch + 1, 2 * pitch + 2, pitch + 3, 3, -pitch + 3, -2 * pitch + 2, -3 * pitch + 1,
+                         -3 * pitch, -3 * pitch - 1, -2 * pitch - 2, -pitch - 3, -3, pitch - 3, 2 * pitch - 2, 3 * pitch - 1};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int d = (int)c[ofs[k]] - cv;
+        v[k] = ((unsigned)d & 0xffffu) | ((unsigned)(-d) << 16);
+    }
+    unsigned m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m2[k] = __vmins2(v[k], v[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m8[k] = __vmins2(m4[k], m4[(k + 4) & 15]);
+    unsigned best = __vmins2(m8[0], v[8]);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) best = __vmaxs2(best, __vmins2(m8[k], v[(k + 8) & 15]));
+    const int lo = (int)(short)(best & 0xffffu), hi = (int)(short)(best >> 16);
+    return max(lo, hi) - 1;
+}
+
+__device__ __forceinline__ bool fast_maybe(const uint8_t* c, int pitch, int t) {
+    const int cv = c[0];
+#define NAV24_PAIR(oa)                                                      \
+    {                                                                       \
+        const int a = abs((int)c[(oa)] - cv), b = abs((int)c[-(oa)] - cv);  \
+        if (a <= t && b <= t) return false;                                 \
+    }
+    NAV24_PAIR(3 * pitch)        // ring 0 / 8
+    NAV24_PAIR(3)                // ring 4 / 12
+    NAV24_PAIR(2 * pitch + 2)    // ring 2 / 10
+    NAV24_PAIR(-2 * pitch + 2)   // ring 6 / 14
+    NAV24_PAIR(3 * pitch + 1)    // ring 1 / 9
+    NAV24_PAIR(pitch + 3)        // ring 3 / 11
+    NAV24_PAIR(-pitch + 3)       // ring 5 / 13
+    NAV24_PAIR(-3 * pitch + 1)   // ring 7 / 15
+#undef NAV24_PAIR
+    return true;
+}
+
+__global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+                                                         int iniTh, int minTh) {
+    __shared__ __align__(16) uint8_t tile[kMaxCellTile * kCellTilePitch];
+    __shared__ __align__(16) uint8_t smap[kMaxCellTile * kCellTilePitch];
+    __shared__ int s_cnt[2];
+    __shared__ int s_base;
+    __shared__ int s_wsum[4];
+
+    const int tid = threadIdx.x, f = blockIdx.y, cell = blockIdx.x;
+    int l = 0;
+    while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) ++l;
+    const LevelGeom& L = g.lv[l];
+    const int c = cell - L.cellBase;
+    const int ci = c / L.nCols, cj = c - ci * L.nCols;
+    uint2* info = p.cellInfo + (long long)f * g.totalCells + cell;
+
+    const int iniY = kMinBorder + ci * L.hCell, iniX = kMinBorder + cj * L.wCell;
+    int maxY = iniY + L.hCell + 6, maxX = iniX + L.wCell + 6;
+    const bool skip = (iniY >= L.maxBY - 3) || (iniX >= L.maxBX - 6);      // :756, :765
+    if (maxY > L.maxBY) maxY = L.maxBY;
+    if (maxX > L.maxBX) maxX = L.maxBX;
+    const int cw = maxX - iniX, ch = maxY - iniY;
+    if (skip || cw < 7 || ch < 7) {
+        if (tid == 0) *info = make_uint2(0u, 0u);
+        return;
+    }
+    if (cw > kMaxCellTile || ch > kMaxCellTile) {
+        if (tid == 0) { atomicOr(p.err, ERR_CELL_SIZE); *info = make_uint2(0u, 0u); }
+        return;
+    }
+    const long long pitch = level_pitch(g, p, l);
+    const uint8_t* src = level_ptr(g, p, f, l) + (long long)iniY * pitch + iniX;
+
+    for (int idx = tid; idx < cw * ch; idx += 128) {
+        const int y = idx / cw, x = idx - y * cw;
+        tile[y * kCellTilePitch + x] = src[(long long)y * pitch + x];
+        smap[y * kCellTilePitch + x] = 0;
+    }
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+
+    const int iw = cw - 6, ih = ch - 6, npx = iw * ih;
+    const int lowTh = min(iniTh, minTh);
+    for (int idx = tid; idx < npx; idx += 128) {
+        const int y = idx / iw, x = idx - y * iw;
+        const uint8_t* cpx = tile + (y + 3) * kCellTilePitch + (x + 3);
+        if (fast_maybe(cpx, kCellTilePitch, lowTh)) {
+            const int s = fast_score(cpx, kCellTilePitch);
+            if (s >= lowTh) smap[(y + 3) * kCellTilePitch + (x + 3)] = (uint8_t)s;
+        }
+    }
+    __syncthreads();
+
+    // pass 1: count strict local maxima at both thresholds
+    int n_ini = 0, n_min = 0;
+    for (int idx = tid; idx < npx; idx += 128) {
+        const int y = idx / iw, x = idx - y * iw;
+        const uint8_t* m = smap + (y + 3) * kCellTilePitch + (x + 3);
+        const int s = m[0];
+        if (s == 0) continue;
+        const bool mx = s > m[-1] && s > m[1] && s > m[-kCellTilePitch - 1] && s > m[-kCellTilePitch] &&
+                        s > m[-kCellTilePitch + 1] && s > m[kCellTilePitch - 1] && s > m[kCellTilePitch] &&
+                        s > m[kCellTilePitch + 1];
+        if (mx) { n_ini += (s >= iniTh); n_min += (s >= minTh); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_ini += __shfl_xor_sync(0xffffffffu, n_ini, o);
+        n_min += __shfl_xor_sync(0xffffffffu, n_min, o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_cnt[0], n_ini); atomicAdd(&s_cnt[1], n_min); }
+    __syncthreads();
+    const int th = s_cnt[0] > 0 ? iniTh : minTh;            // :787 "if(vKeysCell.empty())"
+    const int total = s_cnt[0] > 0 ? s_cnt[0] : s_cnt[1];
+    if (tid == 0) {
+        int base = 0;
+        if (total > 0) {
+            base = atomicAdd(p.rawCount + f * g.nlevels + l, total);
+            if (base + total > L.rawCap) { atomicOr(p.err, ERR_RAW_OVERFLOW); base = -1; }
+        }
+        s_base = base;
+        *info = make_uint2((unsigned)max(base, 0), base < 0 ? 0u : (unsigned)total);
+    }
+    __syncthreads();
+    if (total == 0 || s_base < 0) return;
+    RawRec* out = p.raw + (long long)f * g.rawPerFrame + L.rawOff + s_base;
+
+    // pass 2: ordered (row-major) compaction
+    int run = 0;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int base = 0; base < npx; base += 128) {
+        const int idx = base + tid;
+        bool keep = false;
+        int x = 0, y = 0, s = 0;
+        if (idx < npx) {
+            y = idx / iw; x = idx - y * iw;
+            const uint8_t* m = smap + (y + 3) * kCellTilePitch + (x + 3);
+            s = m[0];
+            keep = s >= th && s > m[-1] && s > m[1] && s > m[-kCellTilePitch - 1] && s > m[-kCellTilePitch] &&
+                   s > m[-kCellTilePitch + 1] && s > m[kCellTilePitch - 1] && s > m[kCellTilePitch] &&
+                   s > m[kCellTilePitch + 1];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wsum[wid] = __popc(bal);
+        __syncthreads();
+        int wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { const int v = s_wsum[w]; if (w < wid) wbase += v; tot += v; }
+        if (keep) {
+            RawRec r;
+            r.x = (unsigned short)(x + 3 + cj * L.wCell);     // :811-812, relative to (minBorderX, minBorderY)
+            r.y = (unsigned short)(y + 3 + ci * L.hCell);
+            r.score = (unsigned short)s; r.pad = 0;
+            out[run + wbase + __popc(bal & ((1u << lane) - 1u))] = r;
+        }
+        run += tot;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3  quadtree distribution, one CTA per (level, frame).  Reproduces DistributeOctTree
+// (OP_FtDtOrbSlam.cpp:502-725) including std::list ordering and the unstable std::sort of the
+// "largest first" phase.  The node list is an array in list order; every key carries the index
+// of its node.  One pass = count children (parallel over keys) -> choose the parents to split
+// (all non-leaf nodes, or the sorted order with the size>=N break) -> rebuild the list:
+//   new list = reverse(children in creation order) ++ (old list minus split parents)
+// which is what push_front of each child + erase of the parent produce.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quadrant_of(const QNode& n, int x, int y) {
+    const int mx = n.x0 + ((n.x1 - n.x0 + 1) >> 1);     // UL.x + ceil(w/2)  (:386)
+    const int my = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
+    return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+}
+
+__global__ void __launch_bounds__(256) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+                                                       int sortSmemCap) {
+    extern __shared__ unsigned long long s_sort[];
+    __shared__ int s_scan[33];
+    __shared__ int s_K, s_nexp;
+
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int l = blockIdx.x, f = blockIdx.y;
+    const LevelGeom& L = g.lv[l];
+    const long long fr = (long long)f * g.rawPerFrame + L.rawOff;
+    const long long fn = (long long)f * g.nodesPerFrame + L.nodeOff;
+    const uint2* cinfo = p.cellInfo + (long long)f * g.totalCells + L.cellBase;
+    int* cdst = p.cellDst + (long long)f * g.totalCells + L.cellBase;
+    const RawRec* raw = p.raw + fr;
+    RawRec* keys = p.keys + fr;
+    int* nodeOfKey = p.nodeOfKey + fr;
+    QNode* cur = p.nodesA + fn;
+    QNode* nxt = p.nodesB + fn;
+    int* childCnt = p.childCnt + 4 * fn;
+    int* aux = p.nodeAux + fn;
+    unsigned long long* best = p.best + fn;
+    unsigned long long* sortRec = p.sortRec + fn;
+    LevelKp* lkp = p.lkp + (long long)f * g.kpPerFrame + L.kpOff;
+
+    // (a) bring the per-cell lists into the reference order: cells row-major, row-major inside a cell
+    const int nC = L.nCols * L.nRows;
+    int n = 0;
+    for (int base = 0; base < nC; base += nth) {
+        const int c = base + tid;
+        const int cnt = c < nC ? (int)cinfo[c].y : 0;
+        int tot;
+        const int ex = block_excl_scan(cnt, &tot, s_scan);
+        if (c < nC) cdst[c] = n + ex;
+        n += tot;
+    }
+    __syncthreads();
+    for (int c = tid >> 5; c < nC; c += nth >> 5) {
+        const uint2 ci = cinfo[c];
+        const int d = cdst[c];
+        for (int k = tid & 31; k < (int)ci.y; k += 32) keys[d + k] = raw[ci.x + k];
+    }
+    if (tid == 0) p.rawTotal[f * g.nlevels + l] = n;
+    __syncthreads();
+    if (n == 0) {
+        if (tid == 0) p.levelCount[f * g.nlevels + l] = 0;
+        return;
+    }
+
+    // (b) root nodes (:505-547)
+    const int N = L.quota, nIni = L.nIni;
+    const float hX = L.hX;
+    for (int r = tid; r < nIni; r += nth) childCnt[r] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nth) {
+        int r = (int)__fdiv_rn((float)keys[i].x, hX);
+        if (r >= nIni || r < 0) { atomicOr(p.err, ERR_ROOT_RANGE); r = nIni - 1; }
+        nodeOfKey[i] = r;
+        atomicAdd(&childCnt[r], 1);
+    }
+    __syncthreads();
+    int size = 0;
+    for (int base = 0; base < nIni; base += nth) {
+        const int r = base + tid;
+        const int cnt = r < nIni ? childCnt[r] : 0;
+        int tot;
+        const int ex = block_excl_scan(cnt > 0, &tot, s_scan);
+        if (cnt > 0) {
+            QNode q;
+            q.x0 = (short)(int)__fmul_rn(hX, (float)r);
+            q.x1 = (short)(int)__fmul_rn(hX, (float)(r + 1));
+            q.y0 = 0; q.y1 = (short)(L.maxBY - kMinBorder);
+            q.count = cnt;
+            cur[size + ex] = q;
+        }
+        if (r < nIni) aux[r] = size + ex;
+        size += tot;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nth) nodeOfKey[i] = aux[nodeOfKey[i]];
+    __syncthreads();
+
+    // (c) split passes (:555-700)
+    bool finish = false, phase2 = false;
+    while (!finish) {
+        const int prevSize = size;
+        for (int k = tid; k < 4 * size; k += nth) childCnt[k] = 0;
+        if (tid == 0) { s_nexp = 0; s_K = 0x7fffffff; }
+        __syncthreads();
+        for (int i = tid; i < n; i += nth) {
+            const int nd = nodeOfKey[i];
+            const QNode q = cur[nd];
+            if (q.count > 1) atomicAdd(&childCnt[nd * 4 + quadrant_of(q, keys[i].x, keys[i].y)], 1);
+        }
+        __syncthreads();
+
+        int C = 0, U = 0;
+        if (!phase2) {
+            // every non-leaf node is split, in list order (:568-627)
+            for (int base = 0; base < size; base += nth) {
+                const int nd = base + tid;
+                const bool valid = nd < size;
+                const bool split = valid && cur[nd].count > 1;
+                int ne = 0;
+                if (split) {
+                    const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);
+                    ne = (cc.x > 0) + (cc.y > 0) + (cc.z > 0) + (cc.w > 0);
+                }
+                int totNe, totUn;
+                const int exNe = block_excl_scan(ne, &totNe, s_scan);
+                const int exUn = block_excl_scan(valid && !split, &totUn, s_scan);
+                if (valid) aux[nd] = split ? (C + exNe) : -(U + exUn) - 1;
+                C += totNe; U += totUn;
+            }
+        } else {
+            // "largest first" (:635-700): candidates = non-leaf nodes in creation order (= reverse list
+            // order), std::sort by (count, UL.x), processed from the back until size >= N.
+            int m = 0;
+            for (int base = 0; base < size; base += nth) {
+                const int ridx = base + tid;
+                const int nd = size - 1 - ridx;
+                const bool split = ridx < size && cur[nd].count > 1;
+                int tot;
+                const int ex = block_excl_scan(split, &tot, s_scan);
+                if (split) {
+                    const QNode q = cur[nd];
+                    const unsigned key = (unsigned)q.count * 8192u + (unsigned)q.x0;
+                    const unsigned long long rec = ((unsigned long long)key << 32) | (unsigned)nd;
+                    if (m + ex < sortSmemCap) s_sort[m + ex] = rec; else sortRec[m + ex] = rec;
+                }
+                m += tot;
+            }
+            __syncthreads();
+            unsigned long long* sv = s_sort;
+            if (m > sortSmemCap) {   // does not fit: sort in global memory (slow path, still exact)
+                for (int k = tid; k < min(m, sortSmemCap); k += nth) sortRec[k] = s_sort[k];
+                sv = sortRec;
+                __syncthreads();
+            }
+            if (tid == 0) stdsort::sort(sv, m);
+            __syncthreads();
+            // break point: first processed parent after which size >= N
+            int runD = 0;
+            for (int base = 0; base < m; base += nth) {
+                const int pp = base + tid;
+                int d = 0;
+                if (pp < m) {
+                    const int nd = (int)(sv[m - 1 - pp] & 0xffffffffu);
+                    const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);
+                    d = (cc.x > 0) + (cc.y > 0) + (cc.z > 0) + (cc.w > 0) - 1;
+                }
+                int tot;
+                const int ex = block_excl_scan(d, &tot, s_scan);
+                if (pp < m && size + runD + ex + d >= N) atomicMin(&s_K, pp + 1);
+                runD += tot;
+            }
+            __syncthreads();
+            const int K = min(s_K, m);
+            for (int nd = tid; nd < size; nd += nth) aux[nd] = -0x40000000;   // "not split" marker
+            __syncthreads();
+            for (int base = 0; base < K; base += nth) {
+                const int pp = base + tid;
+                int ne = 0, nd = 0;
+                if (pp < K) {
+                    nd = (int)(sv[m - 1 - pp] & 0xffffffffu);
+                    const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);
+                    ne = (cc.x > 0) + (cc.y > 0) + (cc.z > 0) + (cc.w > 0);
+                }
+                int tot;
+                const int ex = block_excl_scan(ne, &tot, s_scan);
+                if (pp < K) aux[nd] = C + ex;
+                C += tot;
+            }
+            __syncthreads();
+            for (int base = 0; base < size; base += nth) {
+                const int nd = base + tid;
+                const bool un = nd < size && aux[nd] < 0;
+                int tot;
+                const int ex = block_excl_scan(un, &tot, s_scan);
+                if (un) aux[nd] = -(U + ex) - 1;
+                U += tot;
+            }
+        }
+        __syncthreads();
+        if (C + U > L.nodeCap) {     // cannot happen (size <= max(4*nIni, N+3)); fail loudly if it does
+            if (tid == 0) { atomicOr(p.err, ERR_NODE_OVERFLOW); p.levelCount[f * g.nlevels + l] = 0; }
+            return;
+        }
+        // rebuild the list
+        int nexp = 0;
+        for (int nd = tid; nd < size; nd += nth) {
+            const int a = aux[nd];
+            const QNode q = cur[nd];
+            if (a >= 0) {
+                const int mx = q.x0 + ((q.x1 - q.x0 + 1) >> 1), my = q.y0 + ((q.y1 - q.y0 + 1) >> 1);
+                int cidx = a;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cnt = childCnt[nd * 4 + k];
+                    if (cnt > 0) {
+                        QNode ch;
+                        ch.x0 = (k & 1) ? (short)mx : q.x0;  ch.x1 = (k & 1) ? q.x1 : (short)mx;
+                        ch.y0 = (k & 2) ? (short)my : q.y0;  ch.y1 = (k & 2) ? q.y1 : (short)my;
+                        ch.count = cnt;
+                        nxt[C - 1 - cidx] = ch;
+                        ++cidx;
+                        nexp += cnt > 1;
+                    }
+                }
+            } else {
+                nxt[C + (-a - 1)] = q;
+            }
+        }
+        if (nexp) atomicAdd(&s_nexp, nexp);
+        for (int i = tid; i < n; i += nth) {
+            const int nd = nodeOfKey[i];
+            const int a = aux[nd];
+            if (a >= 0) {
+                const int k = quadrant_of(cur[nd], keys[i].x, keys[i].y);
+                int cidx = a;
+                for (int kk = 0; kk < k; ++kk) cidx += childCnt[nd * 4 + kk] > 0;
+                nodeOfKey[i] = C - 1 - cidx;
+            } else {
+                nodeOfKey[i] = C + (-a - 1);
+            }
+        }
+        __syncthreads();
+        { QNode* t = cur; cur = nxt; nxt = t; }
+        size = C + U;
+        if (size >= N || size == prevSize) finish = true;
+        else if (!phase2 && size + 3 * s_nexp > N) phase2 = true;
+        __syncthreads();   // s_nexp is reset at the top of the next pass
+    }
+
+    // (d) best response per node, first key wins ties (:703-722); add the border (:829-836)
+    for (int nd = tid; nd < size; nd += nth) best[nd] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < n; i += nth)
+        atomicMax(&best[nodeOfKey[i]], ((unsigned long long)keys[i].score << 32) | (unsigned)(0xffffffffu - (unsigned)i));
+    __syncthreads();
+    for (int nd = tid; nd < size; nd += nth) {
+        const unsigned i = 0xffffffffu - (unsigned)(best[nd] & 0xffffffffu);
+        const RawRec k = keys[i];
+        LevelKp o;
+        o.x = (unsigned short)(k.x + kMinBorder); o.y = (unsigned short)(k.y + kMinBorder);
+        o.score = k.score; o.pad = 0; o.dst = -1; o.angle = -1.f;
+        lkp[nd] = o;
+    }
+    if (tid == 0) p.levelCount[f * g.nlevels + l] = size;
+}
+
+// ------------------------------------------------------------------------------------------
+// K7  output order.  One CTA per frame.  Reproduces the two-ended placement of detect()
+// (OP_FtDtOrbSlam.cpp:877-921): keypoints with 0 <= x*scale <= 1000 fill the output from the back,
+// the others from the front; monoIndex = number of the latter.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) order_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+    __shared__ int s_scan[33];
+    const int tid = threadIdx.x, f = blockIdx.x;
+    int n = 0;
+    for (int l = 0; l < g.nlevels; ++l) n += p.levelCount[f * g.nlevels + l];
+    int nSt = 0, nMo = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const int cnt = p.levelCount[f * g.nlevels + l];
+        LevelKp* lkp = p.lkp + (long long)f * g.kpPerFrame + g.lv[l].kpOff;
+        const float sc = g.lv[l].scale;
+        for (int base = 0; base < cnt; base += 256) {
+            const int i = base + tid;
+            bool st = false, mo = false;
+            if (i < cnt) {
+                const float x = (float)lkp[i].x;
+                const float xs = l ? __fmul_rn(x, sc) : x;
+                st = xs >= 0.f && xs <= 1000.f;
+                mo = !st;
+            }
+            int tS, tM;
+            const int eS = block_excl_scan(st, &tS, s_scan);
+            const int eM = block_excl_scan(mo, &tM, s_scan);
+            if (i < cnt) lkp[i].dst = st ? n - 1 - (nSt + eS) : nMo + eM;
+            nSt += tS; nMo += tM;
+        }
+    }
+    if (tid == 0) {
+        if (n > g.outCap) { atomicOr(p.err, ERR_KP_OVERFLOW); n = 0; nMo = 0; }
+        p.nOut[f] = n; p.monoOut[f] = nMo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5  7x7 Gaussian blur, sigma 2, BORDER_REFLECT_101: exact integer kernel [18 34 48 56 48 34 18]
+// twice, (v + 32768) >> 16; replaces GaussianBlur at OP_FtDtOrbSlam.cpp:890-891.
+// 64x16 output tile per CTA, horizontal pass into shared memory as u16 (max 255*256 fits).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int v, int n) {
+    if (n == 1) return 0;
+    while (v < 0 || v >= n) v = v < 0 ? -v : 2 * n - 2 - v;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, int l) {
+    __shared__ uint8_t s_src[22][72];
+    __shared__ unsigned short s_h[22][64];
+    const LevelGeom& L = g.lv[l];
+    const int f = blockIdx.z, x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
+    const int tid = threadIdx.x;
+    const long long pitch = level_pitch(g, p, l);
+    const uint8_t* src = level_ptr(g, p, f, l);
+    for (int idx = tid; idx < 22 * 70; idx += 256) {
+        const int yy = idx / 70, xx = idx - yy * 70;
+        const int sy = reflect101(y0 + yy - 3, L.h), sx = reflect101(x0 + xx - 3, L.w);
+        s_src[yy][xx] = src[(long long)sy * pitch + sx];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 22 * 64; idx += 256) {
+        const int yy = idx >> 6, xx = idx & 63;
+        const uint8_t* s = &s_src[yy][xx];
+        s_h[yy][xx] = (unsigned short)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
+    }
+    __syncthreads();
+    uint8_t* dst = p.blur + (long long)f * g.blurFrameBytes + L.boff;
+    for (int idx = tid; idx < 16 * 64; idx += 256) {
+        const int yy = idx >> 6, xx = idx & 63;
+        const int x = x0 + xx, y = y0 + yy;
+        if (x < L.w && y < L.h) {
+            const int v = 18 * (s_h[yy][xx] + s_h[yy + 6][xx]) + 34 * (s_h[yy + 1][xx] + s_h[yy + 5][xx]) +
+                          48 * (s_h[yy + 2][xx] + s_h[yy + 4][xx]) + 56 * s_h[yy + 3][xx];
+            dst[(long long)y * L.pitch + x] = (uint8_t)((v + 32768) >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4+K6  orientation and rBRIEF-256, one warp per keypoint.
+//   IC_Angle (OP_FtDtOrbSlam.cpp:18-44): integer moments over the 31-px disc of the un-blurred level,
+//   angle = cv::fastAtan2 with un-contracted f32 arithmetic.
+//   computeOrbDescriptor (:48-87): 256 rotated pair comparisons on the blurred level; lane i
+//   produces descriptor byte i.  Writes the final nav24_kp (coordinates scaled to level 0, :905-907)
+//   and the descriptor at the keypoint's slot of the two-ended output order.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
+    const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+__global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int f = blockIdx.y;
+    if (slot >= g.kpPerFrame) return;
+    int l = 0;
+    while (l + 1 < g.nlevels && slot >= g.lv[l + 1].kpOff) ++l;
+    const LevelGeom& L = g.lv[l];
+    const int i = slot - L.kpOff;
+    if (i >= p.levelCount[f * g.nlevels + l]) return;
+    LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + slot;
+    const int cx = kp->x, cy = kp->y;
+
+    // orientation on the un-blurred level
+    const long long pitch = level_pitch(g, p, l);
+    const uint8_t* img = level_ptr(g, p, f, l) + (long long)cy * pitch + cx;
+    int m10 = 0, m01 = 0;
+    const int u = lane - 15;
+    if (lane < 31) {
+#pragma unroll 1
+        for (int v = -15; v <= 15; ++v) {
+            if (abs(u) <= c_umax[abs(v)]) {
+                const int val = img[(long long)v * pitch + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // descriptor on the blurred level
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = cosf(ang), b = sinf(ang);
+    const uint8_t* bl = p.blur + (long long)f * g.blurFrameBytes + L.boff + (long long)cy * L.pitch + cx;
+    const signed char* pat = kPattern + lane * 32;
+    unsigned val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = bl[(long long)r0 * L.pitch + q0], t1 = bl[(long long)r1 * L.pitch + q1];
+        val |= (unsigned)(t0 < t1) << j;
+    }
+    const int dst = kp->dst;
+    p.outDesc[((long long)f * g.outCap + dst) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        kp->angle = angle;
+        nav24_kp o;
+        o.x = l ? __fmul_rn((float)cx, L.scale) : (float)cx;
+        o.y = l ? __fmul_rn((float)cy, L.scale) : (float)cy;
+        o.size = L.patch; o.angle = angle; o.response = (float)kp->score; o.octave = l; o.class_id = -1;
+        p.outKp[(long long)f * g.outCap + dst] = o;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, int B, cudaStream_t s) {
+    int n = 0;
+    for (int l = 1; l < g.nlevels; ++l) {
+        const LevelGeom& S = g.lv[l - 1];
+        const LevelGeom& D = g.lv[l];
+        const uint8_t* src = (l == 1) ? p.l0 : p.pyr + S.off;
+        const long long sPitch = (l == 1) ? p.l0Pitch : S.pitch;
+        const long long sFrame = (l == 1) ? p.l0Frame : g.pyrFrameBytes;
+        dim3 grid((D.w + 127) / 128, (D.h + 7) / 8, B), block(32, 8);
+        resize_kernel<<<grid, block, 0, s>>>(src, sPitch, sFrame, S.w, S.h, p.pyr + D.off, D.pitch, g.pyrFrameBytes,
+                                             D.w, D.h, tabs[l]);
+        ++n;
+    }
+    return n;
+}
+
+int launch_fast(const FrameGeom& g, const DevPtrs& p, int B, int iniTh, int minTh, cudaStream_t s) {
+    cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
+    dim3 grid(g.totalCells, B);
+    fast_cells_kernel<<<grid, 128, 0, s>>>(g, p, iniTh, minTh);
+    return 1;
+}
+
+int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
+    int maxNode = 0;
+    for (int l = 0; l < g.nlevels; ++l) maxNode = max(maxNode, g.lv[l].nodeCap);
+    int cap = min(maxNode, 20000);
+    size_t smem = (size_t)cap * sizeof(unsigned long long);
+    static bool attr_done = false;
+    if (smem > 48 * 1024 || !attr_done) {
+        cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    dim3 grid(g.nlevels, B);
+    quadtree_kernel<<<grid, 256, smem, s>>>(g, p, cap);
+    order_kernel<<<B, 256, 0, s>>>(g, p);
+    return 2;
+}
+
+int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
+    int n = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        dim3 grid((L.w + 63) / 64, (L.h + 15) / 16, B);
+        blur_kernel<<<grid, 256, 0, s>>>(g, p, l);
+        ++n;
+    }
+    dim3 grid((g.kpPerFrame + 7) / 8, B);
+    describe_kernel<<<grid, 256, 0, s>>>(g, p);
+    return n + 1;
+}
+
+}  // namespace nav24

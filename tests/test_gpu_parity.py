@@ -1,0 +1,205 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded frames.
+
+Bit-exact: pyramid pixels, blurred pixels, raw FAST corners (coordinates, scores, order), retained keypoint
+sets and their order, orientation, final two-ended output order, match indices.  Descriptors: bit-exact
+except where a 1-ulp cosf/sinf difference flips a rounded sample coordinate; mismatching descriptors are
+counted and must stay <= 0.1 % (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from nav24_b200 import capi
+from nav24_b200.synth import synth, sequence
+from oracle import orb_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+DESC_TOL = 1e-3   # fraction of descriptors allowed to differ (north_star: <= 0.1 %)
+
+CASES = [  # H, W, nFeatures, seed, lowtex
+    (480, 752, 1000, 24, False),      # config 1 (EuRoC)
+    (480, 752, 5000, 25, False),      # config 1, the front end's x5 init mode
+    (480, 752, 200, 26, True),        # x0.2 mode, low texture
+    (376, 1241, 2000, 24, False),     # config 2 (KITTI): monoIndex > 0
+    (376, 1241, 2000, 31, True),
+    (480, 640, 1000, 7, False),       # config 3 (TUM)
+    (260, 340, 300, 5, True),         # near the minimum size
+    (300, 900, 700, 9, False),        # 3:1 panorama, nIni = 3
+]
+
+
+@pytest.fixture(scope="module")
+def ctxs(cuda_required):
+    cache = {}
+    yield cache
+    for c in cache.values():
+        c.close()
+
+
+def _ctx(cache, nf):
+    if nf not in cache:
+        cache[nf] = capi.OrbContext(nf)
+    return cache[nf]
+
+
+def _compare_detect(ctx, img, nf, check_stages=True):
+    o = oo.OrbOracle(nf)
+    mono_o, k_o, d_o = o.detect(img)
+    mono_g, k_g, d_g = ctx.detect(img)
+    if check_stages:
+        s_g, i_g, q_g = ctx.tables(); s_o, i_o, q_o, _ = o.tables()
+        assert np.array_equal(s_g, s_o) and np.array_equal(i_g, i_o) and np.array_equal(q_g, q_o)
+        for l in range(8):
+            assert np.array_equal(ctx.level(0, l), o.level(l)), f"pyramid level {l}"
+            assert np.array_equal(ctx.raw_keys(0, l), o.raw(l)), f"raw FAST keys level {l}"
+            b = o.blurred(l)
+            if b is not None:
+                assert np.array_equal(ctx.level(0, l, blurred=True), b), f"blurred level {l}"
+            lk_o, _ = o.level_kps(l)
+            lk_g = ctx.level_keypoints(0, l)
+            assert lk_g.tobytes() == lk_o.tobytes(), f"level keypoints {l}"
+    assert mono_g == mono_o
+    assert len(k_g) == len(k_o)
+    assert k_g.tobytes() == k_o.tobytes()
+    bad = int((d_g != d_o).any(axis=1).sum())
+    assert bad <= DESC_TOL * max(1, len(k_o)), f"{bad}/{len(k_o)} descriptors differ"
+    return bad, len(k_o), (mono_g, k_g, d_g), (mono_o, k_o, d_o)
+
+
+@pytest.mark.parametrize("H,W,nf,seed,low", CASES)
+def test_detect_parity(ctxs, H, W, nf, seed, low):
+    img = synth(H, W, seed, lowtex=low)
+    bad, n, _, _ = _compare_detect(_ctx(ctxs, nf), img, nf)
+    print(f"descriptor mismatches {bad}/{n}")
+
+
+def test_detect_strided_input_and_reuse(ctxs):
+    ctx = _ctx(ctxs, 1000)
+    big = synth(500, 800, 3)
+    view = big[10:490, 20:772]                  # non-contiguous rows, odd base alignment
+    _compare_detect(ctx, view, 1000)
+    _compare_detect(ctx, synth(480, 640, 4), 1000)       # shape change on the same context
+    ctx.set_num_features(5000)                           # scaleNumFeatures(5.f) of the front end
+    _compare_detect(ctx, synth(480, 640, 4), 5000)
+    ctx.set_num_features(1000)
+
+
+def test_flat_and_noise_images(ctxs):
+    ctx = _ctx(ctxs, 1000)
+    flat = np.full((480, 640), 93, np.uint8)
+    mono, k, d = ctx.detect(flat)
+    assert len(k) == 0 and mono == 0
+    o = oo.OrbOracle(1000); assert len(o.detect(flat)[1]) == 0
+    rng = np.random.default_rng(1)
+    noise = rng.integers(0, 256, (300, 400), dtype=np.uint8)        # corners everywhere: buffer stress
+    c2 = capi.OrbContext(1000, raw_keys_per_kpx=250)
+    try:
+        _compare_detect(c2, noise, 1000)
+    finally:
+        c2.close()
+    with pytest.raises(capi.Nav24Error) as e:                       # default capacity must fail loudly, not truncate
+        c3 = capi.OrbContext(1000, raw_keys_per_kpx=5)
+        try:
+            c3.detect(noise)
+        finally:
+            c3.close()
+    assert e.value.code == capi.E_OVERFLOW
+
+
+def test_error_codes(ctxs):
+    ctx = _ctx(ctxs, 1000)
+    with pytest.raises(capi.Nav24Error) as e:
+        ctx.detect(np.zeros((100, 120), np.uint8))                  # too small for 8 levels
+    assert e.value.code == capi.E_GEOMETRY
+    n = capi.C.c_int(0)
+    rc = ctx.L.nav24_orb_detect(ctx.h, None, 0, 0, 0, None, None, 0, capi.C.byref(n))
+    assert rc == capi.E_BADARG                                      # empty image -> -1 like the reference
+
+
+def test_batch_equals_single(ctxs):
+    ctx = _ctx(ctxs, 2000)
+    frames = np.stack([synth(376, 1241, 100 + i, lowtex=(i % 2 == 1)) for i in range(5)])
+    n, mono, kps, desc = ctx.detect_batch(frames)
+    o = oo.OrbOracle(2000)
+    for f in range(5):
+        mo, ko, do = o.detect(frames[f])
+        assert mono[f] == mo and n[f] == len(ko)
+        assert kps[f, :n[f]].tobytes() == ko.tobytes()
+        assert int((desc[f, :n[f]] != do).any(axis=1).sum()) <= DESC_TOL * len(ko)
+
+
+def test_window_matcher_parity(ctxs):
+    ctx = _ctx(ctxs, 1000)
+    for (H, W, step) in [(480, 752, (2, 1)), (376, 1241, (17, 0)), (480, 640, (3, 1))]:
+        fr = sequence(H, W, 77, 4, step=step)
+        o = oo.OrbOracle(1000)
+        dets = [o.detect(f) for f in fr]
+        grid_o = oo.grid_for(W, H); grid_g = capi.grid_for(W, H)
+        for a, b in [(0, 1), (0, 3), (2, 3)]:
+            (_, k1, d1), (_, k2, d2) = dets[a], dets[b]
+            ud1 = np.stack([k1["x"], k1["y"]], 1); ud2 = np.stack([k2["x"], k2["y"]], 1)
+            for ori in (True, False):
+                ref = oo.match_window(k1, ud1, d1, k2, ud2, d2, grid_o, check_ori=ori)
+                got, nm = ctx.match_window(k1, ud1, d1, k2, ud2, d2, grid_g, check_ori=ori)
+                assert np.array_equal(got, ref)
+                assert nm == int((ref >= 0).sum())
+            assert (ref >= 0).sum() > 20
+
+
+def test_window_matcher_adversarial(ctxs):
+    """Many near-identical descriptors: steals, ties and the >32-candidate slow path."""
+    ctx = _ctx(ctxs, 1000)
+    rng = np.random.default_rng(3)
+    n1, n2 = 600, 900
+    base = rng.integers(0, 256, (6, 32), dtype=np.uint8)
+    def mk(n):
+        d = base[rng.integers(0, 6, n)].copy()
+        flips = rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8) & \
+            rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        return d ^ flips
+    def kp(n):
+        k = np.zeros(n, capi.KP_DTYPE)
+        k["x"] = rng.uniform(0, 300, n).astype(np.float32); k["y"] = rng.uniform(0, 200, n).astype(np.float32)
+        k["angle"] = rng.uniform(0, 360, n).astype(np.float32); k["octave"] = rng.integers(0, 3, n) // 2
+        k["class_id"] = -1
+        return k
+    k1, k2, d1, d2 = kp(n1), kp(n2), mk(n1), mk(n2)
+    ud1 = np.stack([k1["x"], k1["y"]], 1); ud2 = np.stack([k2["x"], k2["y"]], 1) + np.float32(0.25)
+    for (th, ratio) in [(50, 0.6), (90, 0.9), (120, 1.0), (256, 1.5)]:
+        ref = oo.match_window(k1, ud1, d1, k2, ud2, d2, oo.grid_for(300, 200), th_low=th, nnratio=ratio)
+        got, _ = ctx.match_window(k1, ud1, d1, k2, ud2, d2, capi.grid_for(300, 200), th_low=th, nnratio=ratio)
+        assert np.array_equal(got, ref), (th, ratio)
+
+
+def test_device_resident_match_frames(ctxs):
+    ctx = _ctx(ctxs, 2000)
+    H, W = 376, 1241
+    fr = sequence(H, W, 5, 3, step=(9, 0))
+    n, mono, kps, desc = ctx.detect_batch(fr)
+    m, nm = ctx.match_window_frames([(0, 1), (0, 2), (1, 2)], capi.grid_for(W, H))
+    for p, (a, b) in enumerate([(0, 1), (0, 2), (1, 2)]):
+        k1, k2 = kps[a, :n[a]], kps[b, :n[b]]
+        ud1 = np.stack([k1["x"], k1["y"]], 1); ud2 = np.stack([k2["x"], k2["y"]], 1)
+        ref = oo.match_window(k1, ud1, desc[a, :n[a]], k2, ud2, desc[b, :n[b]], oo.grid_for(W, H))
+        assert np.array_equal(m[p, :n[a]], ref)
+        assert nm[p] == (ref >= 0).sum() and nm[p] > 50
+
+
+@pytest.mark.parametrize("norm", [0, 1])
+def test_bf_knn2_parity(ctxs, norm):
+    ctx = _ctx(ctxs, 1000)
+    rng = np.random.default_rng(11)
+    d2 = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    d1 = d2[rng.integers(0, 1500, 1100)].copy()
+    d1 ^= rng.integers(0, 256, d1.shape, dtype=np.uint8) & rng.integers(0, 256, d1.shape, dtype=np.uint8) & \
+        rng.integers(0, 256, d1.shape, dtype=np.uint8)
+    d2[40] = d2[41]; d1[0] = d2[40]
+    ref = oo.match_bf_knn2(d1, d2, norm, 0.7)
+    got = ctx.match_bf_knn2(d1, d2, norm, 0.7)
+    for r, g in zip(ref, got):
+        assert np.array_equal(r, g)
+    # degenerate sizes
+    got = ctx.match_bf_knn2(d1[:3], d2[:1], norm, 0.7)
+    ref = oo.match_bf_knn2(d1[:3], d2[:1], norm, 0.7)
+    for r, g in zip(ref, got):
+        assert np.array_equal(r, g)
