@@ -119,8 +119,14 @@ int nav24_orb_get_level_keypoints(nav24_orb* ctx, int frame, int level, nav24_kp
 /* Device time (ms, CUDA events on the context's stream) of the stages of the last detect call:
  * [0] pyramid, [1] FAST, [2] quadtree, [3] order+orientation+blur+descriptors, [4] total kernels. */
 int nav24_orb_stage_ms(nav24_orb* ctx, float* ms5);
+/* Same stages summed over the detect calls since the last reset (at most the last 64); *calls = how many. */
+int nav24_orb_stage_ms_sum(nav24_orb* ctx, float* ms5, int* calls, int reset);
 /* Number of kernels launched by this context so far. */
 long long nav24_orb_launch_count(const nav24_orb* ctx);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel of this context runs on):
+ * start records an event; stop records a second one, waits for it and returns the elapsed device ms. */
+int nav24_orb_timer_start(nav24_orb* ctx);
+int nav24_orb_timer_stop(nav24_orb* ctx, float* ms);
 
 /* ---- matchers --------------------------------------------------------------------------- */
 /* Replaces FtAssocOrbSlam::matchV (OP_FtAssocOrbSlam.cpp:91-223) + FeatureGrid (FeatureGrid.cpp:20-152).
@@ -140,7 +146,8 @@ int nav24_match_window_batch(nav24_orb* ctx, int n_pairs, int cap, const nav24_k
 
 /* Device-resident: matches frame a against frame b of the LAST detect batch (identity undistortion), no
  * host round trip of keypoints/descriptors.  pairs = n_pairs x (a,b) frame indices. matches12 is
- * [n_pairs][cap] on the host, cap >= nav24_orb_max_keypoints. */
+ * [n_pairs][cap] on the host, cap >= nav24_orb_max_keypoints.  With matches12 == NULL and n_matches == NULL the call only
+ * enqueues the kernel (no host synchronisation; results stay on the device). */
 int nav24_match_window_frames(nav24_orb* ctx, int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid,
                               float window, float nnratio, int th_low, int check_ori, int32_t* matches12,
                               int cap, int* n_matches);

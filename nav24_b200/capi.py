@@ -74,6 +74,9 @@ def lib():
     L.nav24_orb_get_level_keypoints.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
     L.nav24_orb_stage_ms.argtypes = [vp, vp]
     L.nav24_orb_launch_count.argtypes = [vp]; L.nav24_orb_launch_count.restype = C.c_longlong
+    L.nav24_orb_stage_ms_sum.argtypes = [vp, vp, ip, C.c_int]
+    L.nav24_orb_timer_start.argtypes = [vp]
+    L.nav24_orb_timer_stop.argtypes = [vp, vp]
     L.nav24_match_window.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.POINTER(GridCfg), C.c_float, C.c_float,
                                      C.c_int, C.c_int, vp]
     L.nav24_match_window_batch.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(GridCfg), C.c_float,
@@ -222,6 +225,19 @@ class OrbContext:
         self._check(self.L.nav24_orb_stage_ms(self.h, _p(ms)))
         return ms
 
+    def stage_ms_sum(self, reset=True):
+        ms = np.zeros(5, np.float32); calls = C.c_int(0)
+        self._check(self.L.nav24_orb_stage_ms_sum(self.h, _p(ms), C.byref(calls), int(reset)))
+        return ms, calls.value
+
+    def timer_start(self):
+        self._check(self.L.nav24_orb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._check(self.L.nav24_orb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         return int(self.L.nav24_orb_launch_count(self.h))
 
@@ -234,6 +250,12 @@ class OrbContext:
         nm = self._check(self.L.nav24_match_window(self.h, _p(k1), _p(ud1), _p(d1), len(k1), _p(k2), _p(ud2), _p(d2), len(k2),
                                                    C.byref(grid), window, nnratio, th_low, int(check_ori), _p(m)))
         return m[:len(k1)], nm
+
+    def match_window_frames_async(self, pairs, grid, window=100.0, nnratio=0.6, th_low=50, check_ori=True):
+        """Enqueue only; results stay on the device (no host synchronisation)."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self._check(self.L.nav24_match_window_frames(self.h, len(pairs), _p(pairs), C.byref(grid), window, nnratio, th_low,
+                                                     int(check_ori), None, 0, None))
 
     def match_window_frames(self, pairs, grid, window=100.0, nnratio=0.6, th_low=50, check_ori=True, want_matches=True):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)

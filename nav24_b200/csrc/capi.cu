@@ -49,7 +49,11 @@ struct nav24_orb {
     std::vector<int> quota;
     std::string err;
     cudaStream_t stream = nullptr, copyStream = nullptr;
-    cudaEvent_t ev[6]{};
+    static constexpr int kEvRing = 64;
+    cudaEvent_t evRing[kEvRing][5]{};
+    long long evCalls = 0;      // pipeline runs since the last stage-sum reset
+    cudaEvent_t* ev = evRing[0];
+    cudaEvent_t evT[2]{};
     long long launches = 0;
 
     // workspace keyed on (w, h, nFeatures); batch capacity grows on demand
@@ -246,6 +250,8 @@ int run_pipeline(nav24_orb* ctx, int B) {
     const FrameGeom& g = ctx->g;
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), s));
+    ctx->ev = ctx->evRing[ctx->evCalls % nav24_orb::kEvRing];
+    ctx->evCalls++;
     CK(cudaEventRecord(ctx->ev[0], s));
     ctx->launches += launch_pyramid(g, ctx->p, ctx->tabs.data(), B, s);
     CK(cudaEventRecord(ctx->ev[1], s));
@@ -331,7 +337,8 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
         delete ctx;
         return NAV24_E_CUDA;
     }
-    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& r : ctx->evRing) for (auto& e : r) cudaEventCreate(&e);
+    for (auto& e : ctx->evT) cudaEventCreate(&e);
     *out = ctx;
     return NAV24_OK;
 }
@@ -348,7 +355,8 @@ void nav24_orb_destroy(nav24_orb* ctx) {
                       &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mI0, &ctx->mI1,
                       &ctx->mF0, &ctx->mF1, &ctx->mPass};
     for (DevBuf* b : bufs) b->release();
-    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& r : ctx->evRing) for (auto& e : r) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->evT) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     delete ctx;
@@ -507,7 +515,39 @@ int nav24_orb_stage_ms(nav24_orb* ctx, float* ms5) {
     return NAV24_OK;
 }
 
+int nav24_orb_stage_ms_sum(nav24_orb* ctx, float* ms5, int* calls, int reset) {
+    if (!ctx || !ms5) return NAV24_E_BADARG;
+    cudaSetDevice(ctx->device);
+    const int n = (int)std::min<long long>(ctx->evCalls, nav24_orb::kEvRing);
+    for (int i = 0; i < 5; ++i) ms5[i] = 0.f;
+    for (int c = 0; c < n; ++c) {
+        cudaEvent_t* e = ctx->evRing[(ctx->evCalls - 1 - c) % nav24_orb::kEvRing];
+        CK(cudaEventSynchronize(e[4]));
+        float t;
+        for (int i = 0; i < 4; ++i) { CK(cudaEventElapsedTime(&t, e[i], e[i + 1])); ms5[i] += t; }
+        CK(cudaEventElapsedTime(&t, e[0], e[4])); ms5[4] += t;
+    }
+    if (calls) *calls = n;
+    if (reset) ctx->evCalls = 0;
+    return NAV24_OK;
+}
+
 long long nav24_orb_launch_count(const nav24_orb* ctx) { return ctx ? ctx->launches : 0; }
+
+int nav24_orb_timer_start(nav24_orb* ctx) {
+    if (!ctx) return NAV24_E_BADARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->evT[0], ctx->stream));
+    return NAV24_OK;
+}
+int nav24_orb_timer_stop(nav24_orb* ctx, float* ms) {
+    if (!ctx || !ms) return NAV24_E_BADARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->evT[1], ctx->stream));
+    CK(cudaEventSynchronize(ctx->evT[1]));
+    CK(cudaEventElapsedTime(ms, ctx->evT[0], ctx->evT[1]));
+    return NAV24_OK;
+}
 
 }  // extern "C"
 
@@ -639,6 +679,7 @@ int nav24_match_window_frames(nav24_orb* ctx, int P, const int* pairs_ab, const 
     a.n1 = a.n2 = ctx->p.nOut; a.stride1 = a.stride2 = oc; a.pairs = (const int*)ctx->mPairs.ptr;
     ctx->launches += launch_match_window(a, P, s);
     CK(cudaGetLastError());
+    if (!matches12 && !n_matches) return NAV24_OK;      // fully asynchronous: results stay on the device
     if (matches12)
         CK(cudaMemcpy2DAsync(matches12, (size_t)cap * 4, a.matches12, (size_t)oc * 4, (size_t)oc * 4, P, cudaMemcpyDeviceToHost, s));
     std::vector<int> nm(P);
