@@ -61,6 +61,9 @@ struct nav24_orb {
     FrameGeom g{};
     DevPtrs p{};
     std::vector<ResizeTab> tabs;
+    TmaMaps maps{};
+    int mapsB = 0;            // frame count the level>=1 maps were encoded for
+    const void* mapsPyr = nullptr;
     DevBuf bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
         bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs;
     // matcher scratch
@@ -123,6 +126,9 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.wCell = (int)std::ceil(width / L.nCols);
         L.hCell = (int)std::ceil(height / L.nRows);
         if (L.wCell + 6 > kMaxCellTile || L.hCell + 6 > kMaxCellTile) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
+        L.boxW = align_up(L.wCell + 7 + 15, 16);
+        L.boxH = L.hCell + 6;
+        if (L.boxW * L.boxH > kCellTileBytes) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
         L.cellBase = cellBase;
         cellBase += L.nCols * L.nRows;
         long long cap = ((long long)L.w * L.h * rawPerKpx + 999) / 1000 + 64;
@@ -169,6 +175,41 @@ void build_resize_table(int ssize, int dsize, std::vector<int>& ofs, std::vector
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D (x, y, frame) u8 tensor map over one pyramid level; box = one FAST cell tile
+int encode_level_map(nav24_orb* ctx, CUtensorMap* m, const void* base, int w, int h, int frames, long long pitch,
+                     long long frameStride, int boxW, int boxH) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return ctx->fail(NAV24_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
+    cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u};
+    cuuint32_t es[3] = {1u, 1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ctx->err = "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r);
+        return NAV24_E_CUDA;
+    }
+    return NAV24_OK;
+}
+
 int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
     cudaSetDevice(ctx->device);
     const bool shapeChanged = (w != ctx->wsW || h != ctx->wsH || ctx->prm.n_features != ctx->wsFeat);
@@ -199,7 +240,7 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         }
         ctx->tabs.assign(nl, ResizeTab{});
         for (int l = 1; l < nl; ++l) ctx->tabs[l] = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l]};
-        ctx->wsW = w; ctx->wsH = h; ctx->wsFeat = ctx->prm.n_features; ctx->wsB = 0;
+        ctx->wsW = w; ctx->wsH = h; ctx->wsFeat = ctx->prm.n_features; ctx->wsB = 0; ctx->mapsB = 0;
         ctx->lastValid = false;
     }
     if (B > ctx->wsB || shapeChanged) {
@@ -255,7 +296,20 @@ int run_pipeline(nav24_orb* ctx, int B) {
     CK(cudaEventRecord(ctx->ev[0], s));
     ctx->launches += launch_pyramid(g, ctx->p, ctx->tabs.data(), B, s);
     CK(cudaEventRecord(ctx->ev[1], s));
-    ctx->launches += launch_fast(g, ctx->p, B, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);
+    {   // tensor maps: levels >= 1 live in the workspace, level 0 is the caller's (or the staging) buffer
+        if (ctx->mapsB != ctx->wsB || ctx->mapsPyr != ctx->p.pyr) {
+            for (int l = 1; l < g.nlevels; ++l) {
+                int rc = encode_level_map(ctx, &ctx->maps.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
+                                          g.lv[l].pitch, g.pyrFrameBytes, g.lv[l].boxW, g.lv[l].boxH);
+                if (rc != NAV24_OK) return rc;
+            }
+            ctx->mapsB = ctx->wsB; ctx->mapsPyr = ctx->p.pyr;
+        }
+        int rc = encode_level_map(ctx, &ctx->maps.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch,
+                                  B > 1 ? ctx->p.l0Frame : ctx->p.l0Pitch * g.lv[0].h, g.lv[0].boxW, g.lv[0].boxH);
+        if (rc != NAV24_OK) return rc;
+    }
+    ctx->launches += launch_fast(g, ctx->p, ctx->maps, B, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);
     CK(cudaEventRecord(ctx->ev[2], s));
     ctx->launches += launch_quadtree(g, ctx->p, B, s);
     CK(cudaEventRecord(ctx->ev[3], s));

@@ -1,5 +1,6 @@
 // orb_internal.cuh — shared device-side layout of the B200 ORB front end (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -11,7 +12,8 @@ constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;           // EDGE_THRESHOLD (OP_FtDtOrbSlam.cpp:14)
 constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
-constexpr int kCellTilePitch = 80;
+constexpr int kCellTileBytes = 96 * 76;   // TMA box: align16(wCell+7+15) x (hCell+6) bytes (x start is 16-B aligned)
+constexpr int kCellQueue = 70 * 70 + 4;   // interior pixels of the largest cell
 
 // device error bits (ctx->d_err)
 enum : int { ERR_RAW_OVERFLOW = 1, ERR_ROOT_RANGE = 2, ERR_NODE_OVERFLOW = 4, ERR_CELL_SIZE = 8, ERR_KP_OVERFLOW = 16 };
@@ -23,6 +25,7 @@ struct LevelGeom {
     long long boff;          // byte offset inside one frame's blurred slab
     // FAST cell grid (OP_FtDtOrbSlam.cpp:735-768)
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
+    int boxW, boxH;          // TMA box of one FAST cell: align16(wCell+6+1+15) x (hCell+6)
     int cellBase;            // first cell id of this level inside the per-frame cell table
     int rawCap;              // raw-corner capacity of this level (records)
     int rawOff;              // record offset of the level inside one frame's raw slab
@@ -93,13 +96,15 @@ struct DevPtrs {
     int* err;                // device error bits
 };
 
+struct TmaMaps { CUtensorMap m[kMaxLevels]; };   // one 3-D (x, y, frame) u8 tensor map per pyramid level
+
 struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;
 };
 
 // launchers (orb_kernels.cu); each returns the number of kernels launched
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, int B, cudaStream_t s);
-int launch_fast(const FrameGeom& g, const DevPtrs& p, int B, int iniTh, int minTh, cudaStream_t s);
+int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
 int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
 

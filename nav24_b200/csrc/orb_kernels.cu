@@ -90,17 +90,15 @@ __global__ void __launch_bounds__(256) resize_kernel(const uint8_t* __restrict__
 // detection domain is the cell minus a 3-px rim, and a cell with no survivor at iniThFAST is
 // redone at minThFAST.
 // ------------------------------------------------------------------------------------------
+// score of one pixel: (d, -d) packed as s16x2, window-9 minima by doubling, max over the 16 arcs.
 __device__ __forceinline__ int fast_score(const uint8_t* c, int pitch) {
-    // packed (d, -d) as s16x2; window-9 minima by doubling; max over the 16 arcs
     const int cv = c[0];
+    const unsigned cn = ((unsigned)(-cv) & 0xffffu) | ((unsigned)cv << 16);     // (-c, +c)
     unsigned v[16];
     const int ofs[16] = {3 * pitch, 3 * pitch + 1, 2 * pitch + 2, pitch + 3, 3, -pitch + 3, -2 * pitch + 2, -3 * pitch + 1,
                          -3 * pitch, -3 * pitch - 1, -2 * pitch - 2, -pitch - 3, -3, pitch - 3, 2 * pitch - 2, 3 * pitch - 1};
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int d = (int)c[ofs[k]] - cv;
-        v[k] = ((unsigned)d & 0xffffu) | ((unsigned)(-d) << 16);
-    }
+    for (int k = 0; k < 16; ++k) v[k] = __vadd2((unsigned)c[ofs[k]] * 0xFFFF0001u, cn);   // (r - c, c - r)
     unsigned m2[16], m4[16], m8[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) m2[k] = __vmins2(v[k], v[(k + 1) & 15]);
@@ -115,34 +113,25 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int pitch) {
     return max(lo, hi) - 1;
 }
 
-__device__ __forceinline__ bool fast_maybe(const uint8_t* c, int pitch, int t) {
-    const int cv = c[0];
-#define NAV24_PAIR(oa)                                                      \
-    {                                                                       \
-        const int a = abs((int)c[(oa)] - cv), b = abs((int)c[-(oa)] - cv);  \
-        if (a <= t && b <= t) return false;                                 \
-    }
-    NAV24_PAIR(3 * pitch)        // ring 0 / 8
-    NAV24_PAIR(3)                // ring 4 / 12
-    NAV24_PAIR(2 * pitch + 2)    // ring 2 / 10
-    NAV24_PAIR(-2 * pitch + 2)   // ring 6 / 14
-    NAV24_PAIR(3 * pitch + 1)    // ring 1 / 9
-    NAV24_PAIR(pitch + 3)        // ring 3 / 11
-    NAV24_PAIR(-pitch + 3)       // ring 5 / 13
-    NAV24_PAIR(-3 * pitch + 1)   // ring 7 / 15
-#undef NAV24_PAIR
-    return true;
+// per-byte (x > t) for t < 128: 0x80 in every byte that passes.  k = (0x7f - t) * 0x01010101
+__device__ __forceinline__ unsigned gt_bytes2(unsigned x1, unsigned x2, unsigned k) {
+    const unsigned s1 = (x1 & 0x7f7f7f7fu) + k, s2 = (x2 & 0x7f7f7f7fu) + k;
+    return (s1 | x1 | s2 | x2) & 0x80808080u;
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
-                                                         int iniTh, int minTh) {
-    __shared__ __align__(16) uint8_t tile[kMaxCellTile * kCellTilePitch];
-    __shared__ __align__(16) uint8_t smap[kMaxCellTile * kCellTilePitch];
-    __shared__ int s_cnt[2];
-    __shared__ int s_base;
+                                                         const __grid_constant__ TmaMaps maps, int iniTh, int minTh) {
+    __shared__ __align__(128) uint8_t tile[kCellTileBytes + 64];
+    __shared__ __align__(16) uint8_t smap[kCellTileBytes + 64];
+    __shared__ unsigned short queue[kCellQueue];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ int s_q, s_cnt, s_base;
     __shared__ int s_wsum[4];
 
     const int tid = threadIdx.x, f = blockIdx.y, cell = blockIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
     int l = 0;
     while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) ++l;
     const LevelGeom& L = g.lv[l];
@@ -160,54 +149,119 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         if (tid == 0) *info = make_uint2(0u, 0u);
         return;
     }
-    if (cw > kMaxCellTile || ch > kMaxCellTile) {
-        if (tid == 0) { atomicOr(p.err, ERR_CELL_SIZE); *info = make_uint2(0u, 0u); }
-        return;
+    // TMA needs a 16-byte aligned start in x: the box starts at xa <= iniX-1, the interior at tile column o+4
+    const int xa = (iniX - 1) & ~15, o = iniX - 1 - xa;
+    const int pitch = L.boxW;
+    const unsigned barAddr = smem_u32(&bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const long long pitch = level_pitch(g, p, l);
-    const uint8_t* src = level_ptr(g, p, f, l) + (long long)iniY * pitch + iniX;
-
-    for (int idx = tid; idx < cw * ch; idx += 128) {
-        const int y = idx / cw, x = idx - y * cw;
-        tile[y * kCellTilePitch + x] = src[(long long)y * pitch + x];
-        smap[y * kCellTilePitch + x] = 0;
-    }
-    if (tid < 2) s_cnt[tid] = 0;
+    for (int i = tid; i < (pitch * L.boxH + 64) / 16; i += 128) reinterpret_cast<uint4*>(smap)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-
-    const int iw = cw - 6, ih = ch - 6, npx = iw * ih;
-    const int lowTh = min(iniTh, minTh);
-    for (int idx = tid; idx < npx; idx += 128) {
-        const int y = idx / iw, x = idx - y * iw;
-        const uint8_t* cpx = tile + (y + 3) * kCellTilePitch + (x + 3);
-        if (fast_maybe(cpx, kCellTilePitch, lowTh)) {
-            const int s = fast_score(cpx, kCellTilePitch);
-            if (s >= lowTh) smap[(y + 3) * kCellTilePitch + (x + 3)] = (uint8_t)s;
+    if (tid == 0) {
+        const unsigned bytes = (unsigned)(pitch * L.boxH);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                smem_u32(tile)),
+            "l"(&maps.m[l]), "r"(xa), "r"(iniY), "r"(f), "r"(barAddr)
+            : "memory");
+    }
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(barAddr), "r"(0u)
+                : "memory");
         }
     }
-    __syncthreads();
 
-    // pass 1: count strict local maxima at both thresholds
-    int n_ini = 0, n_min = 0;
-    for (int idx = tid; idx < npx; idx += 128) {
-        const int y = idx / iw, x = idx - y * iw;
-        const uint8_t* m = smap + (y + 3) * kCellTilePitch + (x + 3);
-        const int s = m[0];
-        if (s == 0) continue;
-        const bool mx = s > m[-1] && s > m[1] && s > m[-kCellTilePitch - 1] && s > m[-kCellTilePitch] &&
-                        s > m[-kCellTilePitch + 1] && s > m[kCellTilePitch - 1] && s > m[kCellTilePitch] &&
-                        s > m[kCellTilePitch + 1];
-        if (mx) { n_ini += (s >= iniTh); n_min += (s >= minTh); }
-    }
+    const int iw = cw - 6, ih = ch - 6;
+    const int c_lo = o + 4, c_hi = o + 4 + iw;      // interior tile columns [c_lo, c_hi)
+    const int gx0 = c_lo >> 2;
+    const int ngx = ((c_hi - 1) >> 2) - gx0 + 1, ngroups = ngx * ih;
+    const unsigned* tile32 = reinterpret_cast<const unsigned*>(tile);
+    const unsigned* smap32 = reinterpret_cast<const unsigned*>(smap);
+    const int pw = pitch >> 2;
+
+    // strict 3x3 local maxima of one 4-px group of the score map with score >= th; bit b = pixel b
+    auto group_maxima = [&](int gi, int th) -> unsigned {
+        const int yy = gi / ngx, gx = gi - yy * ngx;
+        const int widx = (yy + 3) * pw + gx0 + gx;
+        const unsigned w = smap32[widx];
+        if (w == 0u) return 0u;
+        unsigned flags = 0;
+        const uint8_t* m = smap + widx * 4;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_ini += __shfl_xor_sync(0xffffffffu, n_ini, o);
-        n_min += __shfl_xor_sync(0xffffffffu, n_min, o);
+        for (int b = 0; b < 4; ++b) {
+            const int s = (w >> (8 * b)) & 0xff;
+            if (s >= th && s > 0) {
+                const uint8_t* q = m + b;
+                if (s > q[-1] && s > q[1] && s > q[-pitch - 1] && s > q[-pitch] && s > q[-pitch + 1] && s > q[pitch - 1] &&
+                    s > q[pitch] && s > q[pitch + 1])
+                    flags |= 1u << b;
+            }
+        }
+        return flags;
+    };
+
+    int th = iniTh, total = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        th = pass == 0 ? iniTh : minTh;
+        if (tid == 0) { s_q = 0; s_cnt = 0; }
+        __syncthreads();
+        // stage A: antipodal-pair rejection on 4 pixels at a time (necessary condition for score >= th)
+        const unsigned kk = (unsigned)(0x7f - min(th, 127)) * 0x01010101u;
+        for (int gi = tid; gi < ngroups; gi += 128) {
+            const int yy = gi / ngx, gx = gi - yy * ngx;
+            const int widx = (yy + 3) * pw + gx0 + gx;
+            const unsigned C = tile32[widx];
+            const int cb = 4 * (gx0 + gx);                           // tile column of byte 0
+            const int first = max(c_lo - cb, 0), last = min(c_hi - cb, 4);     // valid bytes [first, last)
+            unsigned alive = (0x80808080u >> (8 * (4 - last))) & (0x80808080u << (8 * first));
+            if (th < 128) {
+                const unsigned up = tile32[widx + 3 * pw], dn = tile32[widx - 3 * pw];
+                alive &= gt_bytes2(__vabsdiffu4(up, C), __vabsdiffu4(dn, C), kk);
+                if (alive) {
+                    const unsigned Lw = tile32[widx - 1], Rw = tile32[widx + 1];
+                    const unsigned left3 = __byte_perm(Lw, C, 0x4321), right3 = __byte_perm(C, Rw, 0x6543);
+                    alive &= gt_bytes2(__vabsdiffu4(left3, C), __vabsdiffu4(right3, C), kk);
+                }
+            }
+            if (alive) {
+                const int n = __popc(alive);
+                int pos = atomicAdd(&s_q, n);
+                while (alive) {
+                    const int b = (__ffs(alive) - 1) >> 3;
+                    alive &= alive - 1;
+                    queue[pos++] = (unsigned short)(widx * 4 + b);
+                }
+            }
+        }
+        __syncthreads();
+        // stage B: exact score of the survivors, balanced over the CTA
+        const int nq = s_q;
+        for (int qi = tid; qi < nq; qi += 128) {
+            const int idx = queue[qi];
+            const int s = fast_score(tile + idx, pitch);
+            if (s >= th) smap[idx] = (uint8_t)s;
+        }
+        __syncthreads();
+        // stage C: count the keypoints of cv::FAST(cell, th, nms=true)
+        int cnt = 0;
+        for (int gi = tid; gi < ngroups; gi += 128) cnt += __popc(group_maxima(gi, th));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        total = s_cnt;
+        if (total > 0) break;                       // :787 "if(vKeysCell.empty())" -> retry at minThFAST
+        __syncthreads();
     }
-    if ((tid & 31) == 0) { atomicAdd(&s_cnt[0], n_ini); atomicAdd(&s_cnt[1], n_min); }
-    __syncthreads();
-    const int th = s_cnt[0] > 0 ? iniTh : minTh;            // :787 "if(vKeysCell.empty())"
-    const int total = s_cnt[0] > 0 ? s_cnt[0] : s_cnt[1];
+
     if (tid == 0) {
         int base = 0;
         if (total > 0) {
@@ -221,33 +275,36 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     if (total == 0 || s_base < 0) return;
     RawRec* out = p.raw + (long long)f * g.rawPerFrame + L.rawOff + s_base;
 
-    // pass 2: ordered (row-major) compaction
+    // ordered (row-major) compaction
     int run = 0;
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int base = 0; base < npx; base += 128) {
-        const int idx = base + tid;
-        bool keep = false;
-        int x = 0, y = 0, s = 0;
-        if (idx < npx) {
-            y = idx / iw; x = idx - y * iw;
-            const uint8_t* m = smap + (y + 3) * kCellTilePitch + (x + 3);
-            s = m[0];
-            keep = s >= th && s > m[-1] && s > m[1] && s > m[-kCellTilePitch - 1] && s > m[-kCellTilePitch] &&
-                   s > m[-kCellTilePitch + 1] && s > m[kCellTilePitch - 1] && s > m[kCellTilePitch] &&
-                   s > m[kCellTilePitch + 1];
+    for (int base = 0; base < ngroups; base += 128) {
+        const int gi = base + tid;
+        const unsigned flags = gi < ngroups ? group_maxima(gi, th) : 0u;
+        const int n = __popc(flags);
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) s_wsum[wid] = __popc(bal);
+        if (lane == 31) s_wsum[wid] = incl;
         __syncthreads();
         int wbase = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) { const int v = s_wsum[w]; if (w < wid) wbase += v; tot += v; }
-        if (keep) {
-            RawRec r;
-            r.x = (unsigned short)(x + 3 + cj * L.wCell);     // :811-812, relative to (minBorderX, minBorderY)
-            r.y = (unsigned short)(y + 3 + ci * L.hCell);
-            r.score = (unsigned short)s; r.pad = 0;
-            out[run + wbase + __popc(bal & ((1u << lane) - 1u))] = r;
+        if (flags) {
+            const int yy = gi / ngx, gx = gi - yy * ngx;
+            int pos = run + wbase + incl - n;
+            const uint8_t* m = smap + ((yy + 3) * pw + gx0 + gx) * 4;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (flags & (1u << b)) {
+                    RawRec r;
+                    r.x = (unsigned short)(4 * (gx0 + gx) + b - o - 1 + cj * L.wCell);   // :811-812, relative to (minBorderX, minBorderY)
+                    r.y = (unsigned short)(yy + 3 + ci * L.hCell);
+                    r.score = m[b]; r.pad = 0;
+                    out[pos++] = r;
+                }
         }
         run += tot;
         __syncthreads();
@@ -715,10 +772,10 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
     return n;
 }
 
-int launch_fast(const FrameGeom& g, const DevPtrs& p, int B, int iniTh, int minTh, cudaStream_t s) {
+int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
     cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
     dim3 grid(g.totalCells, B);
-    fast_cells_kernel<<<grid, 128, 0, s>>>(g, p, iniTh, minTh);
+    fast_cells_kernel<<<grid, 128, 0, s>>>(g, p, maps, iniTh, minTh);
     return 1;
 }
 
