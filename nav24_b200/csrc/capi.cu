@@ -127,6 +127,7 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.hCell = (int)std::ceil(height / L.nRows);
         if (L.wCell + 6 > kMaxCellTile || L.hCell + 6 > kMaxCellTile) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
         L.boxW = align_up(L.wCell + 7 + 15, 16);
+        if (((L.boxW / 16) & 1) == 0) L.boxW += 16;     // 16 x odd: rows 4*odd words apart -> conflict-free over 8 rows
         L.boxH = L.hCell + 6;
         if (L.boxW * L.boxH > kCellTileBytes) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
         L.cellBase = cellBase;

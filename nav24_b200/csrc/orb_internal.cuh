@@ -12,7 +12,7 @@ constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;           // EDGE_THRESHOLD (OP_FtDtOrbSlam.cpp:14)
 constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
-constexpr int kCellTileBytes = 96 * 76;   // TMA box: align16(wCell+7+15) x (hCell+6) bytes (x start is 16-B aligned)
+constexpr int kCellTileBytes = 112 * 76;  // TMA box: (16 x odd >= wCell+7+15) x (hCell+6) bytes (x start is 16-B aligned)
 constexpr int kCellQueue = 70 * 70 + 4;   // interior pixels of the largest cell
 
 // device error bits (ctx->d_err)
@@ -25,7 +25,7 @@ struct LevelGeom {
     long long boff;          // byte offset inside one frame's blurred slab
     // FAST cell grid (OP_FtDtOrbSlam.cpp:735-768)
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
-    int boxW, boxH;          // TMA box of one FAST cell: align16(wCell+6+1+15) x (hCell+6)
+    int boxW, boxH;          // TMA box of one FAST cell: 16*odd >= wCell+6+1+15 (bank-conflict-free row pitch) x (hCell+6)
     int cellBase;            // first cell id of this level inside the per-frame cell table
     int rawCap;              // raw-corner capacity of this level (records)
     int rawOff;              // record offset of the level inside one frame's raw slab
@@ -97,6 +97,8 @@ struct DevPtrs {
 };
 
 struct TmaMaps { CUtensorMap m[kMaxLevels]; };   // one 3-D (x, y, frame) u8 tensor map per pyramid level
+
+struct FastSmem { int offMap, offQueue, offMask, total; };   // dynamic shared memory layout of fast_cells_kernel
 
 struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;

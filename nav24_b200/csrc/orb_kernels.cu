@@ -90,27 +90,33 @@ __global__ void __launch_bounds__(256) resize_kernel(const uint8_t* __restrict__
 // detection domain is the cell minus a 3-px rim, and a cell with no survivor at iniThFAST is
 // redone at minThFAST.
 // ------------------------------------------------------------------------------------------
-// score of one pixel: (d, -d) packed as s16x2, window-9 minima by doubling, max over the 16 arcs.
+// Score of one pixel.  Ring differences are packed as biased u16x2 lanes (d+256, 256-d) by one IMAD;
+// min over an arc of 9 = min3 of three min3's (VIMNMX3.U16x2); max over the 16 arcs by max3.
 __device__ __forceinline__ int fast_score(const uint8_t* c, int pitch) {
-    const int cv = c[0];
-    const unsigned cn = ((unsigned)(-cv) & 0xffffu) | ((unsigned)cv << 16);     // (-c, +c)
+    const unsigned cv = c[0];
+    const unsigned cn = (256u - cv) + ((cv + 256u) << 16);
+    const uint8_t* rm3 = c - 3 * pitch; const uint8_t* rm2 = c - 2 * pitch; const uint8_t* rm1 = c - pitch;
+    const uint8_t* rp1 = c + pitch;     const uint8_t* rp2 = c + 2 * pitch; const uint8_t* rp3 = c + 3 * pitch;
     unsigned v[16];
-    const int ofs[16] = {3 * pitch, 3 * pitch + 1, 2 * pitch + 2, pitch + 3, 3, -pitch + 3, -2 * pitch + 2, -3 * pitch + 1,
-                         -3 * pitch, -3 * pitch - 1, -2 * pitch - 2, -pitch - 3, -3, pitch - 3, 2 * pitch - 2, 3 * pitch - 1};
+#define NAV24_V(k, ptr, dx) v[k] = (unsigned)(ptr)[dx] * 0xFFFF0001u + cn;
+    NAV24_V(0, rp3, 0)  NAV24_V(1, rp3, 1)   NAV24_V(2, rp2, 2)   NAV24_V(3, rp1, 3)
+    NAV24_V(4, c, 3)    NAV24_V(5, rm1, 3)   NAV24_V(6, rm2, 2)   NAV24_V(7, rm3, 1)
+    NAV24_V(8, rm3, 0)  NAV24_V(9, rm3, -1)  NAV24_V(10, rm2, -2) NAV24_V(11, rm1, -3)
+    NAV24_V(12, c, -3)  NAV24_V(13, rp1, -3) NAV24_V(14, rp2, -2) NAV24_V(15, rp3, -1)
+#undef NAV24_V
+    unsigned m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = __vadd2((unsigned)c[ofs[k]] * 0xFFFF0001u, cn);   // (r - c, c - r)
-    unsigned m2[16], m4[16], m8[16];
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(v[k], v[(k + 1) & 15], v[(k + 2) & 15]);
+    unsigned a[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m2[k] = __vmins2(v[k], v[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m8[k] = __vmins2(m4[k], m4[(k + 4) & 15]);
-    unsigned best = __vmins2(m8[0], v[8]);
-#pragma unroll
-    for (int k = 1; k < 16; ++k) best = __vmaxs2(best, __vmins2(m8[k], v[(k + 8) & 15]));
-    const int lo = (int)(short)(best & 0xffffu), hi = (int)(short)(best >> 16);
-    return max(lo, hi) - 1;
+    for (int k = 0; k < 16; ++k) a[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+    unsigned b0 = __vimax3_u16x2(a[0], a[1], a[2]), b1 = __vimax3_u16x2(a[3], a[4], a[5]);
+    unsigned b2 = __vimax3_u16x2(a[6], a[7], a[8]), b3 = __vimax3_u16x2(a[9], a[10], a[11]);
+    unsigned b4 = __vimax3_u16x2(a[12], a[13], a[14]);
+    b0 = __vimax3_u16x2(b0, b1, b2);
+    b3 = __vimax3_u16x2(b3, b4, a[15]);
+    b0 = __vmaxu2(b0, b3);
+    return (int)max(b0 & 0xffffu, b0 >> 16) - 257;
 }
 
 // per-byte (x > t) for t < 128: 0x80 in every byte that passes.  k = (0x7f - t) * 0x01010101
@@ -121,11 +127,15 @@ __device__ __forceinline__ unsigned gt_bytes2(unsigned x1, unsigned x2, unsigned
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Dynamic shared memory: [tile | score map | queue u16 | keypoint bit mask], sizes from FastSmem.
 __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
-                                                         const __grid_constant__ TmaMaps maps, int iniTh, int minTh) {
-    __shared__ __align__(128) uint8_t tile[kCellTileBytes + 64];
-    __shared__ __align__(16) uint8_t smap[kCellTileBytes + 64];
-    __shared__ unsigned short queue[kCellQueue];
+                                                         const __grid_constant__ TmaMaps maps, const FastSmem sm,
+                                                         int iniTh, int minTh) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    uint8_t* tile = s_dyn;
+    uint8_t* smap = s_dyn + sm.offMap;
+    unsigned short* queue = reinterpret_cast<unsigned short*>(s_dyn + sm.offQueue);
+    unsigned* kmask = reinterpret_cast<unsigned*>(s_dyn + sm.offMask);
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_q, s_cnt, s_base;
     __shared__ int s_wsum[4];
@@ -157,7 +167,10 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const int iw = cw - 6, ih = ch - 6;
     for (int i = tid; i < (pitch * L.boxH + 64) / 16; i += 128) reinterpret_cast<uint4*>(smap)[i] = make_uint4(0, 0, 0, 0);
+    const int nmask = (iw * ih + 31) >> 5;
+    for (int i = tid; i < nmask; i += 128) kmask[i] = 0u;
     __syncthreads();
     if (tid == 0) {
         const unsigned bytes = (unsigned)(pitch * L.boxH);
@@ -179,82 +192,91 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
         }
     }
 
-    const int iw = cw - 6, ih = ch - 6;
     const int c_lo = o + 4, c_hi = o + 4 + iw;      // interior tile columns [c_lo, c_hi)
     const int gx0 = c_lo >> 2;
     const int ngx = ((c_hi - 1) >> 2) - gx0 + 1, ngroups = ngx * ih;
+    const unsigned magicG = 0xFFFFFFFFu / (unsigned)ngx + 1u;      // exact floor(n / ngx) for n < 65536
+    const unsigned magicW = 0xFFFFFFFFu / (unsigned)iw + 1u;
     const unsigned* tile32 = reinterpret_cast<const unsigned*>(tile);
-    const unsigned* smap32 = reinterpret_cast<const unsigned*>(smap);
     const int pw = pitch >> 2;
-
-    // strict 3x3 local maxima of one 4-px group of the score map with score >= th; bit b = pixel b
-    auto group_maxima = [&](int gi, int th) -> unsigned {
-        const int yy = gi / ngx, gx = gi - yy * ngx;
-        const int widx = (yy + 3) * pw + gx0 + gx;
-        const unsigned w = smap32[widx];
-        if (w == 0u) return 0u;
-        unsigned flags = 0;
-        const uint8_t* m = smap + widx * 4;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int s = (w >> (8 * b)) & 0xff;
-            if (s >= th && s > 0) {
-                const uint8_t* q = m + b;
-                if (s > q[-1] && s > q[1] && s > q[-pitch - 1] && s > q[-pitch] && s > q[-pitch + 1] && s > q[pitch - 1] &&
-                    s > q[pitch] && s > q[pitch + 1])
-                    flags |= 1u << b;
-            }
-        }
-        return flags;
-    };
 
     int th = iniTh, total = 0;
     for (int pass = 0; pass < 2; ++pass) {
         th = pass == 0 ? iniTh : minTh;
         if (tid == 0) { s_q = 0; s_cnt = 0; }
         __syncthreads();
-        // stage A: antipodal-pair rejection on 4 pixels at a time (necessary condition for score >= th)
+        // stage A: antipodal-pair rejection on 4 pixels at a time (necessary condition for score >= th);
+        // survivors are queued as (row << 7 | column)
         const unsigned kk = (unsigned)(0x7f - min(th, 127)) * 0x01010101u;
-        for (int gi = tid; gi < ngroups; gi += 128) {
-            const int yy = gi / ngx, gx = gi - yy * ngx;
-            const int widx = (yy + 3) * pw + gx0 + gx;
-            const unsigned C = tile32[widx];
-            const int cb = 4 * (gx0 + gx);                           // tile column of byte 0
-            const int first = max(c_lo - cb, 0), last = min(c_hi - cb, 4);     // valid bytes [first, last)
-            unsigned alive = (0x80808080u >> (8 * (4 - last))) & (0x80808080u << (8 * first));
-            if (th < 128) {
-                const unsigned up = tile32[widx + 3 * pw], dn = tile32[widx - 3 * pw];
-                alive &= gt_bytes2(__vabsdiffu4(up, C), __vabsdiffu4(dn, C), kk);
-                if (alive) {
-                    const unsigned Lw = tile32[widx - 1], Rw = tile32[widx + 1];
-                    const unsigned left3 = __byte_perm(Lw, C, 0x4321), right3 = __byte_perm(C, Rw, 0x6543);
-                    alive &= gt_bytes2(__vabsdiffu4(left3, C), __vabsdiffu4(right3, C), kk);
+        for (int base = 0; base < ngroups; base += 128) {
+            const int gi = base + tid;
+            unsigned alive = 0;
+            int row = 0, cb = 0;
+            if (gi < ngroups) {
+                const int yy = (int)__umulhi((unsigned)gi, magicG), gx = gi - yy * ngx;
+                row = yy + 3;
+                const int widx = row * pw + gx0 + gx;
+                const unsigned C = tile32[widx];
+                cb = 4 * (gx0 + gx);                                     // tile column of byte 0
+                const int first = max(c_lo - cb, 0), last = min(c_hi - cb, 4);     // valid bytes [first, last)
+                alive = (0x80808080u >> (8 * (4 - last))) & (0x80808080u << (8 * first));
+                if (th < 128) {
+                    const unsigned up = tile32[widx + 3 * pw], dn = tile32[widx - 3 * pw];
+                    alive &= gt_bytes2(__vabsdiffu4(up, C), __vabsdiffu4(dn, C), kk);
+                    if (alive) {
+                        const unsigned Lw = tile32[widx - 1], Rw = tile32[widx + 1];
+                        const unsigned left3 = __byte_perm(Lw, C, 0x4321), right3 = __byte_perm(C, Rw, 0x6543);
+                        alive &= gt_bytes2(__vabsdiffu4(left3, C), __vabsdiffu4(right3, C), kk);
+                    }
                 }
             }
-            if (alive) {
+            if (__ballot_sync(0xffffffffu, alive != 0u)) {
                 const int n = __popc(alive);
-                int pos = atomicAdd(&s_q, n);
+                int incl = n;
+#pragma unroll
+                for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+                    if (lane >= ofs) incl += t;
+                }
+                int wbase = 0;
+                if (lane == 31) wbase = atomicAdd(&s_q, incl);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                int pos = wbase + incl - n;
                 while (alive) {
                     const int b = (__ffs(alive) - 1) >> 3;
                     alive &= alive - 1;
-                    queue[pos++] = (unsigned short)(widx * 4 + b);
+                    queue[pos++] = (unsigned short)((row << 7) | (cb + b));
                 }
             }
         }
         __syncthreads();
-        // stage B: exact score of the survivors, balanced over the CTA
+        // stage B: exact score of the survivors, balanced over the CTA; stage C: 3x3 non-max suppression of the
+        // scored pixels -> bit (row-major interior index) in kmask
         const int nq = s_q;
         for (int qi = tid; qi < nq; qi += 128) {
-            const int idx = queue[qi];
+            const int e = queue[qi];
+            const int idx = (e >> 7) * pitch + (e & 127);
             const int s = fast_score(tile + idx, pitch);
-            if (s >= th) smap[idx] = (uint8_t)s;
+            if (s >= th) smap[idx] = (uint8_t)s; else queue[qi] = 0xffffu;
         }
         __syncthreads();
-        // stage C: count the keypoints of cv::FAST(cell, th, nms=true)
+        for (int qi = tid; qi < nq; qi += 128) {
+            const int e = queue[qi];
+            if (e == 0xffff) continue;
+            const int row = e >> 7, col = e & 127;
+            const uint8_t* q = smap + row * pitch + col;
+            const int s = q[0];
+            if (s > q[-1] && s > q[1] && s > q[-pitch - 1] && s > q[-pitch] && s > q[-pitch + 1] && s > q[pitch - 1] &&
+                s > q[pitch] && s > q[pitch + 1]) {
+                const int bi = (row - 3) * iw + (col - c_lo);
+                atomicOr(&kmask[bi >> 5], 1u << (bi & 31));
+            }
+        }
+        __syncthreads();
         int cnt = 0;
-        for (int gi = tid; gi < ngroups; gi += 128) cnt += __popc(group_maxima(gi, th));
+        for (int i = tid; i < nmask; i += 128) cnt += __popc(kmask[i]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        for (int ofs = 16; ofs > 0; ofs >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, ofs);
         if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
         __syncthreads();
         total = s_cnt;
@@ -275,36 +297,33 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
     if (total == 0 || s_base < 0) return;
     RawRec* out = p.raw + (long long)f * g.rawPerFrame + L.rawOff + s_base;
 
-    // ordered (row-major) compaction
+    // ordered emit: bit order of kmask is the row-major order cv::FAST reports
     int run = 0;
-    for (int base = 0; base < ngroups; base += 128) {
-        const int gi = base + tid;
-        const unsigned flags = gi < ngroups ? group_maxima(gi, th) : 0u;
-        const int n = __popc(flags);
+    for (int base = 0; base < nmask; base += 128) {
+        const int wi = base + tid;
+        unsigned bits = wi < nmask ? kmask[wi] : 0u;
+        const int n = __popc(bits);
         int incl = n;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+        for (int ofs = 1; ofs < 32; ofs <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+            if (lane >= ofs) incl += t;
         }
         if (lane == 31) s_wsum[wid] = incl;
         __syncthreads();
         int wbase = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) { const int v = s_wsum[w]; if (w < wid) wbase += v; tot += v; }
-        if (flags) {
-            const int yy = gi / ngx, gx = gi - yy * ngx;
-            int pos = run + wbase + incl - n;
-            const uint8_t* m = smap + ((yy + 3) * pw + gx0 + gx) * 4;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (flags & (1u << b)) {
-                    RawRec r;
-                    r.x = (unsigned short)(4 * (gx0 + gx) + b - o - 1 + cj * L.wCell);   // :811-812, relative to (minBorderX, minBorderY)
-                    r.y = (unsigned short)(yy + 3 + ci * L.hCell);
-                    r.score = m[b]; r.pad = 0;
-                    out[pos++] = r;
-                }
+        int pos = run + wbase + incl - n;
+        while (bits) {
+            const int bi = wi * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int yy = (int)__umulhi((unsigned)bi, magicW), xx = bi - yy * iw;
+            RawRec r;
+            r.x = (unsigned short)(xx + 3 + cj * L.wCell);     // :811-812, relative to (minBorderX, minBorderY)
+            r.y = (unsigned short)(yy + 3 + ci * L.hCell);
+            r.score = smap[(yy + 3) * pitch + c_lo + xx]; r.pad = 0;
+            out[pos++] = r;
         }
         run += tot;
         __syncthreads();
@@ -774,8 +793,24 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
 
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
     cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
+    FastSmem sm{};
+    int tileBytes = 0, qcap = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        tileBytes = max(tileBytes, g.lv[l].boxW * g.lv[l].boxH + 64);
+        qcap = max(qcap, g.lv[l].wCell * g.lv[l].hCell);
+    }
+    tileBytes = (tileBytes + 127) / 128 * 128;
+    sm.offMap = tileBytes;
+    sm.offQueue = 2 * tileBytes;
+    sm.offMask = sm.offQueue + (qcap * 2 + 15) / 16 * 16;
+    sm.total = sm.offMask + ((qcap + 31) / 32) * 4 + 16;
+    static int attrSet = 0;
+    if (sm.total > attrSet) {
+        cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
+        attrSet = max(sm.total, 48 * 1024);
+    }
     dim3 grid(g.totalCells, B);
-    fast_cells_kernel<<<grid, 128, 0, s>>>(g, p, maps, iniTh, minTh);
+    fast_cells_kernel<<<grid, 128, sm.total, s>>>(g, p, maps, sm, iniTh, minTh);
     return 1;
 }
 
