@@ -105,7 +105,7 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
     g.nlevels = nl;
     const int rawPerKpx = ctx->prm.raw_keys_per_kpx > 0 ? ctx->prm.raw_keys_per_kpx : 125;
     long long off = 0, boff = 0;
-    int cellBase = 0, rawOff = 0, nodeOff = 0, kpOff = 0;
+    int cellBase = 0, rawOff = 0, nodeOff = 0, kpOff = 0, stripBase = 0;
     for (int l = 0; l < nl; ++l) {
         LevelGeom& L = g.lv[l];
         L.w = (int)lrintf((float)w * ctx->invScale[l]);
@@ -131,6 +131,8 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.boxH = L.hCell + 6;
         if (L.boxW * L.boxH > kCellTileBytes) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
         L.cellBase = cellBase;
+        L.blurStripBase = stripBase;
+        stripBase += (L.h + 27) / 28;          // kBlurRows
         cellBase += L.nCols * L.nRows;
         long long cap = ((long long)L.w * L.h * rawPerKpx + 999) / 1000 + 64;
         if (cap >= (1 << 19)) cap = (1 << 19) - 1;      // sort key packs count into 19 bits

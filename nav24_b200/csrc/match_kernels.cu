@@ -66,12 +66,67 @@ __device__ __forceinline__ bool cell_range(const MatchArgs& a, float x, float y,
     return true;
 }
 
-// One CTA per frame pair.
-__global__ void __launch_bounds__(256) match_window_kernel(const MatchArgs a) {
+// One CTA (1024 threads) per frame pair.  Dynamic shared memory (sizes in MatchSmem; 0 = that table stays
+// in global memory, the kernel is still exact): CSR cell starts | dist2 | m21 | active-query table | candidate pool.
+struct MatchSmem { int cells, n2, act, pool, total; };
+
+// evaluates the entries [s_col + ...) of up to 32 grid columns for one query; calls emit(j, dist, lane_has) in
+// the grid's iteration order, 32 candidates at a time.  All lanes of the warp must call it.
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const MatchArgs& a, const PairView& v, const int* cs, const int* items,
+                                                   int i1, F&& emit) {
+    const int lane = threadIdx.x & 31;
+    const int level1 = v.k1[i1].octave;
+    const float2 q = ud_of(v.k1, v.ud1, i1);
+    int cx0, cx1, cy0, cy1;
+    if (!cell_range(a, q.x, q.y, cx0, cx1, cy0, cy1)) return;
+    const uint4* dq = v.d1 + 2 * i1;
+    const uint4 qa = dq[0], qb = dq[1];
+    for (int cbase = cx0; cbase <= cx1; cbase += 32) {
+        const int ncol = min(32, cx1 - cbase + 1);
+        int s = 0, cnt = 0;
+        if (lane < ncol) {
+            s = cs[(cbase + lane) * a.grid.rows + cy0];
+            cnt = cs[(cbase + lane) * a.grid.rows + cy1 + 1] - s;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            int col = 0;
+            for (int k = 0; k < ncol; ++k) col += (t >= __shfl_sync(0xffffffffu, incl, k));
+            const int sc = __shfl_sync(0xffffffffu, s, col & 31), ic = __shfl_sync(0xffffffffu, incl, col & 31);
+            const int cc = __shfl_sync(0xffffffffu, cnt, col & 31);
+            int j = -1, d = 0;
+            if (t < T) {
+                const int jj = items[sc + (t - (ic - cc))];
+                const int oc = v.k2[jj].octave;
+                if (oc >= level1 && oc <= level1) {                  // minLevel = maxLevel = level1 (:124)
+                    const float2 pt = ud_of(v.k2, v.ud2, jj);
+                    if (fabsf(__fsub_rn(pt.x, q.x)) < a.window && fabsf(__fsub_rn(pt.y, q.y)) < a.window) {
+                        const uint4 ta = v.d2[2 * jj], tb = v.d2[2 * jj + 1];
+                        d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                            __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                        j = jj;
+                    }
+                }
+            }
+            emit(j, d);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, const MatchSmem sm) {
+    extern __shared__ int s_dynm[];
     __shared__ int s_scan[33];
     __shared__ int s_hist[kHisto];
     __shared__ int s_ind[3];
-    __shared__ int s_nm;
+    __shared__ int s_nm, s_nA, s_poolUsed;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
     const int pr = blockIdx.x;
     PairView v;
@@ -86,14 +141,17 @@ __global__ void __launch_bounds__(256) match_window_kernel(const MatchArgs a) {
         v.n2 = a.pairs ? a.n2[a.pairs[2 * pr + 1]] : a.n2[pr];
     }
     const int nCells = a.grid.cols * a.grid.rows;
-    int* cellOf = a.cellOf + (long long)pr * a.cap;
-    int* cellStart = a.cellStart + (long long)pr * (nCells + 1);
+    int* cellOf = a.cellOf + (long long)pr * a.cap;           // later reused as the active-query list
+    int* cellStart = sm.cells ? s_dynm : a.cellStart + (long long)pr * (nCells + 1);
     int* cellFill = a.cellFill + (long long)pr * nCells;
     int* items = a.cellItems + (long long)pr * a.cap;
     int* cand = a.cand + (long long)pr * a.cap * kCandCap;
     int* candCnt = a.candCnt + (long long)pr * a.cap;
-    int* dist2 = a.dist2 + (long long)pr * a.cap;
-    int* m21 = a.m21 + (long long)pr * a.cap;
+    const bool n2InSmem = sm.n2 >= v.n2 && sm.n2 > 0;
+    int* dist2 = n2InSmem ? s_dynm + sm.cells : a.dist2 + (long long)pr * a.cap;
+    int* m21 = n2InSmem ? s_dynm + sm.cells + sm.n2 : a.m21 + (long long)pr * a.cap;
+    int* s_act = s_dynm + sm.cells + 2 * sm.n2;                // [3][sm.act]: i1, pool offset, count
+    int* s_pool = s_act + 3 * sm.act;
     int* bins = a.bins + (long long)pr * a.cap;
     int* m12 = a.matches12 + (long long)pr * a.cap;
 
@@ -102,6 +160,7 @@ __global__ void __launch_bounds__(256) match_window_kernel(const MatchArgs a) {
     for (int j = tid; j < v.n2; j += nth) { dist2[j] = 0x7fffffff; m21[j] = -1; }
     for (int i = tid; i < v.n1; i += nth) { m12[i] = -1; bins[i] = -1; candCnt[i] = 0; }
     if (tid < kHisto) s_hist[tid] = 0;
+    if (tid == 0) { s_nA = 0; s_poolUsed = 0; }
     __syncthreads();
     for (int j = tid; j < v.n2; j += nth) {
         const float2 pt = ud_of(v.k2, v.ud2, j);
@@ -141,114 +200,92 @@ __global__ void __launch_bounds__(256) match_window_kernel(const MatchArgs a) {
     }
     __syncthreads();
 
-    // ---- phase A: per query, pruned candidate list in the grid's iteration order ------------------------
+    // ---- phase A: per query (one warp each), pruned candidate list in the grid's iteration order -----------
     // A candidate whose distance can neither be an accepted best (dist > TH_LOW) nor fail the ratio
     // test as second best ((float)dist*ratio > TH_LOW >= best) is equivalent to "no candidate".
     const float thLowF = (float)a.thLow;
     for (int i1 = wid; i1 < v.n1; i1 += nw) {
         if (v.k1[i1].octave > 0) continue;                       // :120-122
-        const int level1 = v.k1[i1].octave;
-        const float2 q = ud_of(v.k1, v.ud1, i1);
-        int cx0, cx1, cy0, cy1;
-        if (!cell_range(a, q.x, q.y, cx0, cx1, cy0, cy1)) continue;
-        const uint4* dq = v.d1 + 2 * i1;
         int cnt = 0;
-        for (int ix = cx0; ix <= cx1; ++ix) {
-            const int s = cellStart[ix * a.grid.rows + cy0], e = cellStart[ix * a.grid.rows + cy1 + 1];
-            for (int b = s; b < e; b += 32) {
-                const int idx = b + lane;
-                bool keep = false;
-                int packed = 0;
-                if (idx < e) {
-                    const int j = items[idx];
-                    const int oc = v.k2[j].octave;
-                    if (oc >= level1 && oc <= level1) {          // minLevel = maxLevel = level1 (:124)
-                        const float2 pt = ud_of(v.k2, v.ud2, j);
-                        if (fabsf(__fsub_rn(pt.x, q.x)) < a.window && fabsf(__fsub_rn(pt.y, q.y)) < a.window) {
-                            const int d = hamming256(dq, v.d2 + 2 * j);
-                            const bool prune = d > a.thLow && __fmul_rn((float)d, a.nnratio) > thLowF;
-                            keep = !prune;
-                            packed = (j << 9) | d;
-                        }
-                    }
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-                    if (pos < kCandCap) cand[(long long)i1 * kCandCap + pos] = packed;
-                }
-                cnt += __popc(bal);
+        for_each_candidate(a, v, cellStart, items, i1, [&](int j, int d) {
+            const bool keep = j >= 0 && !(d > a.thLow && __fmul_rn((float)d, a.nnratio) > thLowF);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+                if (pos < kCandCap) cand[(long long)i1 * kCandCap + pos] = (j << 9) | d;
             }
-        }
+            cnt += __popc(bal);
+        });
         if (lane == 0) candCnt[i1] = cnt;
+    }
+    __syncthreads();
+
+    // ---- ordered compaction of the active queries (+ their candidates into the shared pool) -----------------
+    int* actList = cellOf;      // global list of active i1 (always), shared table when it fits
+    {
+        int nA = 0, poolUsed = 0;
+        for (int base = 0; base < v.n1; base += nth) {
+            const int i1 = base + tid;
+            const int cnt = i1 < v.n1 ? candCnt[i1] : 0;
+            const int stored = (cnt > 0 && cnt <= kCandCap) ? cnt : 0;
+            int totA, totP;
+            const int exA = block_excl_scan_m(cnt > 0, &totA, s_scan);
+            const int exP = block_excl_scan_m(stored, &totP, s_scan);
+            if (cnt > 0) {
+                const int k = nA + exA;
+                actList[k] = i1;
+                if (k < sm.act) {
+                    const bool fits = poolUsed + exP + stored <= sm.pool;
+                    s_act[k] = i1; s_act[sm.act + k] = fits ? poolUsed + exP : -1; s_act[2 * sm.act + k] = cnt;
+                    if (fits)
+                        for (int c = 0; c < stored; ++c) s_pool[poolUsed + exP + c] = cand[(long long)i1 * kCandCap + c];
+                }
+            }
+            nA += totA; poolUsed += totP;
+        }
+        if (tid == 0) s_nA = nA;
     }
     __syncthreads();
 
     // ---- phase B: the sequential accept / steal scan over i1 (:114-187), one warp ------------------------
     if (wid == 0) {
-        for (int i1 = 0; i1 < v.n1; ++i1) {
-            const int cnt = candCnt[i1];
-            if (cnt == 0) continue;
+        const int nA = s_nA;
+        for (int k = 0; k < nA; ++k) {
+            int i1, cnt, off = -1;
+            if (k < sm.act) { i1 = s_act[k]; off = s_act[sm.act + k]; cnt = s_act[2 * sm.act + k]; }
+            else { i1 = actList[k]; cnt = candCnt[i1]; }
             int best = 0x7fffffff, best2 = 0x7fffffff, bestIdx = -1;
             if (cnt <= kCandCap) {
                 int d = 0x7fffffff, j = -1;
                 if (lane < cnt) {
-                    const int pk = cand[(long long)i1 * kCandCap + lane];
+                    const int pk = off >= 0 ? s_pool[off + lane] : cand[(long long)i1 * kCandCap + lane];
                     j = pk >> 9;
                     const int dd = pk & 511;
                     if (!(dist2[j] <= dd)) d = dd;               // :146
                 }
                 // first minimum in list order, then the second smallest of the multiset
-                int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
-                int kmin = key;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                const int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
+                const int kmin = __reduce_min_sync(0xffffffffu, key);
                 if (kmin != 0x7fffffff) {
                     const int bl = kmin & 31;
                     best = kmin >> 5;
                     bestIdx = __shfl_sync(0xffffffffu, j, bl);
-                    int d2 = (lane == bl) ? 0x7fffffff : d;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) d2 = min(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-                    best2 = d2;
+                    best2 = __reduce_min_sync(0xffffffffu, (lane == bl) ? 0x7fffffff : d);
                 }
             } else {
                 // exact slow path: re-enumerate every candidate of this query in order
-                const int level1 = v.k1[i1].octave;
-                const float2 q = ud_of(v.k1, v.ud1, i1);
-                int cx0, cx1, cy0, cy1;
-                cell_range(a, q.x, q.y, cx0, cx1, cy0, cy1);
-                const uint4* dq = v.d1 + 2 * i1;
-                for (int ix = cx0; ix <= cx1; ++ix) {
-                    const int s = cellStart[ix * a.grid.rows + cy0], e = cellStart[ix * a.grid.rows + cy1 + 1];
-                    for (int b = s; b < e; b += 32) {
-                        const int idx = b + lane;
-                        int d = 0x7fffffff, j = -1;
-                        if (idx < e) {
-                            j = items[idx];
-                            const int oc = v.k2[j].octave;
-                            if (oc >= level1 && oc <= level1) {
-                                const float2 pt = ud_of(v.k2, v.ud2, j);
-                                if (fabsf(__fsub_rn(pt.x, q.x)) < a.window && fabsf(__fsub_rn(pt.y, q.y)) < a.window) {
-                                    const int dd = hamming256(dq, v.d2 + 2 * j);
-                                    if (!(dist2[j] <= dd)) d = dd;
-                                }
-                            }
-                        }
-                        int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
-                        int kmin = key;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-                        if (kmin == 0x7fffffff) continue;
-                        const int bl = kmin & 31, cb = kmin >> 5;
-                        const int cj = __shfl_sync(0xffffffffu, j, bl);
-                        int d2 = (lane == bl) ? 0x7fffffff : d;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) d2 = min(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-                        if (cb < best) { best2 = min(best, d2); best = cb; bestIdx = cj; }
-                        else best2 = min(best2, cb);
-                    }
-                }
+                for_each_candidate(a, v, cellStart, items, i1, [&](int j, int dd) {
+                    int d = 0x7fffffff;
+                    if (j >= 0 && !(dist2[j] <= dd)) d = dd;
+                    const int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
+                    const int kmin = __reduce_min_sync(0xffffffffu, key);
+                    if (kmin == 0x7fffffff) return;
+                    const int bl = kmin & 31, cb = kmin >> 5;
+                    const int cj = __shfl_sync(0xffffffffu, j, bl);
+                    const int d2 = __reduce_min_sync(0xffffffffu, (lane == bl) ? 0x7fffffff : d);
+                    if (cb < best) { best2 = min(best, d2); best = cb; bestIdx = cj; }
+                    else best2 = min(best2, cb);
+                });
             }
             if (best <= a.thLow && (float)best < __fmul_rn((float)best2, a.nnratio)) {      // :161-163
                 if (lane == 0) {
@@ -356,7 +393,24 @@ __global__ void __launch_bounds__(128) bf_knn2_kernel(const uint4* __restrict__ 
 }  // namespace
 
 int launch_match_window(const MatchArgs& a, int P, cudaStream_t s) {
-    match_window_kernel<<<P, 256, 0, s>>>(a);
+    // shared-memory budget: CSR cell starts, dist2/m21, active-query table, candidate pool (each optional)
+    const int budget = 200 * 1024 / 4;      // ints
+    MatchSmem sm{};
+    const int nCells = a.grid.cols * a.grid.rows;
+    int used = 0;
+    if (nCells + 1 <= 40000) { sm.cells = (nCells + 1 + 3) & ~3; used += sm.cells; }
+    if (2 * a.cap <= budget - used - 4096) { sm.n2 = (a.cap + 3) & ~3; used += 2 * sm.n2; }
+    sm.act = min(max((budget - used) / 8, 0), (a.cap + 3) & ~3);
+    used += 3 * sm.act;
+    sm.pool = min(max(budget - used, 0), 8192);
+    used += sm.pool;
+    sm.total = used * 4;
+    static int attrSet = 0;
+    if (sm.total > attrSet) {
+        cudaFuncSetAttribute(match_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
+        attrSet = max(sm.total, 48 * 1024);
+    }
+    match_window_kernel<<<P, 1024, sm.total, s>>>(a, sm);
     return 1;
 }
 

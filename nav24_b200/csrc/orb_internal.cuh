@@ -27,6 +27,7 @@ struct LevelGeom {
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
     int boxW, boxH;          // TMA box of one FAST cell: 16*odd >= wCell+6+1+15 (bank-conflict-free row pitch) x (hCell+6)
     int cellBase;            // first cell id of this level inside the per-frame cell table
+    int blurStripBase;       // first row-strip index (blockIdx.y) of this level in blur_kernel
     int rawCap;              // raw-corner capacity of this level (records)
     int rawOff;              // record offset of the level inside one frame's raw slab
     // quadtree (:502-725)

@@ -643,34 +643,64 @@ __device__ __forceinline__ int reflect101(int v, int n) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, int l) {
-    __shared__ uint8_t s_src[22][72];
-    __shared__ unsigned short s_h[22][64];
+// One thread owns a 4-pixel-wide column strip of kBlurRows rows: per input row it forms the four horizontal
+// 7-tap sums with two DP4A each (coefficients (18,34,48,56 | 48,34,18,0)), keeps the last seven rows of sums
+// in registers and emits one 32-bit word of output per row.  All levels and frames in one launch.
+constexpr int kBlurRows = 28;
+
+__device__ __forceinline__ void blur_row_sums(const uint8_t* __restrict__ img, long long pitch, int w, int h, int y,
+                                              int x4, bool interior, unsigned out[4]) {
+    const int r = reflect101(y, h);
+    const uint8_t* row = img + (long long)r * pitch;
+    unsigned w0, w1, w2;
+    if (interior) {
+        const unsigned* rw = reinterpret_cast<const unsigned*>(row + x4);
+        w0 = __ldg(rw - 1); w1 = __ldg(rw); w2 = __ldg(rw + 1);
+    } else {
+        unsigned b[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) b[i] = row[reflect101(x4 - 4 + i, w)];
+        w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+    }
+    const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
+    out[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
+    out[1] = __dp4a(__byte_perm(w0, w1, 0x5432), K1, __dp4a(__byte_perm(w1, w2, 0x5432), K2, 0u));
+    out[2] = __dp4a(__byte_perm(w0, w1, 0x6543), K1, __dp4a(__byte_perm(w1, w2, 0x6543), K2, 0u));
+    out[3] = __dp4a(w1, K1, __dp4a(w2, K2, 0u));
+}
+
+__global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.y >= g.lv[l + 1].blurStripBase) ++l;
     const LevelGeom& L = g.lv[l];
-    const int f = blockIdx.z, x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
-    const int tid = threadIdx.x;
+    const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+    if (x4 >= L.w) return;
+    const int y0 = ((int)blockIdx.y - L.blurStripBase) * kBlurRows;
+    const int f = blockIdx.z;
     const long long pitch = level_pitch(g, p, l);
-    const uint8_t* src = level_ptr(g, p, f, l);
-    for (int idx = tid; idx < 22 * 70; idx += 256) {
-        const int yy = idx / 70, xx = idx - yy * 70;
-        const int sy = reflect101(y0 + yy - 3, L.h), sx = reflect101(x0 + xx - 3, L.w);
-        s_src[yy][xx] = src[(long long)sy * pitch + sx];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 22 * 64; idx += 256) {
-        const int yy = idx >> 6, xx = idx & 63;
-        const uint8_t* s = &s_src[yy][xx];
-        s_h[yy][xx] = (unsigned short)(18 * (s[0] + s[6]) + 34 * (s[1] + s[5]) + 48 * (s[2] + s[4]) + 56 * s[3]);
-    }
-    __syncthreads();
-    uint8_t* dst = p.blur + (long long)f * g.blurFrameBytes + L.boff;
-    for (int idx = tid; idx < 16 * 64; idx += 256) {
-        const int yy = idx >> 6, xx = idx & 63;
-        const int x = x0 + xx, y = y0 + yy;
-        if (x < L.w && y < L.h) {
-            const int v = 18 * (s_h[yy][xx] + s_h[yy + 6][xx]) + 34 * (s_h[yy + 1][xx] + s_h[yy + 5][xx]) +
-                          48 * (s_h[yy + 2][xx] + s_h[yy + 4][xx]) + 56 * s_h[yy + 3][xx];
-            dst[(long long)y * L.pitch + x] = (uint8_t)((v + 32768) >> 16);
+    const uint8_t* img = level_ptr(g, p, f, l);
+    uint8_t* dst = p.blur + (long long)f * g.blurFrameBytes + L.boff + x4;
+    const bool interior = (x4 >= 4) && (x4 + 8 <= L.w);
+    unsigned hr[7][4];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) blur_row_sums(img, pitch, L.w, L.h, y0 + s - 3, x4, interior, hr[s]);
+    for (int yy = 0; yy < kBlurRows; yy += 7) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+            const int y = y0 + yy + s;
+            if (y < L.h) {
+                blur_row_sums(img, pitch, L.w, L.h, y + 3, x4, interior, hr[(s + 6) % 7]);
+                unsigned word = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned v = 18u * (hr[s % 7][i] + hr[(s + 6) % 7][i]) + 34u * (hr[(s + 1) % 7][i] + hr[(s + 5) % 7][i]) +
+                                       48u * (hr[(s + 2) % 7][i] + hr[(s + 4) % 7][i]) + 56u * hr[(s + 3) % 7][i] + 32768u;
+                    word |= (v >> 16) << (8 * i);
+                }
+                *reinterpret_cast<unsigned*>(dst + (long long)y * L.pitch) = word;
+            }
         }
     }
 }
@@ -832,10 +862,11 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
 
 int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
     int n = 0;
-    for (int l = 0; l < g.nlevels; ++l) {
-        const LevelGeom& L = g.lv[l];
-        dim3 grid((L.w + 63) / 64, (L.h + 15) / 16, B);
-        blur_kernel<<<grid, 256, 0, s>>>(g, p, l);
+    {
+        const LevelGeom& T = g.lv[g.nlevels - 1];
+        const int strips = T.blurStripBase + (T.h + kBlurRows - 1) / kBlurRows;
+        dim3 grid((g.lv[0].w + 511) / 512, strips, B);
+        blur_kernel<<<grid, 128, 0, s>>>(g, p);
         ++n;
     }
     dim3 grid((g.kpPerFrame + 7) / 8, B);
