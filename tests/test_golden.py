@@ -1,0 +1,97 @@
+"""Known-answer tests against tests/golden/*.npz.
+
+The fixtures were produced by tools/gen_golden.py from the REAL OpenCV (cv2 4.13.0) driven like
+core/operators/objDetection/OP_FtDtOrbSlam.cpp (oracle/orb_ref_cv2.py).  They travel to the GPU box,
+cv2 does not.  CPU tests pin the C++ oracle to them; `-m gpu` tests pin the CUDA path (through the
+C ABI) to them.  Bit-exact everywhere; descriptors within the <= 0.1 % allowance of BASELINE.json.
+"""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import orb_oracle as oo
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+DESC_TOL = 1e-3
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def test_fixtures_present():
+    assert len(GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_golden(path):
+    g = np.load(path)
+    nf = int(g["n_features"]); frames = g["frames"]
+    H, W = frames.shape[1:]
+    dets = []
+    for f in range(len(frames)):
+        o = oo.OrbOracle(nf)
+        mono, k, d = o.detect(frames[f])
+        dets.append((k, d))
+        assert mono == int(g[f"f{f}_mono"])
+        assert k.tobytes() == g[f"f{f}_kps"].tobytes()
+        assert np.array_equal(d, g[f"f{f}_desc"])
+        for l in range(8):
+            assert np.array_equal(_sha(o.level(l)), g[f"f{f}_level_sha"][l]), f"level {l}"
+            assert len(o.raw(l)) == g[f"f{f}_raw_count"][l]
+            assert np.array_equal(_sha(o.raw(l)), g[f"f{f}_raw_sha"][l]), f"raw keys {l}"
+            b = o.blurred(l)
+            if b is not None:
+                assert np.array_equal(_sha(b), g[f"f{f}_blur_sha"][l]), f"blurred {l}"
+            assert len(o.level_kps(l)[0]) == g[f"f{f}_level_count"][l]
+        if f == 0:
+            assert np.array_equal(o.raw(6), g["f0_raw_l6"]) and np.array_equal(o.raw(7), g["f0_raw_l7"])
+            assert np.array_equal(o.level(7), g["f0_level7"])
+    if len(frames) > 1:
+        (k1, d1), (k2, d2) = dets
+        ud1 = np.stack([k1["x"], k1["y"]], 1); ud2 = np.stack([k2["x"], k2["y"]], 1)
+        assert np.array_equal(oo.match_window(k1, ud1, d1, k2, ud2, d2, oo.grid_for(W, H)), g["matches12"])
+        assert (g["matches12"] >= 0).sum() > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_golden(path, cuda_required):
+    from nav24_b200 import capi
+    g = np.load(path)
+    nf = int(g["n_features"]); frames = g["frames"]
+    H, W = frames.shape[1:]
+    ctx = capi.OrbContext(nf)
+    try:
+        n, mono, kps, desc = ctx.detect_batch(np.ascontiguousarray(frames))
+        bad = 0
+        for f in range(len(frames)):
+            assert mono[f] == int(g[f"f{f}_mono"])
+            assert n[f] == len(g[f"f{f}_kps"])
+            assert kps[f, :n[f]].tobytes() == g[f"f{f}_kps"].tobytes()
+            bad += int((desc[f, :n[f]] != g[f"f{f}_desc"]).any(axis=1).sum())
+            for l in range(8):
+                assert np.array_equal(_sha(ctx.level(f, l)), g[f"f{f}_level_sha"][l]), f"level {l}"
+                assert np.array_equal(_sha(ctx.raw_keys(f, l)), g[f"f{f}_raw_sha"][l]), f"raw keys {l}"
+                if g[f"f{f}_level_count"][l] > 0:
+                    assert np.array_equal(_sha(ctx.level(f, l, blurred=True)), g[f"f{f}_blur_sha"][l]), f"blurred {l}"
+                assert len(ctx.level_keypoints(f, l)) == g[f"f{f}_level_count"][l]
+        assert bad <= DESC_TOL * int(n.sum()), f"{bad} descriptors differ from the cv2 fixtures"
+        if len(frames) > 1:
+            m, nm = ctx.match_window_frames([(0, 1)], capi.grid_for(W, H))
+            if bad == 0:
+                assert np.array_equal(m[0, :n[0]], g["matches12"])
+            m2, _ = ctx.match_window_frames([(0, 1)], capi.grid_for(W, H), check_ori=False)
+            if bad == 0:
+                assert np.array_equal(m2[0, :n[0]], g["matches12_noori"])
+            d1 = g["f0_desc"][:400]; d2 = g["f1_desc"][:500]
+            for norm in (0, 1):
+                i0, i1, f0, f1, ps = ctx.match_bf_knn2(d1, d2, norm, 0.7)
+                assert np.array_equal(np.stack([i0, i1]), g[f"bf{norm}_idx"])
+                assert np.array_equal(np.stack([f0, f1]), g[f"bf{norm}_dist"])
+                assert np.array_equal(ps, g[f"bf{norm}_pass"])
+    finally:
+        ctx.close()
