@@ -249,10 +249,11 @@ def main():
     for hb, fr in zip(h_frames, sets_host):
         hb[...] = fr
     h_kps = capi.pinned_empty((F, cap), capi.KP_DTYPE); h_desc = capi.pinned_empty((F, cap, 32))
+    h_m = capi.pinned_empty((P, cap), np.int32)
 
     def step_e2e(i):
         nn, mm, _, _ = ctx.detect_batch(h_frames[i % 2], cap=cap, kps=h_kps, desc=h_desc)
-        mt, nmt = ctx.match_window_frames(pairs, grid)
+        mt, nmt = ctx.match_window_frames(pairs, grid, out=h_m)
         return nn, nmt
 
     for i in range(args.warmup):

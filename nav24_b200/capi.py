@@ -257,11 +257,15 @@ class OrbContext:
         self._check(self.L.nav24_match_window_frames(self.h, len(pairs), _p(pairs), C.byref(grid), window, nnratio, th_low,
                                                      int(check_ori), None, 0, None))
 
-    def match_window_frames(self, pairs, grid, window=100.0, nnratio=0.6, th_low=50, check_ori=True, want_matches=True):
+    def match_window_frames(self, pairs, grid, window=100.0, nnratio=0.6, th_low=50, check_ori=True, want_matches=True,
+                            out=None):
+        """out: optional preallocated int32 [P, max_keypoints] (e.g. pinned) receiving matches12."""
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         P = len(pairs)
         cap = self.max_keypoints()
-        m = np.full((P, cap), -1, np.int32) if want_matches else None
+        if out is not None:
+            assert out.dtype == np.int32 and out.shape == (P, cap)
+        m = out if out is not None else (np.full((P, cap), -1, np.int32) if want_matches else None)
         nm = np.zeros(P, np.int32)
         self._check(self.L.nav24_match_window_frames(self.h, P, _p(pairs), C.byref(grid), window, nnratio, th_low, int(check_ori),
                                                      _p(m), cap, _p(nm)))

@@ -48,7 +48,11 @@ struct nav24_orb {
     std::vector<float> scale, invScale;
     std::vector<int> quota;
     std::string err;
-    cudaStream_t stream = nullptr, copyStream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, copyStream = nullptr, outStream = nullptr;
+    std::vector<cudaEvent_t> evIn, evDone;      // per chunk of the host-buffer pipeline (no timing)
+    cudaEvent_t evJoin = nullptr;
+    int chunkFrames = 64;                      // frames per pipeline chunk of nav24_orb_detect_batch
+    int* hN = nullptr; int* hMono = nullptr; int* hErr = nullptr; int hCap = 0;   // pinned result scratch
     static constexpr int kEvRing = 64;
     cudaEvent_t evRing[kEvRing][5]{};
     long long evCalls = 0;      // pipeline runs since the last stage-sum reset
@@ -64,7 +68,7 @@ struct nav24_orb {
     TmaMaps maps{};
     int mapsB = 0;            // frame count the level>=1 maps were encoded for
     const void* mapsPyr = nullptr;
-    DevBuf bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
+    DevBuf bL0Tight, bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
         bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs;
     // matcher scratch
     DevBuf mK1, mK2, mU1, mU2, mD1, mD2, mN1, mN2, mCellOf, mCellStart, mCellFill, mCellItems, mCand, mCandCnt, mDist2,
@@ -72,6 +76,28 @@ struct nav24_orb {
     int lastB = 0;            // frames of the last detect call
     bool lastValid = false;
     int l0Pitch = 0;
+
+    cudaError_t ensure_events(int n) {
+        while ((int)evIn.size() < n) {
+            cudaEvent_t a, b;
+            cudaError_t e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            evIn.push_back(a); evDone.push_back(b);
+        }
+        return cudaSuccess;
+    }
+    cudaError_t ensure_host(int B) {
+        if (B <= hCap) return cudaSuccess;
+        if (hN) cudaFreeHost(hN);
+        hN = nullptr; hCap = 0;
+        const int want = B + B / 2 + 16;
+        cudaError_t e = cudaHostAlloc((void**)&hN, sizeof(int) * (2 * (size_t)want + 4), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        hMono = hN + want; hErr = hMono + want; hCap = want;
+        return cudaSuccess;
+    }
 
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
         err = what;
@@ -289,38 +315,66 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
     return NAV24_OK;
 }
 
-// enqueue the whole per-frame chain on ctx->stream; no host synchronisation
-int run_pipeline(nav24_orb* ctx, int B) {
+// pointers of the frames [f0, ...) of the workspace: every slab is [frame][...], so a chunk is an offset
+DevPtrs chunk_ptrs(const nav24_orb* ctx, int f0) {
     const FrameGeom& g = ctx->g;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), s));
-    ctx->ev = ctx->evRing[ctx->evCalls % nav24_orb::kEvRing];
-    ctx->evCalls++;
-    CK(cudaEventRecord(ctx->ev[0], s));
-    ctx->launches += launch_pyramid(g, ctx->p, ctx->tabs.data(), B, s);
-    CK(cudaEventRecord(ctx->ev[1], s));
-    {   // tensor maps: levels >= 1 live in the workspace, level 0 is the caller's (or the staging) buffer
-        if (ctx->mapsB != ctx->wsB || ctx->mapsPyr != ctx->p.pyr) {
-            for (int l = 1; l < g.nlevels; ++l) {
-                int rc = encode_level_map(ctx, &ctx->maps.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
-                                          g.lv[l].pitch, g.pyrFrameBytes, g.lv[l].boxW, g.lv[l].boxH);
-                if (rc != NAV24_OK) return rc;
-            }
-            ctx->mapsB = ctx->wsB; ctx->mapsPyr = ctx->p.pyr;
+    DevPtrs q = ctx->p;
+    const long long f = f0;
+    q.l0 += f * q.l0Frame; q.pyr += f * g.pyrFrameBytes; q.blur += f * g.blurFrameBytes;
+    q.cellInfo += f * g.totalCells; q.cellDst += f * g.totalCells;
+    q.rawCount += f * g.nlevels; q.levelCount += f * g.nlevels; q.rawTotal += f * g.nlevels;
+    q.raw += f * g.rawPerFrame; q.keys += f * g.rawPerFrame; q.nodeOfKey += f * g.rawPerFrame;
+    q.nodesA += f * g.nodesPerFrame; q.nodesB += f * g.nodesPerFrame; q.childCnt += 4 * f * g.nodesPerFrame;
+    q.nodeAux += f * g.nodesPerFrame; q.best += f * g.nodesPerFrame; q.sortRec += f * g.nodesPerFrame;
+    q.lkp += f * g.kpPerFrame; q.outKp += f * g.outCap; q.outDesc += f * g.outCap * 32;
+    q.nOut += f; q.monoOut += f;
+    q.frameBase = f0;
+    return q;
+}
+
+// (re)encode the tensor maps: levels >= 1 live in the workspace, level 0 is the caller's (or the staging) buffer
+int encode_maps(nav24_orb* ctx, int B) {
+    const FrameGeom& g = ctx->g;
+    if (ctx->mapsB != ctx->wsB || ctx->mapsPyr != ctx->p.pyr) {
+        for (int l = 1; l < g.nlevels; ++l) {
+            int rc = encode_level_map(ctx, &ctx->maps.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
+                                      g.lv[l].pitch, g.pyrFrameBytes, g.lv[l].boxW, g.lv[l].boxH);
+            if (rc != NAV24_OK) return rc;
         }
-        int rc = encode_level_map(ctx, &ctx->maps.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch,
-                                  B > 1 ? ctx->p.l0Frame : ctx->p.l0Pitch * g.lv[0].h, g.lv[0].boxW, g.lv[0].boxH);
-        if (rc != NAV24_OK) return rc;
+        ctx->mapsB = ctx->wsB; ctx->mapsPyr = ctx->p.pyr;
     }
-    ctx->launches += launch_fast(g, ctx->p, ctx->maps, B, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);
-    CK(cudaEventRecord(ctx->ev[2], s));
-    ctx->launches += launch_quadtree(g, ctx->p, B, s);
-    CK(cudaEventRecord(ctx->ev[3], s));
-    ctx->launches += launch_describe(g, ctx->p, B, s);
-    CK(cudaEventRecord(ctx->ev[4], s));
+    return encode_level_map(ctx, &ctx->maps.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch,
+                            B > 1 ? ctx->p.l0Frame : ctx->p.l0Pitch * g.lv[0].h, g.lv[0].boxW, g.lv[0].boxH);
+}
+
+// enqueue the per-frame chain for frames [f0, f0+C) on stream s; no host synchronisation.  With stages = true the
+// five stage events of this run are recorded (nav24_orb_stage_ms).
+int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
+    const FrameGeom& g = ctx->g;
+    const DevPtrs q = chunk_ptrs(ctx, f0);
+    if (stages) {
+        ctx->ev = ctx->evRing[ctx->evCalls % nav24_orb::kEvRing];
+        ctx->evCalls++;
+        CK(cudaEventRecord(ctx->ev[0], s));
+    }
+    ctx->launches += launch_pyramid(g, q, ctx->tabs.data(), C, s);
+    if (stages) CK(cudaEventRecord(ctx->ev[1], s));
+    ctx->launches += launch_fast(g, q, ctx->maps, C, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);
+    if (stages) CK(cudaEventRecord(ctx->ev[2], s));
+    ctx->launches += launch_quadtree(g, q, C, s);
+    if (stages) CK(cudaEventRecord(ctx->ev[3], s));
+    ctx->launches += launch_describe(g, q, C, s);
+    if (stages) CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaGetLastError());
-    ctx->lastB = B;
-    ctx->lastValid = true;
+    return NAV24_OK;
+}
+
+int decode_device_error(nav24_orb* ctx, int e) {
+    if (e & ERR_RAW_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "raw FAST corner buffer overflow (raise raw_keys_per_kpx)");
+    if (e & ERR_ROOT_RANGE) return ctx->fail(NAV24_E_GEOMETRY, "keypoint outside the quadtree roots");
+    if (e & ERR_NODE_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "quadtree node buffer overflow");
+    if (e & ERR_CELL_SIZE) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
+    if (e & ERR_KP_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "output keypoint buffer overflow");
     return NAV24_OK;
 }
 
@@ -328,12 +382,7 @@ int check_device_error(nav24_orb* ctx) {
     int e = 0;
     CK(cudaMemcpyAsync(&e, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (e & ERR_RAW_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "raw FAST corner buffer overflow (raise raw_keys_per_kpx)");
-    if (e & ERR_ROOT_RANGE) return ctx->fail(NAV24_E_GEOMETRY, "keypoint outside the quadtree roots");
-    if (e & ERR_NODE_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "quadtree node buffer overflow");
-    if (e & ERR_CELL_SIZE) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
-    if (e & ERR_KP_OVERFLOW) return ctx->fail(NAV24_E_OVERFLOW, "output keypoint buffer overflow");
-    return NAV24_OK;
+    return decode_device_error(ctx, e);
 }
 
 int fetch_results(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
@@ -389,8 +438,12 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
     for (int i = 1; i < nl; ++i) ctx->scale[i] = ctx->scale[i - 1] * ctx->scaleFactorD;
     for (int i = 0; i < nl; ++i) ctx->invScale[i] = 1.0f / ctx->scale[i];
     ctx->compute_quota(params->n_features);
+    if (const char* e = getenv("NAV24_CHUNK_FRAMES")) { const int v = atoi(e); if (v > 0) ctx->chunkFrames = v; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->outStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return NAV24_E_CUDA;
     }
@@ -404,7 +457,7 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&ctx->bL0, &ctx->bPyr, &ctx->bBlur, &ctx->bCell, &ctx->bCellDst, &ctx->bRawCount, &ctx->bRaw, &ctx->bKeys,
+    DevBuf* bufs[] = {&ctx->bL0Tight, &ctx->bL0, &ctx->bPyr, &ctx->bBlur, &ctx->bCell, &ctx->bCellDst, &ctx->bRawCount, &ctx->bRaw, &ctx->bKeys,
                       &ctx->bNodeOfKey, &ctx->bNodesA, &ctx->bNodesB, &ctx->bChild, &ctx->bAux, &ctx->bBest, &ctx->bSort,
                       &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
                       &ctx->bErr, &ctx->bTabs, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
@@ -414,8 +467,14 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (auto& r : ctx->evRing) for (auto& e : r) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->evT) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->evIn) cudaEventDestroy(e);
+    for (auto& e : ctx->evDone) cudaEventDestroy(e);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->hN) cudaFreeHost(ctx->hN);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->outStream) cudaStreamDestroy(ctx->outStream);
     delete ctx;
 }
 
@@ -462,7 +521,14 @@ int nav24_orb_detect_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames,
                                  d_gray + (size_t)f * frame_stride, stride, w, h, cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->p.l0 = (const uint8_t*)ctx->bL0.ptr; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
     }
-    return run_pipeline(ctx, n_frames);
+    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), ctx->stream));
+    rc = encode_maps(ctx, n_frames);
+    if (rc != NAV24_OK) return rc;
+    rc = run_pipeline(ctx, 0, n_frames, ctx->stream, true);
+    if (rc != NAV24_OK) return rc;
+    ctx->lastB = n_frames;
+    ctx->lastValid = true;
+    return NAV24_OK;
 }
 
 int nav24_orb_fetch(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
@@ -478,24 +544,83 @@ int nav24_orb_sync(nav24_orb* ctx) {
     return NAV24_OK;
 }
 
+// Host-buffer pipeline: the batch is cut into chunks of ctx->chunkFrames frames; chunk k's host->device copy
+// (copy stream), chunk k-1's kernels (two compute streams, alternating, so that the tail of one chunk overlaps the
+// head of the next) and chunk k-2's device->host copy of keypoints and descriptors (output stream) run
+// concurrently.  Contiguous host frames travel as ONE 1-D copy per chunk and are re-pitched on the device.
 int nav24_orb_detect_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int w, int h, size_t stride,
                            size_t frame_stride, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
     if (!ctx) return NAV24_E_BADARG;
     if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
     int rc = ensure_workspace(ctx, w, h, n_frames);
     if (rc != NAV24_OK) return rc;
+    const FrameGeom& g = ctx->g;
+    const int B = n_frames;
+    const bool tight = (stride == (size_t)w) && (B == 1 || frame_stride == stride * (size_t)h);
+    const size_t tightFrame = (size_t)w * h;
+    if (tight) CK(ctx->bL0Tight.ensure((size_t)ctx->wsB * tightFrame + 16));
     uint8_t* l0 = (uint8_t*)ctx->bL0.ptr;
-    if (frame_stride == stride * (size_t)h) {
-        CK(cudaMemcpy2DAsync(l0, ctx->l0Pitch, gray, stride, w, (size_t)h * n_frames, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        for (int f = 0; f < n_frames; ++f)
-            CK(cudaMemcpy2DAsync(l0 + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch, gray + (size_t)f * frame_stride, stride, w,
-                                 h, cudaMemcpyHostToDevice, ctx->stream));
-    }
     ctx->p.l0 = l0; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
-    rc = run_pipeline(ctx, n_frames);
+    rc = encode_maps(ctx, B);
     if (rc != NAV24_OK) return rc;
-    return fetch_results(ctx, kps, desc, cap, n_out, mono_out);
+    const int C = std::max(1, std::min(ctx->chunkFrames, B));
+    const int nChunks = (B + C - 1) / C;
+    CK(ctx->ensure_events(nChunks));
+    CK(ctx->ensure_host(B));
+    CK(cudaStreamSynchronize(ctx->stream));      // a previous asynchronous detect_device may still use the workspace
+    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), ctx->copyStream));
+    const int ccap = std::min(cap, g.outCap);
+    for (int k = 0; k < nChunks; ++k) {
+        const int f0 = k * C, c = std::min(C, B - f0);
+        cudaStream_t cs = (k & 1) ? ctx->stream2 : ctx->stream;
+        // host -> device
+        if (tight) {
+            CK(cudaMemcpyAsync((uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, gray + f0 * tightFrame, c * tightFrame,
+                               cudaMemcpyHostToDevice, ctx->copyStream));
+        } else {
+            for (int f = f0; f < f0 + c; ++f)
+                CK(cudaMemcpy2DAsync(l0 + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch, gray + (size_t)f * frame_stride, stride, w,
+                                     h, cudaMemcpyHostToDevice, ctx->copyStream));
+        }
+        CK(cudaEventRecord(ctx->evIn[k], ctx->copyStream));
+        // kernels
+        CK(cudaStreamWaitEvent(cs, ctx->evIn[k], 0));
+        if (tight)
+            ctx->launches += launch_repack((const uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, w, h,
+                                           l0 + (size_t)f0 * ctx->l0Pitch * h, ctx->l0Pitch, c, cs);
+        rc = run_pipeline(ctx, f0, c, cs, false);
+        if (rc != NAV24_OK) return rc;
+        CK(cudaEventRecord(ctx->evDone[k], cs));
+        // device -> host
+        CK(cudaStreamWaitEvent(ctx->outStream, ctx->evDone[k], 0));
+        CK(cudaMemcpyAsync(ctx->hN + f0, ctx->p.nOut + f0, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
+        CK(cudaMemcpyAsync(ctx->hMono + f0, ctx->p.monoOut + f0, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
+        if (kps && ccap > 0)
+            CK(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(nav24_kp), ctx->p.outKp + (size_t)f0 * g.outCap,
+                                 (size_t)g.outCap * sizeof(nav24_kp), (size_t)ccap * sizeof(nav24_kp), c, cudaMemcpyDeviceToHost,
+                                 ctx->outStream));
+        if (desc && ccap > 0)
+            CK(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, ctx->p.outDesc + (size_t)f0 * g.outCap * 32,
+                                 (size_t)g.outCap * 32, (size_t)ccap * 32, c, cudaMemcpyDeviceToHost, ctx->outStream));
+    }
+    CK(cudaMemcpyAsync(ctx->hErr, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
+    if (nChunks > 1) {      // later work on ctx->stream (matching) must see the chunks that ran on stream2
+        CK(cudaEventRecord(ctx->evJoin, ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+    }
+    CK(cudaStreamSynchronize(ctx->outStream));
+    ctx->lastB = B;
+    ctx->lastValid = true;
+    rc = decode_device_error(ctx, *ctx->hErr);
+    if (rc != NAV24_OK) { ctx->lastValid = false; return rc; }
+    bool small = false;
+    for (int f = 0; f < B; ++f) {
+        if (n_out) n_out[f] = ctx->hN[f];
+        if (mono_out) mono_out[f] = ctx->hMono[f];
+        if ((kps || desc) && ctx->hN[f] > cap) small = true;
+    }
+    if (small) return ctx->fail(NAV24_E_CAPACITY, "output capacity too small");
+    return NAV24_OK;
 }
 
 int nav24_orb_detect(nav24_orb* ctx, const uint8_t* gray, int w, int h, size_t stride, nav24_kp* kps, uint8_t* desc,

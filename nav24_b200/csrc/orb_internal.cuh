@@ -95,6 +95,7 @@ struct DevPtrs {
     uint8_t* outDesc;        // [B][outCap][32]
     int* nOut; int* monoOut; // [B]
     int* err;                // device error bits
+    int frameBase;           // first frame of this chunk inside the buffers the TMA maps were encoded over
 };
 
 struct TmaMaps { CUtensorMap m[kMaxLevels]; };   // one 3-D (x, y, frame) u8 tensor map per pyramid level
@@ -106,6 +107,8 @@ struct ResizeTab {           // per level >= 1: source offsets and 11-bit coeffi
 };
 
 // launchers (orb_kernels.cu); each returns the number of kernels launched
+// tight (pitch = w) host-order frames -> 16-byte aligned pitch (TMA needs it); returns 1
+int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s);
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, int B, cudaStream_t s);
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
