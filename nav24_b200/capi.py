@@ -11,7 +11,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnav24orb.so")
+LIB_PATH = os.environ.get("NAV24_LIB") or os.path.join(_HERE, "libnav24orb.so")     # NAV24_LIB: kernel-variant experiments
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nav24_orb.h")
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),

@@ -157,8 +157,8 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.boxH = L.hCell + 6;
         if (L.boxW * L.boxH > kCellTileBytes) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
         L.cellBase = cellBase;
-        L.blurStripBase = stripBase;
-        stripBase += (L.h + 27) / 28;          // kBlurRows
+        L.blurTileBase = stripBase;
+        stripBase += ((L.w + 127) / 128) * ((L.h + kBlurTileRows - 1) / kBlurTileRows);
         cellBase += L.nCols * L.nRows;
         long long cap = ((long long)L.w * L.h * rawPerKpx + 999) / 1000 + 64;
         if (cap >= (1 << 19)) cap = (1 << 19) - 1;      // sort key packs count into 19 bits
@@ -179,6 +179,7 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.patch = (float)(int)(31 * ctx->scale[l]);
     }
     g.totalCells = cellBase;
+    g.blurTiles = stripBase;
     g.rawPerFrame = rawOff;
     g.nodesPerFrame = nodeOff;
     g.kpPerFrame = kpOff;

@@ -11,6 +11,13 @@ namespace nav24 {
 constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;           // EDGE_THRESHOLD (OP_FtDtOrbSlam.cpp:14)
 constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
+#ifndef NAV24_BLUR_ROWS
+#define NAV24_BLUR_ROWS 35
+#endif
+#ifndef NAV24_BLUR_MINB
+#define NAV24_BLUR_MINB 6
+#endif
+constexpr int kBlurTileRows = NAV24_BLUR_ROWS;   // rows per warp tile of blur_kernel (multiple of 7)
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
 constexpr int kCellTileBytes = 112 * 76;  // TMA box: (16 x odd >= wCell+7+15) x (hCell+6) bytes (x start is 16-B aligned)
 constexpr int kCellQueue = 70 * 70 + 4;   // interior pixels of the largest cell
@@ -27,7 +34,7 @@ struct LevelGeom {
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
     int boxW, boxH;          // TMA box of one FAST cell: 16*odd >= wCell+6+1+15 (bank-conflict-free row pitch) x (hCell+6)
     int cellBase;            // first cell id of this level inside the per-frame cell table
-    int blurStripBase;       // first row-strip index (blockIdx.y) of this level in blur_kernel
+    int blurTileBase;        // first warp tile (128 px x kBlurTileRows rows) of this level in blur_kernel
     int rawCap;              // raw-corner capacity of this level (records)
     int rawOff;              // record offset of the level inside one frame's raw slab
     // quadtree (:502-725)
@@ -49,6 +56,7 @@ struct FrameGeom {
     int nodesPerFrame;
     int kpPerFrame;          // level-keypoint slab size (sum of kpCap)
     int outCap;              // output capacity per frame
+    int blurTiles;           // warp tiles of blur_kernel per frame
     long long pyrFrameBytes, blurFrameBytes;
     LevelGeom lv[kMaxLevels];
 };

@@ -669,63 +669,96 @@ __device__ __forceinline__ int reflect101(int v, int n) {
     return v;
 }
 
-// One thread owns a 4-pixel-wide column strip of kBlurRows rows: per input row it forms the four horizontal
-// 7-tap sums with two DP4A each (coefficients (18,34,48,56 | 48,34,18,0)), keeps the last seven rows of sums
-// in registers and emits one 32-bit word of output per row.  All levels and frames in one launch.
-constexpr int kBlurRows = 28;
+// One WARP owns a 128-pixel-wide, kBlurRows-high tile; lane i owns pixels [4i, 4i+4) of every row.  Per input
+// row a lane loads ONE aligned word, gets its neighbours' words by shuffle (lanes 0/31 load the halo word of the
+// adjacent tile), forms the four horizontal 7-tap sums with two DP4A each (coefficients (18,34,48,56 | 48,34,18,0)),
+// keeps the last seven rows of sums in registers and emits one 32-bit word of output per row.  Loads of seven rows
+// are issued back to back before they are consumed.  BORDER_REFLECT_101: rows by index math (uniform per warp);
+// the left edge by one PRMT; the right edge by PRMTs on the words of the two lanes to the left (selectors depend
+// only on w & 3), so no byte loads and no divergent code.  One code path, 7 row bodies: the body must stay small,
+// the first version of this kernel (two template paths, 34 KB of SASS) stalled on instruction fetch.
+// All levels and frames in one launch; the warp tiles of a frame are numbered level by level (blurTileBase).
+constexpr int kBlurRows = kBlurTileRows;
 
-__device__ __forceinline__ void blur_row_sums(const uint8_t* __restrict__ img, long long pitch, int w, int h, int y,
-                                              int x4, bool interior, unsigned out[4]) {
-    const int r = reflect101(y, h);
-    const uint8_t* row = img + (long long)r * pitch;
-    unsigned w0, w1, w2;
-    if (interior) {
-        const unsigned* rw = reinterpret_cast<const unsigned*>(row + x4);
-        w0 = __ldg(rw - 1); w1 = __ldg(rw); w2 = __ldg(rw + 1);
-    } else {
-        unsigned b[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) b[i] = row[reflect101(x4 - 4 + i, w)];
-        w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-        w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-        w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
-    }
-    const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
-    out[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
-    out[1] = __dp4a(__byte_perm(w0, w1, 0x5432), K1, __dp4a(__byte_perm(w1, w2, 0x5432), K2, 0u));
-    out[2] = __dp4a(__byte_perm(w0, w1, 0x6543), K1, __dp4a(__byte_perm(w1, w2, 0x6543), K2, 0u));
-    out[3] = __dp4a(w1, K1, __dp4a(w2, K2, 0u));
-}
-
-__global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+__global__ void __launch_bounds__(128, NAV24_BLUR_MINB) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= g.blurTiles) return;
     int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.y >= g.lv[l + 1].blurStripBase) ++l;
+    while (l + 1 < g.nlevels && t >= g.lv[l + 1].blurTileBase) ++l;
     const LevelGeom& L = g.lv[l];
-    const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
-    if (x4 >= L.w) return;
-    const int y0 = ((int)blockIdx.y - L.blurStripBase) * kBlurRows;
-    const int f = blockIdx.z;
+    const int w = L.w, h = L.h;
+    const int tilesX = (w + 127) >> 7;
+    const int tt = t - L.blurTileBase;
+    const int ty = tt / tilesX, tx = tt - ty * tilesX;
+    const int x4 = tx * 128 + lane * 4;
+    const int y0 = ty * kBlurRows, yEnd = min(y0 + kBlurRows, h);
     const long long pitch = level_pitch(g, p, l);
-    const uint8_t* img = level_ptr(g, p, f, l);
-    uint8_t* dst = p.blur + (long long)f * g.blurFrameBytes + L.boff + x4;
-    const bool interior = (x4 >= 4) && (x4 + 8 <= L.w);
+    const uint8_t* img = level_ptr(g, p, blockIdx.y, l) + x4;
+    uint8_t* dst = p.blur + (long long)blockIdx.y * g.blurFrameBytes + L.boff + x4;
+    const int dPitch = L.pitch;
+
+    const bool active = x4 < w;
+    const int lastWord = (w - 1) & ~3, valid = w - lastWord;            // valid bytes of the last word: 1..4
+    const bool edgeTile = tx * 128 + 128 >= lastWord;                   // warp-uniform: owns or borders the last word
+    const bool isLast = x4 == lastWord;
+    // warp-uniform and rare: the last word sits in lane 0 or 1 and its mirror reaches two words to the left of it, i.e.
+    // beyond lane 0's halo word.  Lane 31 (idle in such a tile) fetches that word into its halo register instead.
+    const bool needHm = edgeTile && valid <= 2 && lastWord - tx * 128 <= 4;
+    const bool haloL = lane == 0 && x4 > 0, haloR = lane == 31 && (x4 + 4 <= lastWord || needHm);
+    const int xh = haloL ? -4 : (needHm ? -8 - 124 : 4);
+    const bool fixHalo = lane == 31 && x4 + 4 == lastWord;
+    const unsigned selA = valid == 4 ? 0x7654u : valid == 3 ? 0x5654u : valid == 2 ? 0x3454u : 0x1234u;
+    const unsigned selB = (valid & 1) ? 0x0234u : 0x0456u;
+    unsigned half;
+    asm("mov.u32 %0, 32768;" : "=r"(half));      // kept in a register: IMAD has one immediate slot
+
     unsigned hr[7][4];
-#pragma unroll
-    for (int s = 0; s < 6; ++s) blur_row_sums(img, pitch, L.w, L.h, y0 + s - 3, x4, interior, hr[s]);
-    for (int yy = 0; yy < kBlurRows; yy += 7) {
+    for (int yy = y0 - 6; yy < yEnd; yy += 7) {
+        unsigned a[7], hl[7];
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
-            const int y = y0 + yy + s;
-            if (y < L.h) {
-                blur_row_sums(img, pitch, L.w, L.h, y + 3, x4, interior, hr[(s + 6) % 7]);
-                unsigned word = 0;
+            int r = min(yy + s + 3, yEnd + 2);
+            r = r < 0 ? -r : r;
+            r = r >= h ? 2 * h - 2 - r : r;
+            const uint8_t* rp = img + (long long)r * pitch;
+            a[s] = active ? __ldg(reinterpret_cast<const unsigned*>(rp)) : 0u;
+            hl[s] = (haloL || haloR) ? __ldg(reinterpret_cast<const unsigned*>(rp + xh)) : 0u;
+        }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const unsigned v = 18u * (hr[s % 7][i] + hr[(s + 6) % 7][i]) + 34u * (hr[(s + 1) % 7][i] + hr[(s + 5) % 7][i]) +
-                                       48u * (hr[(s + 2) % 7][i] + hr[(s + 4) % 7][i]) + 56u * hr[(s + 3) % 7][i] + 32768u;
-                    word |= (v >> 16) << (8 * i);
+        for (int s = 0; s < 7; ++s) {
+            const int y = yy + s;                   // output row; the row entering the window is y + 3
+            if (y >= yEnd) continue;                // uniform
+            unsigned w1 = a[s], halo = hl[s];
+            unsigned w0 = __shfl_up_sync(0xffffffffu, w1, 1);
+            if (lane == 0) w0 = x4 > 0 ? halo : __byte_perm(w1, w1, 0x1230);      // pixels -3,-2,-1 = 3,2,1
+            unsigned wm = 0u;
+            if (edgeTile) {
+                wm = __shfl_up_sync(0xffffffffu, w0, 1);
+                if (needHm) {
+                    const unsigned far = __shfl_sync(0xffffffffu, halo, 31);
+                    if (lane == 0) wm = far;
                 }
-                *reinterpret_cast<unsigned*>(dst + (long long)y * L.pitch) = word;
+                if (isLast) w1 = __byte_perm(w0, w1, selA);
+                if (fixHalo) halo = __byte_perm(w1, halo, selA);
+            }
+            unsigned w2 = __shfl_down_sync(0xffffffffu, w1, 1);
+            if (lane == 31) w2 = halo;
+            if (edgeTile && isLast) w2 = valid >= 3 ? __byte_perm(w0, w1, selB) : __byte_perm(wm, w0, selB);
+            unsigned* o = hr[(s + 6) % 7];
+            const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
+            o[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
+            o[1] = __dp4a(__byte_perm(w0, w1, 0x5432), K1, __dp4a(__byte_perm(w1, w2, 0x5432), K2, 0u));
+            o[2] = __dp4a(__byte_perm(w0, w1, 0x6543), K1, __dp4a(__byte_perm(w1, w2, 0x6543), K2, 0u));
+            o[3] = __dp4a(w1, K1, __dp4a(w2, K2, 0u));
+            if (y >= y0) {                          // uniform: the first six rows only fill the window
+                unsigned v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    v[i] = 18u * (hr[s % 7][i] + hr[(s + 6) % 7][i]) + (34u * (hr[(s + 1) % 7][i] + hr[(s + 5) % 7][i]) +
+                           (48u * (hr[(s + 2) % 7][i] + hr[(s + 4) % 7][i]) + (56u * hr[(s + 3) % 7][i] + half)));
+                const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+                if (active) *reinterpret_cast<unsigned*>(dst + (long long)y * dPitch) = word;
             }
         }
     }
@@ -895,9 +928,7 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
 int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
     int n = 0;
     {
-        const LevelGeom& T = g.lv[g.nlevels - 1];
-        const int strips = T.blurStripBase + (T.h + kBlurRows - 1) / kBlurRows;
-        dim3 grid((g.lv[0].w + 511) / 512, strips, B);
+        dim3 grid((g.blurTiles + 3) / 4, B);
         blur_kernel<<<grid, 128, 0, s>>>(g, p);
         ++n;
     }

@@ -73,6 +73,20 @@ def test_detect_parity(ctxs, H, W, nf, seed, low):
     print(f"descriptor mismatches {bad}/{n}")
 
 
+@pytest.mark.parametrize("W", [384, 385, 386, 387, 389, 390, 513, 514, 517, 518, 640 + 2, 640 + 5])
+def test_blur_right_edge_geometries(ctxs, W):
+    """Every (width mod 4) and the widths whose last word lands in lane 0/1 of a 128-px blur tile."""
+    ctx = _ctx(ctxs, 300)
+    img = synth(264, W, 1000 + W)
+    o = oo.OrbOracle(300); o.detect(img)
+    ctx.detect(img)
+    for l in range(8):
+        b = o.blurred(l)
+        if b is not None:
+            assert np.array_equal(ctx.level(0, l, blurred=True), b), f"blurred level {l} of width {W}"
+        assert np.array_equal(ctx.level(0, l), o.level(l)), f"pyramid level {l} of width {W}"
+
+
 def test_detect_strided_input_and_reuse(ctxs):
     ctx = _ctx(ctxs, 1000)
     big = synth(500, 800, 3)
