@@ -3,16 +3,14 @@
 // (paths relative to /root/reference/core/operators/objDetection/).  Integer work is bit-exact;
 // float work uses explicit round-to-nearest intrinsics so that nvcc cannot contract mul+add
 // into FMA (the reference is built without contraction).
+#include <algorithm>
+
 #include "orb_internal.cuh"
 #include "stdsort.cuh"
 
 namespace nav24 {
 
 namespace {
-
-__device__ const signed char kPattern[1024] = {
-#include "pattern_31.inc"
-};
 
 __device__ __forceinline__ const uint8_t* level_ptr(const FrameGeom& g, const DevPtrs& p, int f, int l) {
     return l == 0 ? p.l0 + (long long)f * p.l0Frame : p.pyr + (long long)f * g.pyrFrameBytes + g.lv[l].off;
@@ -79,33 +77,99 @@ __global__ void __launch_bounds__(256) repack_kernel(const uint8_t* __restrict__
 // ------------------------------------------------------------------------------------------
 // K1  pyramid level l-1 -> l.  cv::resize(INTER_LINEAR) on CV_8UC1 = 11-bit fixed-point separable
 // bilinear; replaces ComputePyramid (OP_FtDtOrbSlam.cpp:936-960).
-// One thread produces 4 horizontally adjacent destination pixels (one 32-bit store).
+// One thread owns 4 horizontally adjacent destination pixels of `rows` consecutive rows (8 at scale 1.2).  Per SOURCE row it
+// loads the three aligned words that cover its <= 8-byte source window, shifts the window to byte 0 (2 SHF), picks
+// each pixel's two taps with one PRMT (selectors are per-thread constants) and forms S[s]*a0 + S[s+1]*a1 with one
+// DP2A; the horizontally interpolated rows are kept in registers and reused by the next destination row (the
+// source row index advances by 1 or 2 per destination row, a warp-uniform choice).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) resize_kernel(const uint8_t* __restrict__ src, long long sPitch, long long sFrame,
+constexpr int kResizeSrcRows = 12;     // source rows whose words a thread keeps in flight
+
+__global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__ src, unsigned sPitch, long long sFrame,
                                                      int sw, int sh, uint8_t* __restrict__ dst, int dPitch,
-                                                     long long dFrame, int dw, int dh, ResizeTab t) {
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    if (x4 >= dw || y >= dh) return;
-    const int f = blockIdx.z;
-    const int sy0 = t.yofs[y];
-    const int sy1 = min(sy0 + 1, sh - 1);
-    const short2 b = t.yab[y];
-    const uint8_t* r0 = src + (long long)f * sFrame + (long long)sy0 * sPitch;
-    const uint8_t* r1 = src + (long long)f * sFrame + (long long)sy1 * sPitch;
-    unsigned out = 0;
+                                                     long long dFrame, int dw, int dh, int rows, ResizeTab t) {
+    const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    const int y0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * rows;
+    if (y0 >= dh) return;                                  // warp-uniform
+    const bool active = x4 < dw;
+    // per-thread horizontal constants
+    const int s0 = t.xofs[min(x4, dw - 1)];
+    const int sa = s0 & ~3;                                // aligned start of the source window
+    const unsigned shift = (unsigned)(s0 & 3) * 8u;
+    const int lastW = (sw - 1) & ~3;                       // words beyond the row are never read (their taps weigh 0)
+    const uint8_t* sp = src + (long long)blockIdx.z * sFrame;
+    const uint8_t* q0 = sp + sa;
+    const uint8_t* q1 = sp + min(sa + 4, lastW);
+    const uint8_t* q2 = sp + min(sa + 8, lastW);
+    unsigned sel[4], ab[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int x = min(x4 + k, dw - 1);
-        const int s0 = t.xofs[x];
-        const int s1 = min(s0 + 1, sw - 1);
-        const short2 a = t.xab[x];
-        const int h0 = (int)r0[s0] * a.x + (int)r0[s1] * a.y;
-        const int h1 = (int)r1[s0] * a.x + (int)r1[s1] * a.y;
-        const int v = (((b.x * (h0 >> 4)) >> 16) + ((b.y * (h1 >> 4)) >> 16) + 2) >> 2;
-        out |= (unsigned)(v & 0xff) << (8 * k);
+        const int d = t.xofs[x] - s0;                      // 0..5
+        sel[k] = (unsigned)d | ((unsigned)(d + 1) << 4);
+        ab[k] = *reinterpret_cast<const unsigned*>(t.xab + x);  // (a0, a1) as two u16 (both in [0, 2048])
     }
-    *reinterpret_cast<unsigned*>(dst + (long long)f * dFrame + (long long)y * dPitch + x4) = out;
+    uint8_t* dp = dst + (long long)blockIdx.z * dFrame + x4;
+
+    auto hsum = [&](unsigned w0, unsigned w1, unsigned w2, int h[4]) {     // horizontally interpolated row, >> 4
+        const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = (int)(__dp2a_lo(ab[k], __byte_perm(lo, hi, sel[k]), 0u) >> 4);
+    };
+    auto hrow = [&](int sy, int h[4]) {
+        const unsigned long long ro = (unsigned long long)((unsigned)min(sy, sh - 1)) * sPitch;
+        hsum(__ldg(reinterpret_cast<const unsigned*>(q0 + ro)), __ldg(reinterpret_cast<const unsigned*>(q1 + ro)),
+             __ldg(reinterpret_cast<const unsigned*>(q2 + ro)), h);
+    };
+    const int yEnd = min(y0 + rows, dh);
+    int y = y0;
+    auto emit = [&](int sy, const int top[4], const int bot[4]) {      // every destination row whose first tap is row sy
+        while (y < yEnd && t.yofs[y] == sy) {
+            const int bpair = *reinterpret_cast<const int*>(t.yab + y);
+            const int b0 = (short)(bpair & 0xffff), b1 = bpair >> 16;
+            unsigned v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (unsigned)((((b0 * top[k] + 0x20000) >> 16) + ((b1 * bot[k]) >> 16)) >> 2);
+            const unsigned out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+            if (active) *reinterpret_cast<unsigned*>(dp + (long long)y * dPitch) = out;
+            ++y;
+        }
+    };
+    // walk the SOURCE rows once: A/B alternate as (row sy, row sy+1); a destination row is emitted when both are there
+    int ha[4], hb[4];
+    const int syBase = t.yofs[y0];
+    const int nsrc = t.yofs[yEnd - 1] + 2 - syBase;        // warp-uniform
+    if (nsrc <= kResizeSrcRows) {
+        // the usual case: all loads of the tile are issued before the first use (the kernel is latency-bound otherwise)
+        unsigned W[kResizeSrcRows][3];
+#pragma unroll
+        for (int i = 0; i < kResizeSrcRows; ++i) {
+            const unsigned long long ro = (unsigned long long)((unsigned)min(syBase + min(i, nsrc - 1), sh - 1)) * sPitch;
+            W[i][0] = __ldg(reinterpret_cast<const unsigned*>(q0 + ro));
+            W[i][1] = __ldg(reinterpret_cast<const unsigned*>(q1 + ro));
+            W[i][2] = __ldg(reinterpret_cast<const unsigned*>(q2 + ro));
+        }
+        hsum(W[0][0], W[0][1], W[0][2], ha);
+#pragma unroll
+        for (int i = 1; i < kResizeSrcRows; ++i) {
+            if (y < yEnd) {                                // warp-uniform
+                if (i & 1) { hsum(W[i][0], W[i][1], W[i][2], hb); emit(syBase + i - 1, ha, hb); }
+                else       { hsum(W[i][0], W[i][1], W[i][2], ha); emit(syBase + i - 1, hb, ha); }
+            }
+        }
+    } else {
+        int sy = syBase;
+        hrow(sy, ha);
+        while (y < yEnd) {
+            hrow(sy + 1, hb);
+            emit(sy, ha, hb);
+            ++sy;
+            if (y >= yEnd) break;
+            hrow(sy + 1, ha);
+            emit(sy, hb, ha);
+            ++sy;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -793,9 +857,43 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+// volatile loads: ptxas keeps their order and therefore issues all of them before the first use, which is what a
+// latency-bound gather wants (left alone it interleaves loads and uses to save registers)
+__device__ __forceinline__ unsigned ldg_u32_now(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_u8_now(const uint8_t* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (int)v;
+}
+
+// umax[|v|] of the 31-px disc (OP_FtDtOrbSlam.cpp:484-499), a compile-time table so that the unrolled row loop
+// of the orientation carries static predicates
+__device__ __forceinline__ constexpr int umax_of(int av) {
+    constexpr int t[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    return t[av];
+}
+
+// rBRIEF pattern as floats, transposed for the warp: entry [j][lane] = (x0, y0, x1, y1) of test pair 8*lane + j, so that
+// the 32 lanes of one load read 512 consecutive bytes (lane-major order cost 32 L1 wavefronts per load instead of 4).
+struct PatternT { float v[8][32][4]; };
+constexpr PatternT make_pattern_t() {
+    constexpr int src[1024] = {
+#include "pattern_31.inc"
+    };
+    PatternT t{};
+    for (int lane = 0; lane < 32; ++lane)
+        for (int j = 0; j < 8; ++j)
+            for (int c = 0; c < 4; ++c) t.v[j][lane][c] = (float)src[(lane * 8 + j) * 4 + c];
+    return t;
+}
+__device__ const PatternT kPatternT = make_pattern_t();
 
 __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+    __shared__ unsigned s_patch[8][372];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int f = blockIdx.y;
@@ -808,21 +906,37 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ F
     LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + slot;
     const int cx = kp->x, cy = kp->y;
 
-    // orientation on the un-blurred level
-    const long long pitch = level_pitch(g, p, l);
-    const uint8_t* img = level_ptr(g, p, f, l) + (long long)cy * pitch + cx;
-    int m10 = 0, m01 = 0;
-    const int u = lane - 15;
-    if (lane < 31) {
-#pragma unroll 1
-        for (int v = -15; v <= 15; ++v) {
-            if (abs(u) <= c_umax[abs(v)]) {
-                const int val = img[(long long)v * pitch + u];
-                m10 += u * val;
-                m01 += v * val;
-            }
-        }
+    // issue the loads of the blurred 37 x 40 byte patch first (they do not depend on the angle): 12 words per lane
+    const int bp = L.pitch;
+    const int ax = (cx - 18) & ~3, align = (cx - 18) - ax;
+    const uint8_t* bl = p.blur + (long long)f * g.blurFrameBytes + L.boff + (long long)(cy - 18) * bp + ax;
+    unsigned pw[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const int idx = k * 32 + lane;                  // word idx of the 37 x 10 patch
+        const int r = idx / 10, c = idx - r * 10;
+        pw[k] = ldg_u32_now(reinterpret_cast<const unsigned*>(bl + (idx < 370 ? r * bp : 0)) + (idx < 370 ? c : 0));
     }
+
+    // orientation on the un-blurred level: lane u owns column u-15; all 31 row loads are in flight together
+    const int pitch = (int)level_pitch(g, p, l);
+    const uint8_t* img = level_ptr(g, p, f, l) + (long long)cy * pitch + cx;
+    // (every lane may load: |u| <= 16, |v| <= 15 stays inside the image because keypoints keep 19 px from the edges;
+    // pixels outside the disc are masked after the load, so the 31 loads carry no predicates and no branches)
+    int colsum = 0, m01 = 0;
+    const int u = lane - 15, au = abs(u);
+    const uint8_t* rp = img - 15 * pitch + u;
+    int px[31];
+#pragma unroll
+    for (int k = 0; k < 31; ++k) px[k] = ldg_u8_now(rp + k * pitch);
+#pragma unroll
+    for (int k = 0; k < 31; ++k) {
+        const int v = k - 15;
+        const int m = au <= umax_of(v < 0 ? -v : v) ? px[k] : 0;
+        colsum += m;
+        m01 += v * m;
+    }
+    int m10 = u * colsum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -833,18 +947,28 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ F
     // descriptor on the blurred level
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float ang = __fmul_rn(angle, factorPI);
-    const float a = cosf(ang), b = sinf(ang);
-    const uint8_t* bl = p.blur + (long long)f * g.blurFrameBytes + L.boff + (long long)cy * L.pitch + cx;
-    const signed char* pat = kPattern + lane * 32;
+    float a, b;
+    sincosf(ang, &b, &a);
+    // The 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38).  The warp stages that 37-row
+    // patch of the blurred level in shared memory with row-coalesced word loads (rows of 10 words starting at the
+    // aligned column ax <= cx-18) and gathers the samples from there: scattered byte gathers straight from global
+    // memory cost one L1 wavefront per touched line (~25 per load) and made this kernel L1-bound.
+    unsigned* patch = s_patch[threadIdx.x >> 5];
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+        if (k * 32 + lane < 370) patch[k * 32 + lane] = pw[k];
+    __syncwarp();
+    const uint8_t* pc = reinterpret_cast<const uint8_t*>(patch) + 18 * 40 + 18 + align;      // the keypoint
+    const float4* pat = reinterpret_cast<const float4*>(kPatternT.v) + lane;
     unsigned val = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = bl[(long long)r0 * L.pitch + q0], t1 = bl[(long long)r1 * L.pitch + q1];
+        const float4 q4 = __ldg(pat + j * 32);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q4.x, b), __fmul_rn(q4.y, a)));
+        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q4.x, a), __fmul_rn(q4.y, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q4.z, b), __fmul_rn(q4.w, a)));
+        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q4.z, a), __fmul_rn(q4.w, b)));
+        const int t0 = pc[r0 * 40 + q0], t1 = pc[r1 * 40 + q1];
         val |= (unsigned)(t0 < t1) << j;
     }
     const int dst = kp->dst;
@@ -876,11 +1000,14 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
         const LevelGeom& S = g.lv[l - 1];
         const LevelGeom& D = g.lv[l];
         const uint8_t* src = (l == 1) ? p.l0 : p.pyr + S.off;
-        const long long sPitch = (l == 1) ? p.l0Pitch : S.pitch;
+        const unsigned sPitch = (unsigned)((l == 1) ? p.l0Pitch : S.pitch);
         const long long sFrame = (l == 1) ? p.l0Frame : g.pyrFrameBytes;
-        dim3 grid((D.w + 127) / 128, (D.h + 7) / 8, B), block(32, 8);
-        resize_kernel<<<grid, block, 0, s>>>(src, sPitch, sFrame, S.w, S.h, p.pyr + D.off, D.pitch, g.pyrFrameBytes,
-                                             D.w, D.h, tabs[l]);
+        // destination rows per thread such that their source rows (rows * scale + 2) fit the in-flight window
+        const double sc = (double)S.h / D.h;
+        const int rows = std::max(1, std::min(8, (int)((kResizeSrcRows - 2) / sc)));
+        dim3 grid((D.w + 127) / 128, (D.h + 4 * rows - 1) / (4 * rows), B);
+        resize_kernel<<<grid, 128, 0, s>>>(src, sPitch, sFrame, S.w, S.h, p.pyr + D.off, D.pitch, g.pyrFrameBytes,
+                                             D.w, D.h, rows, tabs[l]);
         ++n;
     }
     return n;
