@@ -1,0 +1,274 @@
+// nav24_ops.hpp — C++ host side of the B200 ORB front end: the reference's operator interface for the hot path,
+// implemented on the C ABI of include/nav24_orb.h.
+//
+// The reference is compiled C++ (C++20, OpenCV containers).  OpenCV, Eigen and glog are not in this image, so this
+// header mirrors the reference classes with dependency-free stand-ins of the same names, argument meaning and
+// error behaviour; INTEGRATION.md shows the (shorter) subclasses a nav24 maintainer adds inside the real tree,
+// where Frame / KeyPoint2D / MatchedObs are the reference's own types.
+//
+//   reference class (core/...)                                      here
+//   OP::FtDt            operators/objDetection/OP_FtDt.hpp:14-29      OP::FtDt (same virtuals, same protected members)
+//   OP::FtDtOrbSlam     operators/objDetection/OP_FtDtOrbSlam.hpp     OP::FtDtOrbB200
+//   OP::FtAssoc         operators/objAssoc/OP_FtAssoc.hpp:15-22       OP::FtAssoc
+//   OP::FtAssocOrbSlam  operators/objAssoc/OP_FtAssocOrbSlam.hpp      OP::FtAssocB200
+//   OP::FtAssocOCV      operators/objAssoc/OP_FtAssoc.cpp:63-99       OP::FtAssocBfB200 (intended semantics)
+//   OB::KeyPoint2D      sensorData/observation/Point2D.hpp:37-69      OB::KeyPoint2D (cv::KeyPoint -> nav24_kp, Mat -> 32 B)
+//   OB::MatchedObs      sensorData/observation/MatchedFeatures.hpp    OB::MatchedObs
+//   FrameMonoGrid       dataTypes/frame/Frame.hpp:59-74               FrameMonoGrid (image view instead of ImagePtr)
+//   OB::FeatureGrid cfg sensorData/observation/FeatureGrid.cpp:100    FeatureGridCfg (explicit, not process-global)
+//
+// There is no CPU fallback: constructing FtDtOrbB200 without a CUDA device throws std::runtime_error.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nav24_orb.h"
+
+namespace NAV24 {
+
+namespace OB {
+
+struct Point2f { float x = 0, y = 0; };
+
+// = OB::KeyPoint2D: cv::KeyPoint + cloned 1x32 descriptor + the undistorted point (Point2D::mPointUd)
+class KeyPoint2D {
+public:
+    KeyPoint2D(const nav24_kp& kpt, const uint8_t* desc) : mKPt(kpt) {
+        std::memcpy(mDesc.data(), desc, 32);
+        mPoint = {kpt.x, kpt.y};
+        mPointUd = mPoint;
+    }
+    const nav24_kp& getKeyPoint() const { return mKPt; }
+    const std::array<uint8_t, 32>& getDescriptor() const { return mDesc; }
+    Point2f getPoint() const { return mPoint; }
+    Point2f getPointUd() const { return mPointUd; }
+    void setPointUd(const Point2f& p) { mPointUd = p; }      // Calibration::undistort writes this (Calibration.cpp:135-149)
+private:
+    nav24_kp mKPt;
+    std::array<uint8_t, 32> mDesc;
+    Point2f mPoint, mPointUd;
+};
+typedef std::shared_ptr<KeyPoint2D> ObsPtr;
+
+}  // namespace OB
+
+class FrameMonoGrid;
+typedef std::shared_ptr<FrameMonoGrid> FramePtr;
+
+namespace OB {
+// = OB::MatchedObs (MatchedFeatures.hpp:75-87): matches12 against a weakly referenced first frame
+struct MatchedObs {
+    int mnMatches = 0;
+    std::weak_ptr<FrameMonoGrid> mpMatchedFrame;
+    std::vector<int> mvMatches12;
+};
+typedef std::shared_ptr<MatchedObs> MatchedObsPtr;
+}  // namespace OB
+
+// FeatureGrid::setImageBounds (FeatureGrid.cpp:100-113) for an undistorted W x H image
+inline nav24_grid_cfg FeatureGridCfg(int W, int H, float minX, float maxX, float minY, float maxY) {
+    nav24_grid_cfg g;
+    g.cols = W / 10; g.rows = H / 10; g.min_x = minX; g.max_x = maxX; g.min_y = minY; g.max_y = maxY;
+    return g;
+}
+
+// = FrameMonoGrid (grey image + observations + matches); the image is a non-owning view like cv::Mat's header
+class FrameMonoGrid : public std::enable_shared_from_this<FrameMonoGrid> {
+public:
+    FrameMonoGrid(double ts, const uint8_t* gray, int w, int h, size_t stride) : mTs(ts), mImg(gray), mW(w), mH(h), mStride(stride) {}
+    double getTs() const { return mTs; }
+    const uint8_t* image() const { return mImg; }
+    int width() const { return mW; }
+    int height() const { return mH; }
+    size_t stride() const { return mStride; }
+    const std::vector<OB::ObsPtr>& getObservations() const { return mvpObservations; }
+    void setObservations(const std::vector<OB::ObsPtr>& v) { mvpObservations = v; }
+    void setMatches(const OB::MatchedObsPtr& m) { mpMatches12 = m; }
+    OB::MatchedObsPtr getMatches() const { return mpMatches12; }
+private:
+    double mTs;
+    const uint8_t* mImg;
+    int mW, mH;
+    size_t mStride;
+    std::vector<OB::ObsPtr> mvpObservations;
+    OB::MatchedObsPtr mpMatches12;
+};
+
+namespace OP {
+
+// ---- detector -------------------------------------------------------------------------------------------
+class FtDt {      // OP_FtDt.hpp:14-29
+public:
+    explicit FtDt(int nFt) : mnFeatures(nFt), mnIniNumFts(nFt) {}
+    virtual ~FtDt() = default;
+    virtual int detect(FramePtr& pFrame) = 0;
+    int getNumFeatures() const { return mnFeatures; }
+    void scaleNumFeatures(const float& scale) { this->setNumFeatures((int)(scale * mnIniNumFts)); }
+protected:
+    virtual void setNumFeatures(const int nFt) { mnFeatures = nFt; }
+    int mnFeatures;
+    const int mnIniNumFts;
+};
+typedef std::shared_ptr<FtDt> FtDtPtr;
+
+class FtDtOrbB200 : public FtDt {      // replaces FtDtOrbSlam (OP_FtDtOrbSlam.hpp:27-84)
+public:
+    // same argument list and defaults as FtDtOrbSlam's constructor / FtDt::create (OP_FtDt.cpp:31-48)
+    FtDtOrbB200(int nfeatures = 1000, float scaleFactor = 1.2f, int nlevels = 8, int iniThFAST = 20, int minThFAST = 7,
+                int device = 0)
+        : FtDt(nfeatures), mnLevels(nlevels) {
+        nav24_orb_params p{nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, 0};
+        const int rc = nav24_orb_create(&p, device, &mCtx);
+        if (rc != NAV24_OK) throw std::runtime_error("FtDtOrbB200: nav24_orb_create failed (" + std::to_string(rc) +
+                                                     "); a CUDA device is required, there is no CPU fallback");
+        mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
+        refreshTables();
+    }
+    ~FtDtOrbB200() override { nav24_orb_destroy(mCtx); }
+    FtDtOrbB200(const FtDtOrbB200&) = delete;
+    FtDtOrbB200& operator=(const FtDtOrbB200&) = delete;
+
+    // FtDtOrbSlam::detect (OP_FtDtOrbSlam.cpp:844-934): -1 on an empty image, otherwise monoIndex; replaces the
+    // frame's observations with freshly allocated KeyPoint2D objects in the reference's two-ended order.
+    int detect(FramePtr& pFrame) override {
+        if (!pFrame || !pFrame->image() || pFrame->width() <= 0 || pFrame->height() <= 0) return -1;
+        int cap = nav24_orb_max_keypoints(mCtx), n = 0;
+        mKps.resize(cap); mDesc.resize((size_t)cap * 32);
+        int rc = nav24_orb_detect(mCtx, pFrame->image(), pFrame->width(), pFrame->height(), pFrame->stride(), mKps.data(),
+                                  mDesc.data(), cap, &n);
+        if (rc == NAV24_E_CAPACITY) {
+            cap = n; mKps.resize(cap); mDesc.resize((size_t)cap * 32);
+            rc = nav24_orb_detect(mCtx, pFrame->image(), pFrame->width(), pFrame->height(), pFrame->stride(), mKps.data(),
+                                  mDesc.data(), cap, &n);
+        }
+        if (rc < 0) { mLastError = nav24_last_error_string(mCtx); return rc == NAV24_E_BADARG ? -1 : rc; }
+        std::vector<OB::ObsPtr> vpObservations(n);
+        for (int i = 0; i < n; i++) vpObservations[i] = std::make_shared<OB::KeyPoint2D>(mKps[i], &mDesc[(size_t)i * 32]);
+        pFrame->setObservations(vpObservations);
+        return rc;      // monoIndex
+    }
+
+    int GetLevels() const { return mnLevels; }
+    float GetScaleFactor() const { return mvScaleFactor.size() > 1 ? mvScaleFactor[1] : 1.f; }
+    const std::vector<float>& GetScaleFactors() const { return mvScaleFactor; }
+    const std::vector<float>& GetInverseScaleFactors() const { return mvInvScaleFactor; }
+    const std::vector<int>& GetFeaturesPerLevel() const { return mnFeaturesPerLevel; }
+    const std::string& lastError() const { return mLastError; }
+    nav24_orb* handle() { return mCtx; }
+
+protected:
+    void setNumFeatures(const int nFt) override {      // FtDtOrbSlam::setNumFeatures (OP_FtDtOrbSlam.cpp:962-976)
+        FtDt::setNumFeatures(nFt);
+        nav24_orb_set_num_features(mCtx, nFt);
+        refreshTables();
+    }
+    void refreshTables() { nav24_orb_get_tables(mCtx, mvScaleFactor.data(), mvInvScaleFactor.data(), mnFeaturesPerLevel.data()); }
+
+    nav24_orb* mCtx = nullptr;
+    int mnLevels;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor;
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<nav24_kp> mKps;
+    std::vector<uint8_t> mDesc;
+    std::string mLastError;
+};
+
+// ---- matchers -------------------------------------------------------------------------------------------
+class FtAssoc {      // OP_FtAssoc.hpp:15-22 (the FtTracks overload returns the match count; tracks stay host-side)
+public:
+    virtual ~FtAssoc() = default;
+    virtual void match(const FramePtr& pFrame1, const FramePtr& pFrame2) = 0;
+    virtual std::vector<int> matchV(const FramePtr& pFrame1, const FramePtr& pFrame2) = 0;
+};
+
+class FtAssocB200 : public FtAssoc {      // replaces FtAssocOrbSlam (OP_FtAssocOrbSlam.hpp:13-38)
+public:
+    // The reference keeps the grid configuration in process-global statics (FeatureGrid.cpp:15-18); here it is explicit.
+    FtAssocB200(const std::shared_ptr<FtDtOrbB200>& ctxOwner, const nav24_grid_cfg& grid, float nnratio = 0.6f,
+                bool checkOri = true)
+        : mpOwner(ctxOwner), mGrid(grid), mfNNratio(nnratio), mbCheckOrientation(checkOri), windowSize(100.f) {}
+
+    // FtAssocOrbSlam::matchV (OP_FtAssocOrbSlam.cpp:91-223): one int per observation of frame 1, -1 or an index into
+    // frame 2; {} if a frame is missing (the reference returns {} + LOG(WARNING) when f2 has no grid, :103-107).
+    std::vector<int> matchV(const FramePtr& pFrame1, const FramePtr& pFrame2) override {
+        if (!pFrame1 || !pFrame2) return {};
+        const auto& o1 = pFrame1->getObservations();
+        const auto& o2 = pFrame2->getObservations();
+        const int n1 = (int)o1.size(), n2 = (int)o2.size();
+        std::vector<int> matches12(n1, -1);
+        if (n1 == 0) return matches12;
+        pack(o1, mK1, mU1, mD1); pack(o2, mK2, mU2, mD2);
+        const int rc = nav24_match_window(mpOwner->handle(), mK1.data(), mU1.data(), mD1.data(), n1, mK2.data(), mU2.data(),
+                                          mD2.data(), n2, &mGrid, windowSize, mfNNratio, TH_LOW, mbCheckOrientation ? 1 : 0,
+                                          matches12.data());
+        if (rc < 0) return {};
+        return matches12;
+    }
+    // FtAssocOrbSlam::match(f1, f2) (:247-260): stores a MatchedObs (weak ref to f1) on f2
+    void match(const FramePtr& pFrame1, const FramePtr& pFrame2) override {
+        std::vector<int> matches12 = this->matchV(pFrame1, pFrame2);
+        int nMatches = 0;
+        for (const auto& m : matches12) nMatches += m >= 0;
+        auto pMatchedObs = std::make_shared<OB::MatchedObs>();
+        pMatchedObs->mnMatches = nMatches; pMatchedObs->mvMatches12 = matches12; pMatchedObs->mpMatchedFrame = pFrame1;
+        if (pFrame2) pFrame2->setMatches(pMatchedObs);
+    }
+    static constexpr int TH_LOW = 50, TH_HIGH = 100, HISTO_LENGTH = 30;      // OP_FtAssocOrbSlam.cpp:13-15
+
+private:
+    static void pack(const std::vector<OB::ObsPtr>& obs, std::vector<nav24_kp>& k, std::vector<float>& ud,
+                     std::vector<uint8_t>& d) {
+        const size_t n = obs.size();
+        k.resize(n); ud.resize(2 * n); d.resize(32 * n);
+        for (size_t i = 0; i < n; ++i) {
+            k[i] = obs[i]->getKeyPoint();
+            const OB::Point2f p = obs[i]->getPointUd();
+            ud[2 * i] = p.x; ud[2 * i + 1] = p.y;
+            std::memcpy(&d[32 * i], obs[i]->getDescriptor().data(), 32);
+        }
+    }
+    std::shared_ptr<FtDtOrbB200> mpOwner;
+    nav24_grid_cfg mGrid;
+    float mfNNratio;
+    bool mbCheckOrientation;
+    float windowSize;
+    std::vector<nav24_kp> mK1, mK2;
+    std::vector<float> mU1, mU2;
+    std::vector<uint8_t> mD1, mD2;
+};
+
+// Intended semantics of FtAssocOCV::match (OP_FtAssoc.cpp:63-99): kNN-2 + ratio 0.7, lowest train index wins ties.
+class FtAssocBfB200 {
+public:
+    explicit FtAssocBfB200(const std::shared_ptr<FtDtOrbB200>& ctxOwner, int norm = NAV24_NORM_L2_U8, float ratio = 0.7f)
+        : mpOwner(ctxOwner), mNorm(norm), mRatio(ratio) {}
+    std::vector<int> matchV(const FramePtr& f1, const FramePtr& f2) {
+        const auto& o1 = f1->getObservations();
+        const auto& o2 = f2->getObservations();
+        const int n1 = (int)o1.size(), n2 = (int)o2.size();
+        std::vector<uint8_t> d1(32 * (size_t)n1), d2(32 * (size_t)n2), pass(n1);
+        for (int i = 0; i < n1; ++i) std::memcpy(&d1[32 * (size_t)i], o1[i]->getDescriptor().data(), 32);
+        for (int i = 0; i < n2; ++i) std::memcpy(&d2[32 * (size_t)i], o2[i]->getDescriptor().data(), 32);
+        std::vector<int32_t> i0(n1), i1(n1);
+        std::vector<float> f0(n1), f1v(n1);
+        std::vector<int> m(n1, -1);
+        if (n1 == 0) return m;
+        if (nav24_match_bf_knn2(mpOwner->handle(), d1.data(), n1, d2.data(), n2, mNorm, mRatio, i0.data(), i1.data(), f0.data(),
+                                f1v.data(), pass.data()) < 0)
+            return {};
+        for (int i = 0; i < n1; ++i) if (pass[i]) m[i] = i0[i];
+        return m;
+    }
+private:
+    std::shared_ptr<FtDtOrbB200> mpOwner;
+    int mNorm;
+    float mRatio;
+};
+
+}  // namespace OP
+}  // namespace NAV24

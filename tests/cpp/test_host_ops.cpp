@@ -1,0 +1,61 @@
+// test_host_ops.cpp — drives the C++ host operators exactly like the reference's only caller does
+// (core/frontEnd/FE_SlamMonoV.cpp:104-122): per frame FtDt::detect, identity undistortion (pinhole), then
+// FtAssoc::match(firstFrame, currFrame); with scaleNumFeatures(5.f) before the first frame like initOperators (:247).
+// Input : raw file  [int32 n, h, w, nFeatures] + n*h*w bytes.   Output: raw file read back by tests/test_host_cpp.py
+//         per frame: int32 monoIndex, int32 nObs, nObs*(nav24_kp 28 B), nObs*32 B; then per frame>0: int32 n1, n1*int32.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../nav24_b200/host/nav24_ops.hpp"
+
+using namespace NAV24;
+
+int main(int argc, char** argv) {
+    if (argc < 3) { std::fprintf(stderr, "usage: %s in.raw out.raw [scaleNumFeatures]\n", argv[0]); return 2; }
+    FILE* fi = std::fopen(argv[1], "rb");
+    if (!fi) return 2;
+    int hdr[4];
+    if (std::fread(hdr, 4, 4, fi) != 4) return 2;
+    const int n = hdr[0], h = hdr[1], w = hdr[2], nf = hdr[3];
+    std::vector<uint8_t> img((size_t)n * h * w);
+    if (std::fread(img.data(), 1, img.size(), fi) != img.size()) return 2;
+    std::fclose(fi);
+
+    std::shared_ptr<OP::FtDtOrbB200> pOrbDetector;
+    try {
+        pOrbDetector = std::make_shared<OP::FtDtOrbB200>(nf, 1.2f, 8, 20, 7);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return 3;
+    }
+    if (argc > 3) pOrbDetector->scaleNumFeatures((float)std::atof(argv[3]));
+    OP::FtAssocB200 orbMatcher(pOrbDetector, FeatureGridCfg(w, h, 0.f, (float)w, 0.f, (float)h));
+
+    FILE* fo = std::fopen(argv[2], "wb");
+    std::vector<FramePtr> frames;
+    for (int f = 0; f < n; ++f) {
+        FramePtr pFrame = std::make_shared<FrameMonoGrid>(f * 0.05, img.data() + (size_t)f * h * w, w, h, (size_t)w);
+        const int mono = pOrbDetector->detect(pFrame);
+        const auto& obs = pFrame->getObservations();
+        const int nObs = (int)obs.size();
+        std::fwrite(&mono, 4, 1, fo); std::fwrite(&nObs, 4, 1, fo);
+        for (const auto& o : obs) std::fwrite(&o->getKeyPoint(), sizeof(nav24_kp), 1, fo);
+        for (const auto& o : obs) std::fwrite(o->getDescriptor().data(), 1, 32, fo);
+        frames.push_back(pFrame);
+    }
+    for (int f = 1; f < n; ++f) {
+        orbMatcher.match(frames[0], frames[f]);
+        const auto pm = frames[f]->getMatches();
+        const int n1 = (int)pm->mvMatches12.size();
+        std::fwrite(&n1, 4, 1, fo);
+        std::fwrite(pm->mvMatches12.data(), 4, n1, fo);
+        if (pm->mpMatchedFrame.lock() != frames[0]) return 4;
+    }
+    // error behaviour of detect(): -1 on an empty image (OP_FtDtOrbSlam.cpp:851-852)
+    FramePtr empty = std::make_shared<FrameMonoGrid>(0.0, nullptr, 0, 0, 0);
+    const int rcEmpty = pOrbDetector->detect(empty);
+    std::fwrite(&rcEmpty, 4, 1, fo);
+    std::fclose(fo);
+    return 0;
+}
