@@ -100,6 +100,24 @@ int nav24_orb_detect_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, in
  * fetched; the call returns after enqueueing (no host synchronisation). */
 int nav24_orb_detect_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames, int width, int height,
                             size_t stride_bytes, size_t frame_stride_bytes);
+/* Fused detect + window matching, the stereo / frame-to-frame form of the front end (FE_SlamMonoV.cpp:104-122 calls
+ * detect and then match on every frame).  pairs_ab = n_pairs x (a, b) frame indices of this batch; matching uses the
+ * keypoints as detected (identity undistortion, Pinhole.hpp:75-78).  The batch is processed in chunks on two compute
+ * streams: the latency-bound tail of one chunk (quadtree, the sequential part of the matcher) overlaps the head of
+ * the next, and in the host form the copies overlap the kernels.  Host form: synchronous, outputs as in
+ * nav24_orb_detect_batch plus matches12 [n_pairs][mcap] (mcap >= nav24_orb_max_keypoints) and n_matches [n_pairs]. */
+int nav24_orb_detect_match_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int width, int height,
+                                 size_t stride_bytes, size_t frame_stride_bytes, nav24_kp* kps, uint8_t* desc, int cap,
+                                 int* n_out, int* mono_out, int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid,
+                                 float window, float nnratio, int th_low, int check_ori, int32_t* matches12, int mcap,
+                                 int* n_matches);
+/* Device-resident form: frames in HBM (16-byte aligned base / strides required), returns after enqueueing; results
+ * stay on the device until nav24_orb_fetch / nav24_match_fetch. */
+int nav24_orb_detect_match_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames, int width, int height,
+                                  size_t stride_bytes, size_t frame_stride_bytes, int n_pairs, const int* pairs_ab,
+                                  const nav24_grid_cfg* grid, float window, float nnratio, int th_low, int check_ori);
+/* Waits for the last fused call and copies its matches out; returns the total number of matches. */
+int nav24_match_fetch(nav24_orb* ctx, int32_t* matches12, int mcap, int* n_matches);
 /* Waits for the last nav24_orb_detect_device and copies its results out. kps/desc may be NULL (counts only). */
 int nav24_orb_fetch(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out);
 int nav24_orb_sync(nav24_orb* ctx);
@@ -159,6 +177,12 @@ int nav24_match_window_frames(nav24_orb* ctx, int n_pairs, const int* pairs_ab, 
 #define NAV24_NORM_L2_U8 1
 int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm,
                         float ratio, int32_t* idx0, int32_t* idx1, float* dist0, float* dist1, uint8_t* pass);
+
+/* Test hook for the quadtree's "largest first" ordering (std::sort at OP_FtDtOrbSlam.cpp:646, comparator :358-373):
+ * sorts n records by key with the device restatement of libstdc++'s introsort and returns the permutation
+ * (perm[i] = original index of the record at sorted position i).  Equal keys are "equivalent": their order is
+ * whatever std::sort leaves, which the device code must reproduce exactly. */
+int nav24_debug_sort_u32(nav24_orb* ctx, const uint32_t* keys, int n, int32_t* perm);
 
 /* ---- memory helpers (so that a C/C++ host needs no CUDA headers) --------------------------- */
 int nav24_host_alloc(size_t bytes, void** out);   /* pinned host memory: makes detect_batch copies asynchronous */

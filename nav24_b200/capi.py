@@ -67,6 +67,12 @@ def lib():
     L.nav24_orb_detect_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, vp, vp]
     L.nav24_orb_detect_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t]
     L.nav24_orb_fetch.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    L.nav24_orb_detect_match_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp, vp, C.c_int, vp, vp,
+                                               C.c_int, vp, C.POINTER(GridCfg), C.c_float, C.c_float, C.c_int, C.c_int, vp,
+                                               C.c_int, vp]
+    L.nav24_orb_detect_match_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, vp,
+                                                C.POINTER(GridCfg), C.c_float, C.c_float, C.c_int, C.c_int]
+    L.nav24_match_fetch.argtypes = [vp, vp, C.c_int, vp]
     L.nav24_orb_sync.argtypes = [vp]
     L.nav24_orb_max_keypoints.argtypes = [vp]
     L.nav24_orb_get_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, ip, ip]
@@ -84,6 +90,7 @@ def lib():
     L.nav24_match_window_frames.argtypes = [vp, C.c_int, vp, C.POINTER(GridCfg), C.c_float, C.c_float, C.c_int, C.c_int, vp,
                                             C.c_int, vp]
     L.nav24_match_bf_knn2.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp]
+    L.nav24_debug_sort_u32.argtypes = [vp, vp, C.c_int, vp]
     L.nav24_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.nav24_host_free.argtypes = [vp]
     L.nav24_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -185,6 +192,42 @@ class OrbContext:
         self._check(rc)
         return n, mono, kps, desc
 
+    def detect_match_batch(self, frames, pairs, grid, cap=None, kps=None, desc=None, matches=None, window=100.0, nnratio=0.6,
+                           th_low=50, check_ori=True):
+        """Fused detect + window matching on host frames. Returns (n, mono, kps, desc, matches12[P,cap], n_matches[P])."""
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.strides[2] == 1
+        B, H, W = frames.shape
+        cap = cap or self.max_keypoints()
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        P = len(pairs)
+        kps = np.zeros((B, cap), KP_DTYPE) if kps is None else kps
+        desc = np.zeros((B, cap, 32), np.uint8) if desc is None else desc
+        mcap = max(cap, self.max_keypoints())
+        matches = np.full((max(P, 1), mcap), -1, np.int32) if matches is None else matches
+        n = np.zeros(B, np.int32); mono = np.zeros(B, np.int32); nm = np.zeros(max(P, 1), np.int32)
+        rc = self.L.nav24_orb_detect_match_batch(self.h, _p(frames), B, W, H, frames.strides[1], frames.strides[0], _p(kps),
+                                                 _p(desc), cap, _p(n), _p(mono), P, _p(pairs), C.byref(grid), window, nnratio,
+                                                 th_low, int(check_ori), _p(matches), matches.shape[1], _p(nm))
+        if rc == E_CAPACITY and cap < int(n.max()):
+            return self.detect_match_batch(frames, pairs, grid, cap=int(n.max()), window=window, nnratio=nnratio,
+                                           th_low=th_low, check_ori=check_ori)
+        self._check(rc)
+        return n, mono, kps, desc, matches[:P], nm[:P]
+
+    def detect_match_device(self, dptr, B, W, H, stride, frame_stride, pairs, grid, window=100.0, nnratio=0.6, th_low=50,
+                            check_ori=True):
+        """Enqueue only (device-resident frames); fetch with fetch() / match_fetch()."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self._check(self.L.nav24_orb_detect_match_device(self.h, C.c_void_p(dptr), B, W, H, stride, frame_stride, len(pairs),
+                                                         _p(pairs), C.byref(grid), window, nnratio, th_low, int(check_ori)))
+
+    def match_fetch(self, P, want_matches=True, out=None):
+        cap = self.max_keypoints()
+        m = out if out is not None else (np.full((P, cap), -1, np.int32) if want_matches else None)
+        nm = np.zeros(P, np.int32)
+        self._check(self.L.nav24_match_fetch(self.h, _p(m), cap, _p(nm)))
+        return m, nm
+
     def detect_device(self, dptr, B, W, H, stride, frame_stride):
         self._check(self.L.nav24_orb_detect_device(self.h, C.c_void_p(dptr), B, W, H, stride, frame_stride))
 
@@ -270,6 +313,12 @@ class OrbContext:
         self._check(self.L.nav24_match_window_frames(self.h, P, _p(pairs), C.byref(grid), window, nnratio, th_low, int(check_ori),
                                                      _p(m), cap, _p(nm)))
         return m, nm
+
+    def debug_sort(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint32)
+        perm = np.zeros(len(keys), np.int32)
+        self._check(self.L.nav24_debug_sort_u32(self.h, _p(keys), len(keys), _p(perm)))
+        return perm
 
     def match_bf_knn2(self, d1, d2, norm=NORM_HAMMING, ratio=0.7):
         d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)

@@ -50,8 +50,13 @@ struct nav24_orb {
     std::string err;
     cudaStream_t stream = nullptr, stream2 = nullptr, copyStream = nullptr, outStream = nullptr;
     std::vector<cudaEvent_t> evIn, evDone;      // per chunk of the host-buffer pipeline (no timing)
-    cudaEvent_t evJoin = nullptr;
-    int chunkFrames = 64;                      // frames per pipeline chunk of nav24_orb_detect_batch
+    cudaEvent_t evJoin = nullptr, evPrevEnd = nullptr, evPairs = nullptr;
+    bool prevEndValid = false;
+    unsigned long long prevSig = 0;           // (B, chunk, pairs) signature of the previous chunked call
+    int callParity = 0;                       // ping-pong index of the pair tables
+    int lastP = 0, lastMatchCap = 0;          // pairs / row capacity of the match results left on the device
+    int chunkFrames = 64;                      // frames per pipeline chunk of the host-buffer entry points
+    int residentChunk = 0;                     // 0 = whole batch in one chunk for device-resident frames
     int* hN = nullptr; int* hMono = nullptr; int* hErr = nullptr; int hCap = 0;   // pinned result scratch
     static constexpr int kEvRing = 64;
     cudaEvent_t evRing[kEvRing][5]{};
@@ -72,7 +77,7 @@ struct nav24_orb {
         bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs;
     // matcher scratch
     DevBuf mK1, mK2, mU1, mU2, mD1, mD2, mN1, mN2, mCellOf, mCellStart, mCellFill, mCellItems, mCand, mCandCnt, mDist2,
-        mM21, mBins, mMatches, mNMatches, mPairs, mI0, mI1, mF0, mF1, mPass;
+        mM21, mBins, mMatches, mNMatches, mPairs, mPairOrder, mI0, mI1, mF0, mF1, mPass;
     int lastB = 0;            // frames of the last detect call
     bool lastValid = false;
     int l0Pitch = 0;
@@ -382,6 +387,7 @@ int decode_device_error(nav24_orb* ctx, int e) {
 int check_device_error(nav24_orb* ctx) {
     int e = 0;
     CK(cudaMemcpyAsync(&e, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), ctx->stream));      // sticky until read
     CK(cudaStreamSynchronize(ctx->stream));
     return decode_device_error(ctx, e);
 }
@@ -414,6 +420,51 @@ int fetch_results(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_
 
 }  // namespace
 
+// ---- matchers ---------------------------------------------------------------------------------
+namespace {
+
+int ensure_match_scratch(nav24_orb* ctx, int P, int cap, const nav24_grid_cfg* grid) {
+    const size_t nCells = (size_t)grid->cols * grid->rows;
+    const size_t pc = (size_t)P * cap;
+    CK(ctx->mCellOf.ensure(pc * 4));
+    CK(ctx->mCellStart.ensure((size_t)P * (nCells + 1) * 4));
+    CK(ctx->mCellFill.ensure((size_t)P * nCells * 4));
+    CK(ctx->mCellItems.ensure(pc * 4));
+    CK(ctx->mCand.ensure(pc * 32 * 4));
+    CK(ctx->mCandCnt.ensure(pc * 4));
+    CK(ctx->mDist2.ensure(pc * 4));
+    CK(ctx->mM21.ensure(pc * 4));
+    CK(ctx->mBins.ensure(pc * 4));
+    CK(ctx->mMatches.ensure(pc * 4));
+    CK(ctx->mNMatches.ensure((size_t)P * 4));
+    return NAV24_OK;
+}
+
+void fill_match_args(nav24_orb* ctx, MatchArgs& a, const nav24_grid_cfg* grid, float window, float nnratio, int th_low,
+                     int check_ori, int cap) {
+    a.grid = *grid;
+    a.invW = (float)grid->cols / (grid->max_x - grid->min_x);      // FeatureGrid.cpp:110-111
+    a.invH = (float)grid->rows / (grid->max_y - grid->min_y);
+    a.window = window; a.nnratio = nnratio; a.thLow = th_low; a.checkOri = check_ori; a.cap = cap;
+    a.cellOf = (int*)ctx->mCellOf.ptr; a.cellStart = (int*)ctx->mCellStart.ptr; a.cellFill = (int*)ctx->mCellFill.ptr;
+    a.cellItems = (int*)ctx->mCellItems.ptr; a.cand = (int*)ctx->mCand.ptr; a.candCnt = (int*)ctx->mCandCnt.ptr; a.candCap = 32;
+    a.dist2 = (int*)ctx->mDist2.ptr; a.m21 = (int*)ctx->mM21.ptr; a.bins = (int*)ctx->mBins.ptr;
+    a.matches12 = (int*)ctx->mMatches.ptr; a.nMatches = (int*)ctx->mNMatches.ptr;
+}
+
+bool grid_ok(const nav24_grid_cfg* g) {
+    return g && g->cols > 0 && g->rows > 0 && g->max_x > g->min_x && g->max_y > g->min_y;
+}
+
+}  // namespace
+
+namespace {
+struct MatchPlan;
+int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, size_t stride, size_t frame_stride,
+                const MatchPlan* mp, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
+                int32_t* matches12, int mcap, int* n_matches, int chunkOverride = 0);
+}  // namespace
+
 // ==========================================================================================
 extern "C" {
 
@@ -440,11 +491,14 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
     for (int i = 0; i < nl; ++i) ctx->invScale[i] = 1.0f / ctx->scale[i];
     ctx->compute_quota(params->n_features);
     if (const char* e = getenv("NAV24_CHUNK_FRAMES")) { const int v = atoi(e); if (v > 0) ctx->chunkFrames = v; }
+    if (const char* e = getenv("NAV24_RESIDENT_CHUNK")) { const int v = atoi(e); if (v > 0) ctx->residentChunk = v; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->outStream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evPrevEnd, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evPairs, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return NAV24_E_CUDA;
     }
@@ -463,7 +517,7 @@ void nav24_orb_destroy(nav24_orb* ctx) {
                       &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
                       &ctx->bErr, &ctx->bTabs, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
                       &ctx->mN2, &ctx->mCellOf, &ctx->mCellStart, &ctx->mCellFill, &ctx->mCellItems, &ctx->mCand, &ctx->mCandCnt,
-                      &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mI0, &ctx->mI1,
+                      &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mPairOrder, &ctx->mI0, &ctx->mI1,
                       &ctx->mF0, &ctx->mF1, &ctx->mPass};
     for (DevBuf* b : bufs) b->release();
     for (auto& r : ctx->evRing) for (auto& e : r) if (e) cudaEventDestroy(e);
@@ -471,6 +525,8 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     for (auto& e : ctx->evIn) cudaEventDestroy(e);
     for (auto& e : ctx->evDone) cudaEventDestroy(e);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->evPrevEnd) cudaEventDestroy(ctx->evPrevEnd);
+    if (ctx->evPairs) cudaEventDestroy(ctx->evPairs);
     if (ctx->hN) cudaFreeHost(ctx->hN);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -522,14 +578,8 @@ int nav24_orb_detect_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames,
                                  d_gray + (size_t)f * frame_stride, stride, w, h, cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->p.l0 = (const uint8_t*)ctx->bL0.ptr; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
     }
-    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), ctx->stream));
-    rc = encode_maps(ctx, n_frames);
-    if (rc != NAV24_OK) return rc;
-    rc = run_pipeline(ctx, 0, n_frames, ctx->stream, true);
-    if (rc != NAV24_OK) return rc;
-    ctx->lastB = n_frames;
-    ctx->lastValid = true;
-    return NAV24_OK;
+    return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                       0, nullptr, /*one chunk, one stream, stage events*/ n_frames);
 }
 
 int nav24_orb_fetch(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
@@ -545,73 +595,155 @@ int nav24_orb_sync(nav24_orb* ctx) {
     return NAV24_OK;
 }
 
-// Host-buffer pipeline: the batch is cut into chunks of ctx->chunkFrames frames; chunk k's host->device copy
-// (copy stream), chunk k-1's kernels (two compute streams, alternating, so that the tail of one chunk overlaps the
-// head of the next) and chunk k-2's device->host copy of keypoints and descriptors (output stream) run
-// concurrently.  Contiguous host frames travel as ONE 1-D copy per chunk and are re-pitched on the device.
-int nav24_orb_detect_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int w, int h, size_t stride,
-                           size_t frame_stride, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
-    int rc = ensure_workspace(ctx, w, h, n_frames);
-    if (rc != NAV24_OK) return rc;
+}  // extern "C" (the chunked engine below is internal)
+
+namespace {
+
+struct MatchPlan {
+    int P; const int* pairs; const nav24_grid_cfg* grid; float window, nnratio; int thLow, checkOri;
+};
+
+// The chunked engine behind every batched entry point.  The batch is cut into chunks of ctx->chunkFrames frames.
+// Per chunk: [host->device copy on the copy stream] -> kernels on one of TWO compute streams (alternating, so the
+// latency-bound tail of one chunk — quadtree, the sequential part of the matcher — overlaps the issue-bound head of
+// the next) -> window matching of the pairs whose two frames lie in the chunk -> [device->host copy of keypoints and
+// descriptors on the output stream].  Pairs spanning two chunks are matched after the streams joined.
+//   hostGray != nullptr : frames come from host memory (one contiguous 1-D copy per chunk when rows are tight; the
+//                         device re-pitches them) and results go back to the host; the call synchronises once.
+//   hostGray == nullptr : frames are device-resident (ctx->p.l0 set by the caller); nothing is copied and the call
+//                         returns after enqueueing.
+int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, size_t stride, size_t frame_stride,
+                const MatchPlan* mp, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
+                int32_t* matches12, int mcap, int* n_matches, int chunkOverride) {
     const FrameGeom& g = ctx->g;
-    const int B = n_frames;
-    const bool tight = (stride == (size_t)w) && (B == 1 || frame_stride == stride * (size_t)h);
+    const bool fromHost = hostGray != nullptr;
+    const bool tight = fromHost && (stride == (size_t)w) && (B == 1 || frame_stride == stride * (size_t)h);
     const size_t tightFrame = (size_t)w * h;
-    if (tight) CK(ctx->bL0Tight.ensure((size_t)ctx->wsB * tightFrame + 16));
     uint8_t* l0 = (uint8_t*)ctx->bL0.ptr;
-    ctx->p.l0 = l0; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
-    rc = encode_maps(ctx, B);
+    if (fromHost) {
+        if (tight) CK(ctx->bL0Tight.ensure((size_t)ctx->wsB * tightFrame + 16));
+        ctx->p.l0 = l0; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
+    }
+    int rc = encode_maps(ctx, B);
     if (rc != NAV24_OK) return rc;
-    const int C = std::max(1, std::min(ctx->chunkFrames, B));
+    const int C = std::max(1, std::min(chunkOverride > 0 ? chunkOverride : ctx->chunkFrames, B));
     const int nChunks = (B + C - 1) / C;
     CK(ctx->ensure_events(nChunks));
     CK(ctx->ensure_host(B));
-    CK(cudaStreamSynchronize(ctx->stream));      // a previous asynchronous detect_device may still use the workspace
-    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), ctx->copyStream));
+    unsigned long long sig = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((unsigned long long)B); mix((unsigned long long)C); mix((unsigned long long)w); mix((unsigned long long)h);
+
+    // pairs grouped by chunk (pairs spanning chunks go last)
+    MatchArgs ma{};
+    std::vector<int> firstOfChunk(nChunks + 2, 0);
+    const int P = mp ? mp->P : 0;
+    if (P > 0) {
+        rc = ensure_match_scratch(ctx, P, g.outCap, mp->grid);
+        if (rc != NAV24_OK) return rc;
+        CK(ctx->mPairs.ensure((size_t)P * 16)); CK(ctx->mPairOrder.ensure((size_t)P * 8));      // two copies: ping-pong
+        ctx->callParity ^= 1;
+        int* dPairs = (int*)ctx->mPairs.ptr + (size_t)ctx->callParity * 2 * P;
+        int* dOrder = (int*)ctx->mPairOrder.ptr + (size_t)ctx->callParity * P;
+        std::vector<int> chunkOf(P), order(P);
+        for (int q = 0; q < 2 * P; ++q) mix((unsigned long long)(unsigned)mp->pairs[q]);
+        for (int q = 0; q < P; ++q) {
+            const int ca = mp->pairs[2 * q] / C, cb = mp->pairs[2 * q + 1] / C;
+            chunkOf[q] = ca == cb ? ca : nChunks;
+            firstOfChunk[chunkOf[q] + 1]++;
+        }
+        for (int c = 0; c <= nChunks; ++c) firstOfChunk[c + 1] += firstOfChunk[c];
+        std::vector<int> fill(firstOfChunk.begin(), firstOfChunk.end() - 1);
+        for (int q = 0; q < P; ++q) order[fill[chunkOf[q]]++] = q;
+        // (pageable sources: these two small copies return only after the data was staged, which is what we need)
+        CK(cudaMemcpyAsync(dPairs, mp->pairs, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+        CK(cudaMemcpyAsync(dOrder, order.data(), (size_t)P * 4, cudaMemcpyHostToDevice, ctx->copyStream));
+        fill_match_args(ctx, ma, mp->grid, mp->window, mp->nnratio, mp->thLow, mp->checkOri, g.outCap);
+        ma.k1 = ma.k2 = ctx->p.outKp; ma.ud1 = ma.ud2 = nullptr; ma.d1 = ma.d2 = ctx->p.outDesc;
+        ma.n1 = ma.n2 = ctx->p.nOut; ma.stride1 = ma.stride2 = g.outCap;
+        ma.pairs = dPairs; ma.pairOrder = dOrder;
+    }
+    const int nLate = P > 0 ? firstOfChunk[nChunks + 1] - firstOfChunk[nChunks] : 0;
+    if (nLate > 0) mix(0x9e3779b97f4a7c15ull);
+    if (fromHost) CK(cudaStreamSynchronize(ctx->stream));      // an earlier asynchronous call may still use the workspace
+    // The device error word is sticky: it is read and cleared by the synchronising calls, never by an asynchronous one
+    // (a memset here could race with kernels of the previous asynchronous call).
+    CK(cudaEventRecord(ctx->evPairs, ctx->copyStream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->evPairs, 0));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->evPairs, 0));
+    // stream2 may run ahead into this call only if every slab is touched by the same stream as in the previous call
+    // (same batch, chunking and pairs, and no pair spanning two chunks); otherwise it waits for the previous call's end
+    if (ctx->prevEndValid && (sig != ctx->prevSig || nLate > 0)) CK(cudaStreamWaitEvent(ctx->stream2, ctx->evPrevEnd, 0));
+    ctx->prevSig = sig;
     const int ccap = std::min(cap, g.outCap);
+    const bool stages = nChunks == 1;      // per-stage events only make sense un-overlapped
     for (int k = 0; k < nChunks; ++k) {
         const int f0 = k * C, c = std::min(C, B - f0);
         cudaStream_t cs = (k & 1) ? ctx->stream2 : ctx->stream;
-        // host -> device
-        if (tight) {
-            CK(cudaMemcpyAsync((uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, gray + f0 * tightFrame, c * tightFrame,
-                               cudaMemcpyHostToDevice, ctx->copyStream));
-        } else {
-            for (int f = f0; f < f0 + c; ++f)
-                CK(cudaMemcpy2DAsync(l0 + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch, gray + (size_t)f * frame_stride, stride, w,
-                                     h, cudaMemcpyHostToDevice, ctx->copyStream));
+        if (fromHost) {
+            if (tight) {
+                CK(cudaMemcpyAsync((uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, hostGray + f0 * tightFrame, c * tightFrame,
+                                   cudaMemcpyHostToDevice, ctx->copyStream));
+            } else {
+                for (int f = f0; f < f0 + c; ++f)
+                    CK(cudaMemcpy2DAsync(l0 + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch, hostGray + (size_t)f * frame_stride,
+                                         stride, w, h, cudaMemcpyHostToDevice, ctx->copyStream));
+            }
+            CK(cudaEventRecord(ctx->evIn[k], ctx->copyStream));
+            CK(cudaStreamWaitEvent(cs, ctx->evIn[k], 0));
+            if (tight)
+                ctx->launches += launch_repack((const uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, w, h,
+                                               l0 + (size_t)f0 * ctx->l0Pitch * h, ctx->l0Pitch, c, cs);
         }
-        CK(cudaEventRecord(ctx->evIn[k], ctx->copyStream));
-        // kernels
-        CK(cudaStreamWaitEvent(cs, ctx->evIn[k], 0));
-        if (tight)
-            ctx->launches += launch_repack((const uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, w, h,
-                                           l0 + (size_t)f0 * ctx->l0Pitch * h, ctx->l0Pitch, c, cs);
-        rc = run_pipeline(ctx, f0, c, cs, false);
+        rc = run_pipeline(ctx, f0, c, cs, stages);
         if (rc != NAV24_OK) return rc;
+        const int np = firstOfChunk[k + 1] - firstOfChunk[k];
+        if (np > 0) {
+            ma.pairBase = firstOfChunk[k];
+            ctx->launches += launch_match_window(ma, np, cs);
+        }
         CK(cudaEventRecord(ctx->evDone[k], cs));
-        // device -> host
-        CK(cudaStreamWaitEvent(ctx->outStream, ctx->evDone[k], 0));
-        CK(cudaMemcpyAsync(ctx->hN + f0, ctx->p.nOut + f0, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
-        CK(cudaMemcpyAsync(ctx->hMono + f0, ctx->p.monoOut + f0, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
-        if (kps && ccap > 0)
-            CK(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(nav24_kp), ctx->p.outKp + (size_t)f0 * g.outCap,
-                                 (size_t)g.outCap * sizeof(nav24_kp), (size_t)ccap * sizeof(nav24_kp), c, cudaMemcpyDeviceToHost,
-                                 ctx->outStream));
-        if (desc && ccap > 0)
-            CK(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, ctx->p.outDesc + (size_t)f0 * g.outCap * 32,
-                                 (size_t)g.outCap * 32, (size_t)ccap * 32, c, cudaMemcpyDeviceToHost, ctx->outStream));
+        if (fromHost) {
+            CK(cudaStreamWaitEvent(ctx->outStream, ctx->evDone[k], 0));
+            CK(cudaMemcpyAsync(ctx->hN + f0, ctx->p.nOut + f0, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
+            CK(cudaMemcpyAsync(ctx->hMono + f0, ctx->p.monoOut + f0, c * sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
+            if (kps && ccap > 0)
+                CK(cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(nav24_kp), ctx->p.outKp + (size_t)f0 * g.outCap,
+                                     (size_t)g.outCap * sizeof(nav24_kp), (size_t)ccap * sizeof(nav24_kp), c,
+                                     cudaMemcpyDeviceToHost, ctx->outStream));
+            if (desc && ccap > 0)
+                CK(cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, ctx->p.outDesc + (size_t)f0 * g.outCap * 32,
+                                     (size_t)g.outCap * 32, (size_t)ccap * 32, c, cudaMemcpyDeviceToHost, ctx->outStream));
+        }
     }
-    CK(cudaMemcpyAsync(ctx->hErr, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
-    if (nChunks > 1) {      // later work on ctx->stream (matching) must see the chunks that ran on stream2
+    if (nChunks > 1) {      // later work on ctx->stream must see the chunks that ran on stream2
         CK(cudaEventRecord(ctx->evJoin, ctx->stream2));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
     }
-    CK(cudaStreamSynchronize(ctx->outStream));
+    if (nLate > 0) {
+        ma.pairBase = firstOfChunk[nChunks];
+        ctx->launches += launch_match_window(ma, nLate, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->evPrevEnd, ctx->stream));
+    ctx->prevEndValid = true;
     ctx->lastB = B;
     ctx->lastValid = true;
+    ctx->lastP = P; ctx->lastMatchCap = g.outCap;
+    if (!fromHost) return NAV24_OK;
+
+    // host mode: bring the small tails back and synchronise once
+    CK(cudaStreamWaitEvent(ctx->outStream, ctx->evPrevEnd, 0));
+    CK(cudaMemcpyAsync(ctx->hErr, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
+    std::vector<int> nm(std::max(P, 1));
+    if (P > 0) {
+        if (matches12)
+            CK(cudaMemcpy2DAsync(matches12, (size_t)mcap * 4, ma.matches12, (size_t)g.outCap * 4,
+                                 (size_t)std::min(mcap, g.outCap) * 4, P, cudaMemcpyDeviceToHost, ctx->outStream));
+        CK(cudaMemcpyAsync(nm.data(), ma.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, ctx->outStream));
+    }
+    CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), ctx->outStream));
+    CK(cudaStreamSynchronize(ctx->outStream));
     rc = decode_device_error(ctx, *ctx->hErr);
     if (rc != NAV24_OK) { ctx->lastValid = false; return rc; }
     bool small = false;
@@ -620,8 +752,83 @@ int nav24_orb_detect_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, in
         if (mono_out) mono_out[f] = ctx->hMono[f];
         if ((kps || desc) && ctx->hN[f] > cap) small = true;
     }
+    for (int q = 0; q < P; ++q) if (n_matches) n_matches[q] = nm[q];
     if (small) return ctx->fail(NAV24_E_CAPACITY, "output capacity too small");
     return NAV24_OK;
+}
+
+int check_pairs(nav24_orb* ctx, int P, const int* pairs_ab, int B, const nav24_grid_cfg* grid) {
+    if (P < 0 || (P > 0 && (!pairs_ab || !grid_ok(grid)))) return ctx->fail(NAV24_E_BADARG, "bad matcher argument");
+    for (int q = 0; q < 2 * P; ++q)
+        if (pairs_ab[q] < 0 || pairs_ab[q] >= B) return ctx->fail(NAV24_E_BADARG, "frame index out of range");
+    return NAV24_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nav24_orb_detect_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int w, int h, size_t stride,
+                           size_t frame_stride, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+    int rc = ensure_workspace(ctx, w, h, n_frames);
+    if (rc != NAV24_OK) return rc;
+    return run_chunked(ctx, n_frames, w, h, gray, stride, frame_stride, nullptr, kps, desc, cap, n_out, mono_out, nullptr, 0,
+                       nullptr);
+}
+
+int nav24_orb_detect_match_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int w, int h, size_t stride,
+                                 size_t frame_stride, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
+                                 int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid, float window, float nnratio,
+                                 int th_low, int check_ori, int32_t* matches12, int mcap, int* n_matches) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+    int rc = check_pairs(ctx, n_pairs, pairs_ab, n_frames, grid);
+    if (rc != NAV24_OK) return rc;
+    rc = ensure_workspace(ctx, w, h, n_frames);
+    if (rc != NAV24_OK) return rc;
+    if (matches12 && mcap < ctx->g.outCap) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
+    MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
+    return run_chunked(ctx, n_frames, w, h, gray, stride, frame_stride, n_pairs > 0 ? &mp : nullptr, kps, desc, cap, n_out,
+                       mono_out, matches12, mcap, n_matches);
+}
+
+int nav24_orb_detect_match_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames, int w, int h, size_t stride,
+                                  size_t frame_stride, int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid,
+                                  float window, float nnratio, int th_low, int check_ori) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!d_gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+    if ((((uintptr_t)d_gray | stride | frame_stride) & 15) != 0)
+        return ctx->fail(NAV24_E_BADARG, "device frames need a 16-byte aligned base, row stride and frame stride");
+    int rc = check_pairs(ctx, n_pairs, pairs_ab, n_frames, grid);
+    if (rc != NAV24_OK) return rc;
+    rc = ensure_workspace(ctx, w, h, n_frames);
+    if (rc != NAV24_OK) return rc;
+    ctx->p.l0 = d_gray; ctx->p.l0Pitch = (long long)stride; ctx->p.l0Frame = (long long)frame_stride;
+    MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
+    // Device-resident frames need no copy overlap, and cutting the batch only shortens the latency-bound launches
+    // (quadtree, matcher) without making them cheaper: measured 3.24 ms/step as one chunk vs 3.47 ms in chunks of 64.
+    return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, n_pairs > 0 ? &mp : nullptr, nullptr, nullptr, 0,
+                       nullptr, nullptr, nullptr, 0, nullptr, ctx->residentChunk > 0 ? ctx->residentChunk : n_frames);
+}
+
+int nav24_match_fetch(nav24_orb* ctx, int32_t* matches12, int mcap, int* n_matches) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!ctx->lastValid || ctx->lastP <= 0) return ctx->fail(NAV24_E_BADARG, "no match results on the device");
+    cudaSetDevice(ctx->device);
+    const int P = ctx->lastP, oc = ctx->lastMatchCap;
+    if (matches12 && mcap < oc) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
+    cudaStream_t s = ctx->stream;
+    if (matches12)
+        CK(cudaMemcpy2DAsync(matches12, (size_t)mcap * 4, ctx->mMatches.ptr, (size_t)oc * 4, (size_t)oc * 4, P, cudaMemcpyDeviceToHost, s));
+    std::vector<int> nm(P);
+    CK(cudaMemcpyAsync(nm.data(), ctx->mNMatches.ptr, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    int rc = check_device_error(ctx);      // synchronises ctx->stream (which joined stream2)
+    if (rc != NAV24_OK) return rc;
+    int total = 0;
+    for (int q = 0; q < P; ++q) { if (n_matches) n_matches[q] = nm[q]; total += nm[q]; }
+    return total;
 }
 
 int nav24_orb_detect(nav24_orb* ctx, const uint8_t* gray, int w, int h, size_t stride, nav24_kp* kps, uint8_t* desc,
@@ -734,43 +941,6 @@ int nav24_orb_timer_stop(nav24_orb* ctx, float* ms) {
 
 }  // extern "C"
 
-// ---- matchers ---------------------------------------------------------------------------------
-namespace {
-
-int ensure_match_scratch(nav24_orb* ctx, int P, int cap, const nav24_grid_cfg* grid) {
-    const size_t nCells = (size_t)grid->cols * grid->rows;
-    const size_t pc = (size_t)P * cap;
-    CK(ctx->mCellOf.ensure(pc * 4));
-    CK(ctx->mCellStart.ensure((size_t)P * (nCells + 1) * 4));
-    CK(ctx->mCellFill.ensure((size_t)P * nCells * 4));
-    CK(ctx->mCellItems.ensure(pc * 4));
-    CK(ctx->mCand.ensure(pc * 32 * 4));
-    CK(ctx->mCandCnt.ensure(pc * 4));
-    CK(ctx->mDist2.ensure(pc * 4));
-    CK(ctx->mM21.ensure(pc * 4));
-    CK(ctx->mBins.ensure(pc * 4));
-    CK(ctx->mMatches.ensure(pc * 4));
-    CK(ctx->mNMatches.ensure((size_t)P * 4));
-    return NAV24_OK;
-}
-
-void fill_match_args(nav24_orb* ctx, MatchArgs& a, const nav24_grid_cfg* grid, float window, float nnratio, int th_low,
-                     int check_ori, int cap) {
-    a.grid = *grid;
-    a.invW = (float)grid->cols / (grid->max_x - grid->min_x);      // FeatureGrid.cpp:110-111
-    a.invH = (float)grid->rows / (grid->max_y - grid->min_y);
-    a.window = window; a.nnratio = nnratio; a.thLow = th_low; a.checkOri = check_ori; a.cap = cap;
-    a.cellOf = (int*)ctx->mCellOf.ptr; a.cellStart = (int*)ctx->mCellStart.ptr; a.cellFill = (int*)ctx->mCellFill.ptr;
-    a.cellItems = (int*)ctx->mCellItems.ptr; a.cand = (int*)ctx->mCand.ptr; a.candCnt = (int*)ctx->mCandCnt.ptr; a.candCap = 32;
-    a.dist2 = (int*)ctx->mDist2.ptr; a.m21 = (int*)ctx->mM21.ptr; a.bins = (int*)ctx->mBins.ptr;
-    a.matches12 = (int*)ctx->mMatches.ptr; a.nMatches = (int*)ctx->mNMatches.ptr;
-}
-
-bool grid_ok(const nav24_grid_cfg* g) {
-    return g && g->cols > 0 && g->rows > 0 && g->max_x > g->min_x && g->max_y > g->min_y;
-}
-
-}  // namespace
 
 extern "C" {
 
@@ -899,6 +1069,23 @@ int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t
     int np = 0;
     for (int i = 0; i < n1; ++i) np += pass[i];
     return np;
+}
+
+int nav24_debug_sort_u32(nav24_orb* ctx, const uint32_t* keys, int n, int32_t* perm) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!keys || !perm || n < 0) return ctx->fail(NAV24_E_BADARG, "bad argument");
+    if (n == 0) return NAV24_OK;
+    cudaSetDevice(ctx->device);
+    std::vector<unsigned long long> r(n);
+    for (int i = 0; i < n; ++i) r[i] = ((unsigned long long)keys[i] << 32) | (unsigned)i;
+    CK(ctx->mCand.ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(ctx->mCand.ptr, r.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (launch_debug_sort((unsigned long long*)ctx->mCand.ptr, n, ctx->stream) < 0) return ctx->fail(NAV24_E_CAPACITY, "too many records");
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(r.data(), ctx->mCand.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i) perm[i] = (int32_t)(r[i] & 0xffffffffu);
+    return NAV24_OK;
 }
 
 int nav24_host_alloc(size_t bytes, void** out) {

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
     __shared__ int s_ind[3];
     __shared__ int s_nm, s_nA, s_poolUsed;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
-    const int pr = blockIdx.x;
+    const int pr = a.pairOrder ? a.pairOrder[a.pairBase + blockIdx.x] : a.pairBase + (int)blockIdx.x;
     PairView v;
     {
         long long o1, o2;

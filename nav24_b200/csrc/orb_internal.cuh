@@ -121,6 +121,7 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
 int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
+int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s);   // test hook (stdsort_warp.cuh)
 
 // matchers (match_kernels.cu)
 struct MatchArgs {
@@ -128,6 +129,8 @@ struct MatchArgs {
     const nav24_kp* k2; const float* ud2; const uint8_t* d2; const int* n2;
     long long stride1, stride2;    // element stride between pairs (keypoints); 0 with index lists
     const int* pairs;              // optional [P][2] frame indices into k1/k2 (same arrays), else null
+    const int* pairOrder;          // optional: launch block b handles pair pairOrder[pairBase + b] (chunked pipeline)
+    int pairBase;                  // first pair (or first entry of pairOrder) of this launch
     nav24_grid_cfg grid; float invW, invH;
     float window, nnratio; int thLow, checkOri;
     int cap;

@@ -6,7 +6,7 @@
 #include <algorithm>
 
 #include "orb_internal.cuh"
-#include "stdsort.cuh"
+#include "stdsort_warp.cuh"
 
 namespace nav24 {
 
@@ -573,7 +573,17 @@ __global__ void __launch_bounds__(256) quadtree_kernel(const __grid_constant__ F
                 sv = sortRec;
                 __syncthreads();
             }
-            if (tid == 0) stdsort::sort(sv, m);
+            if (m <= sortSmemCap) {     // one warp produces std::sort's exact permutation (stdsort_warp.cuh)
+                if (tid < 32) {
+                    unsigned short* sa = reinterpret_cast<unsigned short*>(s_sort + sortSmemCap);
+                    unsigned short* sb = sa + sortSmemCap;
+                    unsigned* bits = reinterpret_cast<unsigned*>(sb + sortSmemCap);
+                    int* stk = reinterpret_cast<int*>(bits + ((sortSmemCap + 31) >> 5));
+                    stdsort::sort_warp(sv, m, sa, sb, bits, stk);
+                }
+            } else if (tid == 0) {
+                stdsort::sort(sv, m);
+            }
             __syncthreads();
             // break point: first processed parent after which size >= N
             int runD = 0;
@@ -1036,11 +1046,38 @@ int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B
     return 1;
 }
 
+// records | two u16 position lists | leaf-start bit mask | range stack  (see stdsort_warp.cuh)
+static size_t quadtree_smem_bytes(int cap) { return (size_t)cap * 12 + (size_t)((cap + 31) / 32) * 4 + 192 * 4 + 16; }
+
+// test hook: std::sort of n records (key = high 32 bits) by one warp, in shared memory
+namespace {
+__global__ void __launch_bounds__(32) debug_sort_kernel(unsigned long long* recs, int n, int cap) {
+    extern __shared__ unsigned long long s_rec[];
+    for (int i = threadIdx.x; i < n; i += 32) s_rec[i] = recs[i];
+    __syncwarp();
+    unsigned short* sa = reinterpret_cast<unsigned short*>(s_rec + cap);
+    unsigned short* sb = sa + cap;
+    unsigned* bits = reinterpret_cast<unsigned*>(sb + cap);
+    int* stk = reinterpret_cast<int*>(bits + ((cap + 31) >> 5));
+    stdsort::sort_warp(s_rec, n, sa, sb, bits, stk);
+    for (int i = threadIdx.x; i < n; i += 32) recs[i] = s_rec[i];
+}
+}  // namespace
+
+int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s) {
+    const int cap = (n + 3) & ~3;
+    const size_t smem = quadtree_smem_bytes(cap);
+    if (smem > 200 * 1024) return -1;
+    cudaFuncSetAttribute(debug_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    debug_sort_kernel<<<1, 32, smem, s>>>(d_recs, n, cap);
+    return 1;
+}
+
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
     int maxNode = 0;
     for (int l = 0; l < g.nlevels; ++l) maxNode = max(maxNode, g.lv[l].nodeCap);
-    int cap = min(maxNode, 20000);
-    size_t smem = (size_t)cap * sizeof(unsigned long long);
+    int cap = (min(maxNode, 12000) + 3) & ~3;      // records sorted in shared memory; larger levels sort in global memory
+    size_t smem = quadtree_smem_bytes(cap);
     static bool attr_done = false;
     if (smem > 48 * 1024 || !attr_done) {
         cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -217,3 +217,74 @@ def test_bf_knn2_parity(ctxs, norm):
     ref = oo.match_bf_knn2(d1[:3], d2[:1], norm, 0.7)
     for r, g in zip(ref, got):
         assert np.array_equal(r, g)
+
+
+def test_fused_detect_match_chunked(ctxs, monkeypatch):
+    """nav24_orb_detect_match_batch / _device: chunks on two streams, pairs inside a chunk and pairs spanning chunks."""
+    H, W, nf = 376, 1241, 2000
+    fr = sequence(H, W, 9, 10, step=(6, 0))
+    pairs = [(0, 1), (2, 3), (4, 5), (6, 7), (8, 9), (1, 2), (0, 9), (3, 3)]
+    o = oo.OrbOracle(nf)
+    ref = [o.detect(f) for f in fr]
+    grid_o = oo.grid_for(W, H)
+    mref = []
+    for a, b in pairs:
+        (_, k1, d1), (_, k2, d2) = ref[a], ref[b]
+        mref.append(oo.match_window(k1, np.stack([k1["x"], k1["y"]], 1), d1, k2, np.stack([k2["x"], k2["y"]], 1), d2, grid_o))
+    for chunk in ("4", "2", "64", "3"):
+        monkeypatch.setenv("NAV24_CHUNK_FRAMES", chunk)
+        monkeypatch.setenv("NAV24_RESIDENT_CHUNK", chunk)
+        ctx = capi.OrbContext(nf)
+        try:
+            n, mono, kps, desc, m, nm = ctx.detect_match_batch(fr, pairs, capi.grid_for(W, H))
+            exact = True
+            for f in range(len(fr)):
+                mo, ko, do = ref[f]
+                assert mono[f] == mo and n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes()
+                exact &= np.array_equal(desc[f, :n[f]], do)
+            if exact:
+                for q, (a, b) in enumerate(pairs):
+                    assert np.array_equal(m[q, :n[a]], mref[q]), (chunk, q)
+                    assert nm[q] == (mref[q] >= 0).sum()
+            # device-resident form, twice back to back (asynchronous), then fetch
+            padded = np.zeros((len(fr), H, 1248), np.uint8); padded[:, :, :W] = fr
+            dptr = capi.C.c_void_p()
+            assert ctx.L.nav24_device_alloc(padded.nbytes, capi.C.byref(dptr)) == 0
+            assert ctx.L.nav24_memcpy_h2d(dptr, padded.ctypes.data_as(capi.C.c_void_p), padded.nbytes) == 0
+            for _ in range(2):
+                ctx.detect_match_device(dptr.value, len(fr), W, H, 1248, 1248 * H, pairs, capi.grid_for(W, H))
+            n2, mono2, kps2, desc2 = ctx.fetch(len(fr))
+            m2, nm2 = ctx.match_fetch(len(pairs))
+            assert np.array_equal(n2, n) and np.array_equal(mono2, mono)
+            for f in range(len(fr)):
+                assert kps2[f, :n[f]].tobytes() == kps[f, :n[f]].tobytes() and np.array_equal(desc2[f, :n[f]], desc[f, :n[f]])
+            assert np.array_equal(nm2, nm)
+            for q, (a, b) in enumerate(pairs):
+                assert np.array_equal(m2[q, :n[a]], m[q, :n[a]])
+            ctx.L.nav24_device_free(dptr)
+        finally:
+            ctx.close()
+
+
+def test_warp_sort_equals_std_sort(ctxs):
+    """The warp-parallel introsort must leave the exact permutation libstdc++'s std::sort leaves (ties included)."""
+    ctx = _ctx(ctxs, 1000)
+    rng = np.random.default_rng(2024)
+    sizes = [1, 2, 3, 15, 16, 17, 18, 31, 32, 33, 47, 64, 100, 217, 434, 435, 1000, 1737, 4097, 8687]
+    for n in sizes:
+        for kind in range(6):
+            if kind == 0:   cnt = rng.integers(2, 6, n); ulx = rng.integers(0, 40, n) * 31       # tie-heavy, like the quadtree
+            elif kind == 1: cnt = np.full(n, 3); ulx = np.zeros(n, np.int64)                       # all equivalent
+            elif kind == 2: cnt = np.arange(n) // 7 + 2; ulx = np.zeros(n, np.int64)               # sorted runs of ties
+            elif kind == 3: cnt = (n - np.arange(n)) // 3 + 2; ulx = rng.integers(0, 3, n)         # descending
+            elif kind == 4: cnt = rng.integers(2, 2000, n); ulx = rng.integers(0, 8192, n)         # mostly distinct
+            else:                                                                                  # median-of-3 killer -> heap sort
+                k = n // 2; v = np.zeros(n, np.int64)
+                for i in range(1, k + 1):
+                    if i % 2: v[i - 1] = i; v[i] = k + i
+                    v[k + i - 1] = 2 * i
+                cnt = v + 2; ulx = np.zeros(n, np.int64)
+            cnt = np.asarray(cnt, np.int64); ulx = np.asarray(ulx, np.int64)
+            ref = oo.sort_sized(cnt.astype(np.int32), ulx.astype(np.int32))
+            got = ctx.debug_sort((cnt * 8192 + ulx).astype(np.uint32))
+            assert np.array_equal(got, ref), (n, kind)
