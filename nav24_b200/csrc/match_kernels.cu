@@ -68,7 +68,8 @@ __device__ __forceinline__ bool cell_range(const MatchArgs& a, float x, float y,
 
 // One CTA (1024 threads) per frame pair.  Dynamic shared memory (sizes in MatchSmem; 0 = that table stays
 // in global memory, the kernel is still exact): CSR cell starts | dist2 | m21 | active-query table | candidate pool.
-struct MatchSmem { int cells, n2, act, pool, total; };
+struct MatchSmem { int cells, n2, act, pool, acc, total; };
+constexpr int kAccSlots = 4;        // acceptors remembered per target in the parallel resolution; more -> sequential scan
 
 // evaluates the entries [s_col + ...) of up to 32 grid columns for one query; calls emit(j, dist, lane_has) in
 // the grid's iteration order, 32 candidates at a time.  All lanes of the warp must call it.
@@ -76,7 +77,6 @@ template <typename F>
 __device__ __forceinline__ void for_each_candidate(const MatchArgs& a, const PairView& v, const int* cs, const int* items,
                                                    int i1, F&& emit) {
     const int lane = threadIdx.x & 31;
-    const int level1 = v.k1[i1].octave;
     const float2 q = ud_of(v.k1, v.ud1, i1);
     int cx0, cx1, cy0, cy1;
     if (!cell_range(a, q.x, q.y, cx0, cx1, cy0, cy1)) return;
@@ -98,22 +98,25 @@ __device__ __forceinline__ void for_each_candidate(const MatchArgs& a, const Pai
         const int T = __shfl_sync(0xffffffffu, incl, 31);
         for (int t0 = 0; t0 < T; t0 += 32) {
             const int t = t0 + lane;
+            // column of entry t = number of columns whose inclusive count is <= t (binary search over the lanes)
             int col = 0;
-            for (int k = 0; k < ncol; ++k) col += (t >= __shfl_sync(0xffffffffu, incl, k));
-            const int sc = __shfl_sync(0xffffffffu, s, col & 31), ic = __shfl_sync(0xffffffffu, incl, col & 31);
-            const int cc = __shfl_sync(0xffffffffu, cnt, col & 31);
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int probe = __shfl_sync(0xffffffffu, incl, col + step - 1);
+                if (probe <= t) col += step;
+            }
+            col = min(col, 31);
+            const int sc = __shfl_sync(0xffffffffu, s, col), ic = __shfl_sync(0xffffffffu, incl, col);
+            const int cc = __shfl_sync(0xffffffffu, cnt, col);
             int j = -1, d = 0;
             if (t < T) {
                 const int jj = items[sc + (t - (ic - cc))];
-                const int oc = v.k2[jj].octave;
-                if (oc >= level1 && oc <= level1) {                  // minLevel = maxLevel = level1 (:124)
-                    const float2 pt = ud_of(v.k2, v.ud2, jj);
-                    if (fabsf(__fsub_rn(pt.x, q.x)) < a.window && fabsf(__fsub_rn(pt.y, q.y)) < a.window) {
-                        const uint4 ta = v.d2[2 * jj], tb = v.d2[2 * jj + 1];
-                        d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-                            __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
-                        j = jj;
-                    }
+                const float2 pt = ud_of(v.k2, v.ud2, jj);
+                if (fabsf(__fsub_rn(pt.x, q.x)) < a.window && fabsf(__fsub_rn(pt.y, q.y)) < a.window) {
+                    const uint4 ta = __ldg(v.d2 + 2 * jj), tb = __ldg(v.d2 + 2 * jj + 1);
+                    d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                        __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                    j = jj;
                 }
             }
             emit(j, d);
@@ -121,12 +124,22 @@ __device__ __forceinline__ void for_each_candidate(const MatchArgs& a, const Pai
     }
 }
 
+// rotation-histogram bin of an accepted pair (:175-185); kNoBin when it falls outside [0, HISTO_LENGTH)
+constexpr int kNoBin = 31;
+__device__ __forceinline__ int rot_bin(float angle1, float angle2) {
+    float rot = __fsub_rn(angle1, angle2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHisto));
+    if (bin == kHisto) bin = 0;
+    return (bin >= 0 && bin < kHisto) ? bin : kNoBin;
+}
+
 __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, const MatchSmem sm) {
     extern __shared__ int s_dynm[];
     __shared__ int s_scan[33];
     __shared__ int s_hist[kHisto];
     __shared__ int s_ind[3];
-    __shared__ int s_nm, s_nA, s_poolUsed;
+    __shared__ int s_nm, s_nA, s_poolUsed, s_big, s_changed, s_ovf;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
     const int pr = a.pairOrder ? a.pairOrder[a.pairBase + blockIdx.x] : a.pairBase + (int)blockIdx.x;
     PairView v;
@@ -150,24 +163,31 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
     const bool n2InSmem = sm.n2 >= v.n2 && sm.n2 > 0;
     int* dist2 = n2InSmem ? s_dynm + sm.cells : a.dist2 + (long long)pr * a.cap;
     int* m21 = n2InSmem ? s_dynm + sm.cells + sm.n2 : a.m21 + (long long)pr * a.cap;
-    int* s_act = s_dynm + sm.cells + 2 * sm.n2;                // [3][sm.act]: i1, pool offset, count
-    int* s_pool = s_act + 3 * sm.act;
+    int* s_act = s_dynm + sm.cells + 2 * sm.n2;                // [4][sm.act]: i1, pool offset, count, decision
+    int* s_pool = s_act + 4 * sm.act;
+    int* accCnt = s_pool + sm.pool;                            // [sm.acc] acceptors per target, [sm.acc][kAccSlots] entries
+    int* accList = accCnt + sm.acc;
     int* bins = a.bins + (long long)pr * a.cap;
     int* m12 = a.matches12 + (long long)pr * a.cap;
 
     // ---- FeatureGrid::assignFeaturesToGrid (:115-152) as CSR, cell id = ix*rows + iy ------------------
+    // Only octave-0 keypoints of frame 2 enter the grid: every query has octave 0 (:120-122) and asks for
+    // getFeaturesInArea(..., minLevel = maxLevel = its own octave) (:124), so no other keypoint can be a candidate;
+    // the order inside a cell (insertion = index order) is unchanged for the ones that remain.
     for (int c = tid; c < nCells; c += nth) cellFill[c] = 0;
     for (int j = tid; j < v.n2; j += nth) { dist2[j] = 0x7fffffff; m21[j] = -1; }
     for (int i = tid; i < v.n1; i += nth) { m12[i] = -1; bins[i] = -1; candCnt[i] = 0; }
     if (tid < kHisto) s_hist[tid] = 0;
-    if (tid == 0) { s_nA = 0; s_poolUsed = 0; }
+    if (tid == 0) { s_nA = 0; s_poolUsed = 0; s_big = 0; s_changed = 0; s_ovf = 0; }
     __syncthreads();
     for (int j = tid; j < v.n2; j += nth) {
-        const float2 pt = ud_of(v.k2, v.ud2, j);
-        const int px = (int)roundf(__fmul_rn(__fsub_rn(pt.x, a.grid.min_x), a.invW));
-        const int py = (int)roundf(__fmul_rn(__fsub_rn(pt.y, a.grid.min_y), a.invH));
         int c = -1;
-        if (!(px < 0 || px >= a.grid.cols || py < 0 || py >= a.grid.rows)) { c = px * a.grid.rows + py; atomicAdd(&cellFill[c], 1); }
+        if (v.k2[j].octave == 0) {
+            const float2 pt = ud_of(v.k2, v.ud2, j);
+            const int px = (int)roundf(__fmul_rn(__fsub_rn(pt.x, a.grid.min_x), a.invW));
+            const int py = (int)roundf(__fmul_rn(__fsub_rn(pt.y, a.grid.min_y), a.invH));
+            if (!(px < 0 || px >= a.grid.cols || py < 0 || py >= a.grid.rows)) { c = px * a.grid.rows + py; atomicAdd(&cellFill[c], 1); }
+        }
         cellOf[j] = c;
     }
     __syncthreads();
@@ -203,20 +223,22 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
     // ---- phase A: per query (one warp each), pruned candidate list in the grid's iteration order -----------
     // A candidate whose distance can neither be an accepted best (dist > TH_LOW) nor fail the ratio
     // test as second best ((float)dist*ratio > TH_LOW >= best) is equivalent to "no candidate".
+    // Entry = (j << 14) | (rotation bin << 9) | distance, so that the sequential phase touches no global memory.
     const float thLowF = (float)a.thLow;
     for (int i1 = wid; i1 < v.n1; i1 += nw) {
         if (v.k1[i1].octave > 0) continue;                       // :120-122
+        const float ang1 = v.k1[i1].angle;
         int cnt = 0;
         for_each_candidate(a, v, cellStart, items, i1, [&](int j, int d) {
             const bool keep = j >= 0 && !(d > a.thLow && __fmul_rn((float)d, a.nnratio) > thLowF);
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-                if (pos < kCandCap) cand[(long long)i1 * kCandCap + pos] = (j << 9) | d;
+                if (pos < kCandCap) cand[(long long)i1 * kCandCap + pos] = (j << 14) | (rot_bin(ang1, v.k2[j].angle) << 9) | d;
             }
             cnt += __popc(bal);
         });
-        if (lane == 0) candCnt[i1] = cnt;
+        if (lane == 0) { candCnt[i1] = cnt; if (cnt > kCandCap) s_big = 1; }
     }
     __syncthreads();
 
@@ -247,20 +269,104 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
     }
     __syncthreads();
 
-    // ---- phase B: the sequential accept / steal scan over i1 (:114-187), one warp ------------------------
+    // ---- phase B: the accept / steal scan over i1 (:114-187) --------------------------------------------
+    // Sequentially, query k sees dist2[j] = min{ best(k') : k' < k accepted target j } (a later acceptor always has a
+    // strictly smaller distance, :146) and decides from that alone; so the decisions D_k solve a triangular system
+    // D_k = f(D_0..D_{k-1}).  Parallel form: iterate D <- F(D) from "nobody accepted" with all queries in parallel
+    // (one warp each); after t rounds the first t decisions are final, and a round that changes nothing is the
+    // unique solution, i.e. exactly the sequential result.  In practice a handful of rounds.  Per target the
+    // acceptors of the previous round are kept in kAccSlots slots; an overflow, a query with more than kCandCap
+    // candidates or tables that do not fit in shared memory fall back to the literal sequential scan below.
+    const int nA = s_nA;
+    bool parallelDone = false;
+    if (sm.acc >= v.n2 && sm.acc > 0 && nA <= sm.act && !s_big) {
+        int* dec = s_act + 3 * sm.act;
+        for (int k = tid; k < nA; k += nth) dec[k] = -1;
+        __syncthreads();
+        for (int round = 0; round <= nA; ++round) {
+            for (int j = tid; j < v.n2; j += nth) accCnt[j] = 0;
+            __syncthreads();
+            if (tid == 0) s_changed = 0;      // (everybody read the previous round's flag before the barrier above)
+            for (int k = tid; k < nA; k += nth) {
+                const int d = dec[k];
+                if (d >= 0) {
+                    const int j = d >> 9;
+                    const int slot = atomicAdd(&accCnt[j], 1);
+                    if (slot < kAccSlots) accList[j * kAccSlots + slot] = (k << 9) | (d & 511);
+                    else s_ovf = 1;
+                }
+            }
+            __syncthreads();
+            if (s_ovf) break;
+            for (int k = wid; k < nA; k += nw) {
+                const int cnt = s_act[2 * sm.act + k], off = s_act[sm.act + k];
+                int pk = 0, d = 0x7fffffff;
+                if (lane < cnt) {
+                    pk = off >= 0 ? s_pool[off + lane] : cand[(long long)s_act[k] * kCandCap + lane];
+                    const int j = pk >> 14, dd = pk & 511;
+                    const int c = min(accCnt[j], kAccSlots);
+                    int before = 0x7fffffff;                              // dist2[j] as query k would see it
+                    for (int t = 0; t < c; ++t) {
+                        const int e = accList[j * kAccSlots + t];
+                        if ((e >> 9) < k) before = min(before, e & 511);
+                    }
+                    if (!(before <= dd)) d = dd;                          // :146
+                }
+                int nd = -1;
+                const int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
+                const int kmin = __reduce_min_sync(0xffffffffu, key);
+                if (kmin != 0x7fffffff) {
+                    const int bl = kmin & 31, best = kmin >> 5;
+                    const int bpk = __shfl_sync(0xffffffffu, pk, bl);
+                    const int best2 = __reduce_min_sync(0xffffffffu, (lane == bl) ? 0x7fffffff : d);
+                    if (best <= a.thLow && (float)best < __fmul_rn((float)best2, a.nnratio)) nd = ((bpk >> 14) << 9) | best;   // :161-163
+                }
+                if (lane == 0 && nd != dec[k]) { dec[k] = nd; s_changed = 1; }
+            }
+            __syncthreads();
+            if (!s_changed) { parallelDone = true; break; }
+        }
+        if (parallelDone) {
+            // the acceptor lists now describe the final decisions: the owner of a target is its LAST acceptor (:165-169);
+            // every acceptance, stolen later or not, left its rotation bin in the histogram (:175-185)
+            for (int k = tid; k < nA; k += nth) {
+                const int d = dec[k];
+                if (d < 0) continue;
+                const int j = d >> 9, i1 = s_act[k];
+                const int c = min(accCnt[j], kAccSlots);
+                bool owner = true;
+                for (int t = 0; t < c; ++t) owner &= (accList[j * kAccSlots + t] >> 9) <= k;
+                if (owner) m12[i1] = j;
+                if (a.checkOri) {
+                    const int bin = rot_bin(v.k1[i1].angle, v.k2[j].angle);
+                    if (bin != kNoBin) { bins[i1] = bin; atomicAdd(&s_hist[bin], 1); }
+                }
+            }
+        } else {
+            for (int j = tid; j < v.n2; j += nth) { dist2[j] = 0x7fffffff; m21[j] = -1; }      // the tables share memory
+        }
+        __syncthreads();
+    }
     if (wid == 0) {
-        const int nA = s_nA;
-        for (int k = 0; k < nA; ++k) {
-            int i1, cnt, off = -1;
+        const int nSeq = parallelDone ? 0 : nA;
+        auto fetch = [&](int k, int& i1, int& cnt, int& off, int& pk) {
+            i1 = -1; cnt = 0; off = -1; pk = 0;
+            if (k >= nSeq) return;
             if (k < sm.act) { i1 = s_act[k]; off = s_act[sm.act + k]; cnt = s_act[2 * sm.act + k]; }
             else { i1 = actList[k]; cnt = candCnt[i1]; }
-            int best = 0x7fffffff, best2 = 0x7fffffff, bestIdx = -1;
-            if (cnt <= kCandCap) {
-                int d = 0x7fffffff, j = -1;
-                if (lane < cnt) {
-                    const int pk = off >= 0 ? s_pool[off + lane] : cand[(long long)i1 * kCandCap + lane];
-                    j = pk >> 9;
-                    const int dd = pk & 511;
+            if (cnt <= kCandCap && lane < cnt) pk = off >= 0 ? s_pool[off + lane] : cand[(long long)i1 * kCandCap + lane];
+        };
+        int i1, cnt, off, pk;
+        fetch(0, i1, cnt, off, pk);
+        for (int k = 0; k < nSeq; ++k) {
+            const int ci1 = i1, ccnt = cnt, cpk = pk;
+            fetch(k + 1, i1, cnt, off, pk);
+            int best = 0x7fffffff, best2 = 0x7fffffff, bestIdx = -1, bestBin = kNoBin;
+            if (ccnt <= kCandCap) {
+                int d = 0x7fffffff;
+                const int j = cpk >> 14;
+                if (lane < ccnt) {
+                    const int dd = cpk & 511;
                     if (!(dist2[j] <= dd)) d = dd;               // :146
                 }
                 // first minimum in list order, then the second smallest of the multiset
@@ -269,12 +375,13 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
                 if (kmin != 0x7fffffff) {
                     const int bl = kmin & 31;
                     best = kmin >> 5;
-                    bestIdx = __shfl_sync(0xffffffffu, j, bl);
+                    const int bpk = __shfl_sync(0xffffffffu, cpk, bl);
+                    bestIdx = bpk >> 14; bestBin = (bpk >> 9) & 31;
                     best2 = __reduce_min_sync(0xffffffffu, (lane == bl) ? 0x7fffffff : d);
                 }
             } else {
                 // exact slow path: re-enumerate every candidate of this query in order
-                for_each_candidate(a, v, cellStart, items, i1, [&](int j, int dd) {
+                for_each_candidate(a, v, cellStart, items, ci1, [&](int j, int dd) {
                     int d = 0x7fffffff;
                     if (j >= 0 && !(dist2[j] <= dd)) d = dd;
                     const int key = (d == 0x7fffffff) ? 0x7fffffff : ((d << 5) | lane);
@@ -286,40 +393,35 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
                     if (cb < best) { best2 = min(best, d2); best = cb; bestIdx = cj; }
                     else best2 = min(best2, cb);
                 });
+                if (bestIdx >= 0) bestBin = rot_bin(v.k1[ci1].angle, v.k2[bestIdx].angle);
             }
             if (best <= a.thLow && (float)best < __fmul_rn((float)best2, a.nnratio)) {      // :161-163
                 if (lane == 0) {
                     const int prev = m21[bestIdx];
                     if (prev >= 0) m12[prev] = -1;
-                    m12[i1] = bestIdx;
-                    m21[bestIdx] = i1;
+                    m12[ci1] = bestIdx;
+                    m21[bestIdx] = ci1;
                     dist2[bestIdx] = best;
-                    if (a.checkOri) {
-                        float rot = __fsub_rn(v.k1[i1].angle, v.k2[bestIdx].angle);
-                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                        int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHisto));
-                        if (bin == kHisto) bin = 0;
-                        if (bin >= 0 && bin < kHisto) { bins[i1] = bin; s_hist[bin] += 1; }
-                    }
+                    if (a.checkOri && bestBin != kNoBin) { bins[ci1] = bestBin; s_hist[bestBin] += 1; }
                 }
                 __syncwarp();
             }
         }
         // ComputeThreeMaxima (:28-69)
         if (lane == 0) {
-            int i1 = -1, i2 = -1, i3 = -1;
+            int i1m = -1, i2 = -1, i3 = -1;
             if (a.checkOri) {
                 int m1 = 0, m2 = 0, m3 = 0;
                 for (int i = 0; i < kHisto; ++i) {
                     const int s = s_hist[i];
-                    if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+                    if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1m; i1m = i; }
                     else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
                     else if (s > m3) { m3 = s; i3 = i; }
                 }
                 if ((float)m2 < __fmul_rn(0.1f, (float)m1)) { i2 = -1; i3 = -1; }
                 else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
             }
-            s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3;
+            s_ind[0] = i1m; s_ind[1] = i2; s_ind[2] = i3;
             s_nm = 0;
         }
     }
@@ -400,10 +502,12 @@ int launch_match_window(const MatchArgs& a, int P, cudaStream_t s) {
     int used = 0;
     if (nCells + 1 <= 40000) { sm.cells = (nCells + 1 + 3) & ~3; used += sm.cells; }
     if (2 * a.cap <= budget - used - 4096) { sm.n2 = (a.cap + 3) & ~3; used += 2 * sm.n2; }
-    sm.act = min(max((budget - used) / 8, 0), (a.cap + 3) & ~3);
-    used += 3 * sm.act;
+    sm.act = min(max((budget - used) / 10, 0), (a.cap + 3) & ~3);
+    used += 4 * sm.act;
     sm.pool = min(max(budget - used, 0), 8192);
     used += sm.pool;
+    const int capR = (a.cap + 3) & ~3;
+    if ((1 + kAccSlots) * capR <= budget - used) { sm.acc = capR; used += (1 + kAccSlots) * capR; }
     sm.total = used * 4;
     static int attrSet = 0;
     if (sm.total > attrSet) {
