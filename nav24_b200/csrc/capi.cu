@@ -74,7 +74,7 @@ struct nav24_orb {
     int mapsB = 0;            // frame count the level>=1 maps were encoded for
     const void* mapsPyr = nullptr;
     DevBuf bL0Tight, bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
-        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs;
+        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs, bOriTab;
     // matcher scratch
     DevBuf mK1, mK2, mU1, mU2, mD1, mD2, mN1, mN2, mCellOf, mCellStart, mCellFill, mCellItems, mCand, mCandCnt, mDist2,
         mM21, mBins, mMatches, mNMatches, mPairs, mPairOrder, mI0, mI1, mF0, mF1, mPass;
@@ -304,7 +304,29 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         CK(ctx->bOutDesc.ensure(b * g.outCap * 32));
         CK(ctx->bNOut.ensure(b * sizeof(int)));
         CK(ctx->bMono.ensure(b * sizeof(int)));
-        CK(ctx->bErr.ensure(sizeof(int) * 4));
+        if (!ctx->bErr.ptr) {      // the device error word is sticky (cleared when read), so it starts at zero
+            CK(ctx->bErr.ensure(sizeof(int) * 4));
+            CK(cudaMemset(ctx->bErr.ptr, 0, sizeof(int) * 4));
+        }
+        if (!ctx->bOriTab.ptr) {      // orientation weights: umax (OP_FtDtOrbSlam.cpp:484-499) as DP4A byte weights
+            static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+            std::vector<unsigned> t(4 * 279 * 2);
+            for (int al = 0; al < 4; ++al)
+                for (int r = 0; r < 31; ++r)
+                    for (int c = 0; c < 9; ++c) {
+                        unsigned wx = 0, wm = 0;
+                        for (int b = 0; b < 4; ++b) {
+                            const int u = 4 * c + b - al - 15, v = r - 15;
+                            if (u >= -15 && u <= 15 && std::abs(u) <= umax[std::abs(v)]) {
+                                wx |= (unsigned)(uint8_t)(int8_t)u << (8 * b);
+                                wm |= 1u << (8 * b);
+                            }
+                        }
+                        t[((al * 31 + r) * 9 + c) * 2] = wx; t[((al * 31 + r) * 9 + c) * 2 + 1] = wm;
+                    }
+            CK(ctx->bOriTab.ensure(t.size() * 4));
+            CK(cudaMemcpy(ctx->bOriTab.ptr, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+        }
         ctx->wsB = (int)b;
         DevPtrs& p = ctx->p;
         p.pyr = (uint8_t*)ctx->bPyr.ptr; p.blur = (uint8_t*)ctx->bBlur.ptr;
@@ -316,6 +338,7 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         p.levelCount = (int*)ctx->bLevelCount.ptr; p.rawTotal = (int*)ctx->bRawTotal.ptr;
         p.outKp = (nav24_kp*)ctx->bOutKp.ptr; p.outDesc = (uint8_t*)ctx->bOutDesc.ptr;
         p.nOut = (int*)ctx->bNOut.ptr; p.monoOut = (int*)ctx->bMono.ptr; p.err = (int*)ctx->bErr.ptr;
+        p.oriTab = (const unsigned*)ctx->bOriTab.ptr;
         ctx->lastValid = false;
     }
     return NAV24_OK;
@@ -515,7 +538,7 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     DevBuf* bufs[] = {&ctx->bL0Tight, &ctx->bL0, &ctx->bPyr, &ctx->bBlur, &ctx->bCell, &ctx->bCellDst, &ctx->bRawCount, &ctx->bRaw, &ctx->bKeys,
                       &ctx->bNodeOfKey, &ctx->bNodesA, &ctx->bNodesB, &ctx->bChild, &ctx->bAux, &ctx->bBest, &ctx->bSort,
                       &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
-                      &ctx->bErr, &ctx->bTabs, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
+                      &ctx->bErr, &ctx->bTabs, &ctx->bOriTab, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
                       &ctx->mN2, &ctx->mCellOf, &ctx->mCellStart, &ctx->mCellFill, &ctx->mCellItems, &ctx->mCand, &ctx->mCandCnt,
                       &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mPairOrder, &ctx->mI0, &ctx->mI1,
                       &ctx->mF0, &ctx->mF1, &ctx->mPass};

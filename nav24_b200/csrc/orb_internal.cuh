@@ -102,6 +102,7 @@ struct DevPtrs {
     nav24_kp* outKp;         // [B][outCap]
     uint8_t* outDesc;        // [B][outCap][32]
     int* nOut; int* monoOut; // [B]
+    const unsigned* oriTab;  // orientation DP4A weights [4][279][2] (describe_kernel)
     int* err;                // device error bits
     int frameBase;           // first frame of this chunk inside the buffers the TMA maps were encoded over
 };

@@ -867,26 +867,6 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-// volatile loads: ptxas keeps their order and therefore issues all of them before the first use, which is what a
-// latency-bound gather wants (left alone it interleaves loads and uses to save registers)
-__device__ __forceinline__ unsigned ldg_u32_now(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ldg_u8_now(const uint8_t* p) {
-    unsigned v;
-    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return (int)v;
-}
-
-// umax[|v|] of the 31-px disc (OP_FtDtOrbSlam.cpp:484-499), a compile-time table so that the unrolled row loop
-// of the orientation carries static predicates
-__device__ __forceinline__ constexpr int umax_of(int av) {
-    constexpr int t[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    return t[av];
-}
-
 // rBRIEF pattern as floats, transposed for the warp: entry [j][lane] = (x0, y0, x1, y1) of test pair 8*lane + j, so that
 // the 32 lanes of one load read 512 consecutive bytes (lane-major order cost 32 L1 wavefronts per load instead of 4).
 struct PatternT { float v[8][32][4]; };
@@ -902,68 +882,113 @@ constexpr PatternT make_pattern_t() {
 }
 __device__ const PatternT kPatternT = make_pattern_t();
 
-__global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
-    __shared__ unsigned s_patch[8][372];
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+#ifndef NAV24_DESC_WARPS
+#define NAV24_DESC_WARPS 1
+#endif
+#ifndef NAV24_DESC_BATCH
+#define NAV24_DESC_BATCH 0
+#endif
+// keypoints (warps) per CTA of describe_kernel.  Measured on B200 (256 KITTI frames): 16 warps 0.80 ms, 8: 0.76, 4: 0.60,
+// 2: 0.53, 1: 0.48 — a CTA holds its registers and shared memory until its slowest warp's gathers return.
+constexpr int kDescWarps = NAV24_DESC_WARPS;
+
+// Orientation weights for the DP4A moments, [align 4][row 31][word 9][2]: for the aligned words that cover the 31-px
+// row segment of a keypoint whose left end sits `align` bytes into its first word, (x) the four signed u offsets of the
+// bytes inside the disc (0 outside), (y) their 0/1 mask.  m10 = sum dp4a(word, x), m01 = sum v * dp4a(word, y).
+// Built once per context on the host (capi.cu: build_orientation_table) from umax[] (OP_FtDtOrbSlam.cpp:484-499).
+
+__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+    __shared__ unsigned s_patch[kDescWarps][372];
+    __shared__ int s_mom[kDescWarps][2];
+    __shared__ float s_rot[kDescWarps][3];      // angle, cos, sin
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int slot = blockIdx.x * kDescWarps + wid;
     const int f = blockIdx.y;
-    if (slot >= g.kpPerFrame) return;
     int l = 0;
     while (l + 1 < g.nlevels && slot >= g.lv[l + 1].kpOff) ++l;
     const LevelGeom& L = g.lv[l];
     const int i = slot - L.kpOff;
-    if (i >= p.levelCount[f * g.nlevels + l]) return;
+    const bool live = slot < g.kpPerFrame && i < p.levelCount[f * g.nlevels + l];      // warp-uniform
     LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + slot;
-    const int cx = kp->x, cy = kp->y;
-
-    // issue the loads of the blurred 37 x 40 byte patch first (they do not depend on the angle): 12 words per lane
+    int cx = 0, cy = 0, align = 0;
     const int bp = L.pitch;
-    const int ax = (cx - 18) & ~3, align = (cx - 18) - ax;
-    const uint8_t* bl = p.blur + (long long)f * g.blurFrameBytes + L.boff + (long long)(cy - 18) * bp + ax;
     unsigned pw[12];
+    if (live) {
+        cx = kp->x; cy = kp->y;
+        // issue the loads of the blurred 37 x 40 byte patch first (they do not depend on the angle): 12 words per lane
+        const int ax = (cx - 18) & ~3;
+        align = (cx - 18) - ax;
+        const uint8_t* bl = p.blur + (long long)f * g.blurFrameBytes + L.boff + (long long)(cy - 18) * bp + ax;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        const int idx = k * 32 + lane;                  // word idx of the 37 x 10 patch
-        const int r = idx / 10, c = idx - r * 10;
-        pw[k] = ldg_u32_now(reinterpret_cast<const unsigned*>(bl + (idx < 370 ? r * bp : 0)) + (idx < 370 ? c : 0));
+        for (int k = 0; k < 12; ++k) {
+            const int idx = k * 32 + lane;                  // word idx of the 37 x 10 patch
+            const int r = (idx * 205) >> 11, c = idx - r * 10;      // idx / 10 for idx < 1024
+            pw[k] = idx < 370 ? __ldg(reinterpret_cast<const unsigned*>(bl + r * bp) + c) : 0u;
+        }
+        // orientation on the un-blurred level: integer moments of the 31-px disc by DP4A over the aligned words of the
+        // 31 x 31 patch (279 words, 9 per lane) with the weight table; every load is in flight before the first use
+        const int pitch = (int)level_pitch(g, p, l);
+        const int ox = (cx - 15) & ~3, oal = (cx - 15) - ox;
+        const uint8_t* img = level_ptr(g, p, f, l) + (long long)(cy - 15) * pitch + ox;
+        const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + oal * 279;
+        unsigned ow[9];
+        uint2 wt[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int idx = min(k * 32 + lane, 278);
+            const int r = (idx * 57) >> 9, c = idx - r * 9;         // idx / 9 for idx < 288
+            ow[k] = __ldg(reinterpret_cast<const unsigned*>(img + r * pitch) + c);
+            wt[k] = __ldg(tab + idx);
+        }
+        int m10 = 0, m01 = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int idx = k * 32 + lane;
+            if (idx < 279) {
+                const int r = (idx * 57) >> 9;
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(ow[k]), "r"(wt[k].x));      // u8 pixels x s8 offsets
+                m01 += (r - 15) * (int)__dp4a(ow[k], wt[k].y, 0u);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+#if NAV24_DESC_BATCH
+        if (lane == 0) { s_mom[wid][0] = m01; s_mom[wid][1] = m10; }
     }
-
-    // orientation on the un-blurred level: lane u owns column u-15; all 31 row loads are in flight together
-    const int pitch = (int)level_pitch(g, p, l);
-    const uint8_t* img = level_ptr(g, p, f, l) + (long long)cy * pitch + cx;
-    // (every lane may load: |u| <= 16, |v| <= 15 stays inside the image because keypoints keep 19 px from the edges;
-    // pixels outside the disc are masked after the load, so the 31 loads carry no predicates and no branches)
-    int colsum = 0, m01 = 0;
-    const int u = lane - 15, au = abs(u);
-    const uint8_t* rp = img - 15 * pitch + u;
-    int px[31];
-#pragma unroll
-    for (int k = 0; k < 31; ++k) px[k] = ldg_u8_now(rp + k * pitch);
-#pragma unroll
-    for (int k = 0; k < 31; ++k) {
-        const int v = k - 15;
-        const int m = au <= umax_of(v < 0 ? -v : v) ? px[k] : 0;
-        colsum += m;
-        m01 += v * m;
+    __syncthreads();
+    // the scalar float work (fastAtan2, sin/cos) of the CTA's keypoints runs once, one keypoint per lane of warp 0,
+    // instead of 32-fold redundantly in every warp
+    if (wid == 0 && lane < kDescWarps) {
+        const float angle = fast_atan2_deg((float)s_mom[lane][0], (float)s_mom[lane][1]);
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        float sn, cs;
+        sincosf(__fmul_rn(angle, factorPI), &sn, &cs);
+        s_rot[lane][0] = angle; s_rot[lane][1] = cs; s_rot[lane][2] = sn;
     }
-    int m10 = u * colsum;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    __syncthreads();
+    if (!live) return;
+    const float angle = s_rot[wid][0], a = s_rot[wid][1], b = s_rot[wid][2];
+#else
+        s_mom[wid][0] = m01; s_mom[wid][1] = m10;      // (same value from every lane)
     }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // descriptor on the blurred level
+    if (!live) return;
+    // (batching this scalar float work over the CTA's warps through two block barriers was measured slower: the
+    // barriers serialise the warps' memory latencies)
+    const float angle = fast_atan2_deg((float)s_mom[wid][0], (float)s_mom[wid][1]);
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
-    const float ang = __fmul_rn(angle, factorPI);
-    float a, b;
-    sincosf(ang, &b, &a);
-    // The 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38).  The warp stages that 37-row
-    // patch of the blurred level in shared memory with row-coalesced word loads (rows of 10 words starting at the
-    // aligned column ax <= cx-18) and gathers the samples from there: scattered byte gathers straight from global
-    // memory cost one L1 wavefront per touched line (~25 per load) and made this kernel L1-bound.
-    unsigned* patch = s_patch[threadIdx.x >> 5];
+    float b, a;
+    sincosf(__fmul_rn(angle, factorPI), &b, &a);
+    (void)s_rot;
+#endif
+
+    // descriptor on the blurred level.  The 512 sample points lie within +-18 px of the keypoint (pattern radius
+    // 18.38).  The warp stages that 37-row patch in shared memory with row-coalesced word loads (rows of 10 words
+    // starting at the aligned column ax <= cx-18) and gathers the samples from there: scattered byte gathers
+    // straight from global memory cost one L1 wavefront per touched line (~25 per load) and made this kernel L1-bound.
+    unsigned* patch = s_patch[wid];
 #pragma unroll
     for (int k = 0; k < 12; ++k)
         if (k * 32 + lane < 370) patch[k * 32 + lane] = pw[k];
@@ -1096,8 +1121,8 @@ int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
         blur_kernel<<<grid, 128, 0, s>>>(g, p);
         ++n;
     }
-    dim3 grid((g.kpPerFrame + 7) / 8, B);
-    describe_kernel<<<grid, 256, 0, s>>>(g, p);
+    dim3 grid((g.kpPerFrame + kDescWarps - 1) / kDescWarps, B);
+    describe_kernel<<<grid, kDescWarps * 32, 0, s>>>(g, p);
     return n + 1;
 }
 
