@@ -23,8 +23,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_header_is_plain_c():
     txt = open(capi.HEADER_PATH).read()
-    assert "torch" not in txt.lower().replace("no torch", "") and "at::" not in txt and "std::" not in txt
     assert 'extern "C"' in txt
+    code = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)      # declarations only: comments may cite std::sort etc.
+    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "cv::" not in code
     # compiles as C
     import subprocess, tempfile
     with tempfile.TemporaryDirectory() as d:
