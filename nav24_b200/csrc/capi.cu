@@ -74,7 +74,7 @@ struct nav24_orb {
     int mapsB = 0;            // frame count the level>=1 maps were encoded for
     const void* mapsPyr = nullptr;
     DevBuf bL0Tight, bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
-        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs, bOriTab;
+        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs, bOriTab, bSegs;
     // matcher scratch
     DevBuf mK1, mK2, mU1, mU2, mD1, mD2, mN1, mN2, mCellOf, mCellStart, mCellFill, mCellItems, mCand, mCandCnt, mDist2,
         mM21, mBins, mMatches, mNMatches, mPairs, mPairOrder, mI0, mI1, mF0, mF1, mPass;
@@ -157,10 +157,16 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.wCell = (int)std::ceil(width / L.nCols);
         L.hCell = (int)std::ceil(height / L.nRows);
         if (L.wCell + 6 > kMaxCellTile || L.hCell + 6 > kMaxCellTile) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
-        L.boxW = align_up(L.wCell + 7 + 15, 16);
-        if (((L.boxW / 16) & 1) == 0) L.boxW += 16;     // 16 x odd: rows 4*odd words apart -> conflict-free over 8 rows
+        // FAST segments: runs of cells of one cell row whose tile (interior + 3-px rim + <= 16 px of alignment slack)
+        // fits one TMA box (<= 256 px wide); the cells of a row are dealt evenly over the segments
+        const int fit = std::min(kFastMaxSegCells, (256 - 22) / L.wCell);
+        L.segsPerRow = (L.nCols + fit - 1) / fit;
+        L.segCols = (L.nCols + L.segsPerRow - 1) / L.segsPerRow;
+        L.segsPerRow = (L.nCols + L.segCols - 1) / L.segCols;
+        L.boxW = align_up(L.segCols * L.wCell + 7 + 15, 16);
+        if (((L.boxW / 16) & 1) == 0 && L.boxW + 16 <= 256) L.boxW += 16;     // 16 x odd: conflict-free over 8 rows
         L.boxH = L.hCell + 6;
-        if (L.boxW * L.boxH > kCellTileBytes) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
+        L.magicW = 0xFFFFFFFFu / (unsigned)L.wCell + 1u;
         L.cellBase = cellBase;
         L.blurTileBase = stripBase;
         stripBase += ((L.w + 127) / 128) * ((L.h + kBlurTileRows - 1) / kBlurTileRows);
@@ -184,6 +190,8 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.patch = (float)(int)(31 * ctx->scale[l]);
     }
     g.totalCells = cellBase;
+    g.totalSegs = 0;
+    for (int l = 0; l < nl; ++l) g.totalSegs += g.lv[l].segsPerRow * g.lv[l].nRows;
     g.blurTiles = stripBase;
     g.rawPerFrame = rawOff;
     g.nodesPerFrame = nodeOff;
@@ -207,6 +215,36 @@ void build_resize_table(int ssize, int dsize, std::vector<int>& ofs, std::vector
         ofs[d] = s;
         ab[d].x = (short)lrintf((1.f - f) * 2048.f);
         ab[d].y = (short)lrintf(f * 2048.f);
+    }
+}
+
+// FAST segment table of one frame (fast_band_kernel): the cell loop bounds of ComputeKeyPointsOctTree
+// (OP_FtDtOrbSlam.cpp:751-768) evaluated once on the host.
+void build_fast_segments(const FrameGeom& g, std::vector<FastSeg>& segs) {
+    segs.clear();
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.lv[l];
+        for (int ci = 0; ci < L.nRows; ++ci)
+            for (int sj = 0; sj < L.segsPerRow; ++sj) {
+                FastSeg s{};
+                s.level = (short)l; s.ci = (short)ci; s.cj0 = (short)(sj * L.segCols);
+                s.nc = (short)std::min(L.segCols, L.nCols - s.cj0);
+                s.cell0 = L.cellBase + ci * L.nCols + s.cj0;
+                const int iniY = kMinBorder + ci * L.hCell;
+                const int maxY = std::min(iniY + L.hCell + 6, L.maxBY);
+                s.iniY = (short)iniY; s.iniX0 = (short)(kMinBorder + s.cj0 * L.wCell);
+                const bool rowSkip = iniY >= L.maxBY - 3 || maxY - iniY < 7;      // :756 (and cv::FAST on < 7 rows finds nothing)
+                int nv = 0, iw = 0;
+                for (int j = 0; j < s.nc && !rowSkip; ++j) {
+                    const int iniX = kMinBorder + (s.cj0 + j) * L.wCell;
+                    if (iniX >= L.maxBX - 6) break;                             // :765
+                    const int maxX = std::min(iniX + L.wCell + 6, L.maxBX);
+                    if (maxX - iniX < 7) break;
+                    ++nv; iw += maxX - iniX - 6;
+                }
+                s.nv = (short)nv; s.iw = (short)iw; s.ih = (short)(nv ? maxY - iniY - 6 : 0);
+                segs.push_back(s);
+            }
     }
 }
 
@@ -275,6 +313,10 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         }
         ctx->tabs.assign(nl, ResizeTab{});
         for (int l = 1; l < nl; ++l) ctx->tabs[l] = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l]};
+        std::vector<FastSeg> segs;
+        build_fast_segments(g, segs);
+        CK(ctx->bSegs.ensure(segs.size() * sizeof(FastSeg)));
+        CK(cudaMemcpy(ctx->bSegs.ptr, segs.data(), segs.size() * sizeof(FastSeg), cudaMemcpyHostToDevice));
         ctx->wsW = w; ctx->wsH = h; ctx->wsFeat = ctx->prm.n_features; ctx->wsB = 0; ctx->mapsB = 0;
         ctx->lastValid = false;
     }
@@ -339,6 +381,7 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         p.outKp = (nav24_kp*)ctx->bOutKp.ptr; p.outDesc = (uint8_t*)ctx->bOutDesc.ptr;
         p.nOut = (int*)ctx->bNOut.ptr; p.monoOut = (int*)ctx->bMono.ptr; p.err = (int*)ctx->bErr.ptr;
         p.oriTab = (const unsigned*)ctx->bOriTab.ptr;
+        p.segs = (const FastSeg*)ctx->bSegs.ptr;
         ctx->lastValid = false;
     }
     return NAV24_OK;
@@ -538,7 +581,7 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     DevBuf* bufs[] = {&ctx->bL0Tight, &ctx->bL0, &ctx->bPyr, &ctx->bBlur, &ctx->bCell, &ctx->bCellDst, &ctx->bRawCount, &ctx->bRaw, &ctx->bKeys,
                       &ctx->bNodeOfKey, &ctx->bNodesA, &ctx->bNodesB, &ctx->bChild, &ctx->bAux, &ctx->bBest, &ctx->bSort,
                       &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
-                      &ctx->bErr, &ctx->bTabs, &ctx->bOriTab, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
+                      &ctx->bErr, &ctx->bTabs, &ctx->bOriTab, &ctx->bSegs, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
                       &ctx->mN2, &ctx->mCellOf, &ctx->mCellStart, &ctx->mCellFill, &ctx->mCellItems, &ctx->mCand, &ctx->mCandCnt,
                       &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mPairOrder, &ctx->mI0, &ctx->mI1,
                       &ctx->mF0, &ctx->mF1, &ctx->mPass};

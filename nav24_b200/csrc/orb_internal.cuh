@@ -19,8 +19,8 @@ constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
 #endif
 constexpr int kBlurTileRows = NAV24_BLUR_ROWS;   // rows per warp tile of blur_kernel (multiple of 7)
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
-constexpr int kCellTileBytes = 112 * 76;  // TMA box: (16 x odd >= wCell+7+15) x (hCell+6) bytes (x start is 16-B aligned)
-constexpr int kCellQueue = 70 * 70 + 4;   // interior pixels of the largest cell
+constexpr int kFastThreads = 256;   // threads per CTA of fast_band_kernel
+constexpr int kFastMaxSegCells = 8; // cells of one FAST segment (TMA boxes are <= 256 px wide, cells >= 35 px)
 
 // device error bits (ctx->d_err)
 enum : int { ERR_RAW_OVERFLOW = 1, ERR_ROOT_RANGE = 2, ERR_NODE_OVERFLOW = 4, ERR_CELL_SIZE = 8, ERR_KP_OVERFLOW = 16 };
@@ -32,7 +32,9 @@ struct LevelGeom {
     long long boff;          // byte offset inside one frame's blurred slab
     // FAST cell grid (OP_FtDtOrbSlam.cpp:735-768)
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
-    int boxW, boxH;          // TMA box of one FAST cell: 16*odd >= wCell+6+1+15 (bank-conflict-free row pitch) x (hCell+6)
+    int segCols, segsPerRow; // FAST segment = segCols horizontally adjacent cells of one cell row (the last may hold fewer)
+    int boxW, boxH;          // TMA box of one FAST segment: 16*odd >= segCols*wCell+6+1+15 (<= 256) x (hCell+6)
+    unsigned magicW;         // 0xFFFFFFFF / wCell + 1: floor(n / wCell) = umulhi(n, magicW) for n < 65536
     int cellBase;            // first cell id of this level inside the per-frame cell table
     int blurTileBase;        // first warp tile (128 px x kBlurTileRows rows) of this level in blur_kernel
     int rawCap;              // raw-corner capacity of this level (records)
@@ -52,6 +54,7 @@ struct LevelGeom {
 struct FrameGeom {
     int nlevels;
     int totalCells;
+    int totalSegs;           // FAST segments per frame (grid.x of fast_band_kernel)
     int rawPerFrame;         // records
     int nodesPerFrame;
     int kpPerFrame;          // level-keypoint slab size (sum of kpCap)
@@ -65,6 +68,13 @@ struct RawRec {              // one FAST survivor, 8 bytes
     unsigned short x, y;     // relative to (minBorderX, minBorderY)
     unsigned short score;
     unsigned short pad;
+};
+
+struct FastSeg {             // one CTA of fast_band_kernel: a run of cells of one cell row (host-built, 32 bytes)
+    short level, ci, cj0, nc;       // nc cells [cj0, cj0+nc) of cell row ci (entries of the cell table, skipped ones included)
+    short nv, iniX0, iniY, ih;      // nv valid cells (a prefix of the nc), image position of the tile, interior rows
+    short iw, pad0, pad1, pad2;     // interior columns of the nv cells together
+    int cell0, pad3;                // first cell of the segment in the per-frame cell table
 };
 
 struct QNode {               // 12 bytes
@@ -103,13 +113,14 @@ struct DevPtrs {
     uint8_t* outDesc;        // [B][outCap][32]
     int* nOut; int* monoOut; // [B]
     const unsigned* oriTab;  // orientation DP4A weights [4][279][2] (describe_kernel)
+    const FastSeg* segs;     // [totalSegs] FAST segments of one frame
     int* err;                // device error bits
     int frameBase;           // first frame of this chunk inside the buffers the TMA maps were encoded over
 };
 
 struct TmaMaps { CUtensorMap m[kMaxLevels]; };   // one 3-D (x, y, frame) u8 tensor map per pyramid level
 
-struct FastSmem { int offMap, offQueue, offMask, total; };   // dynamic shared memory layout of fast_cells_kernel
+struct FastSmem { int offMap, offQueue, offMask, total; };   // dynamic shared memory layout of fast_band_kernel
 
 struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;

@@ -173,12 +173,20 @@ __global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// K2  FAST-9/16 per cell with threshold fallback.  One CTA per (cell, frame).
+// K2  FAST-9/16 per cell with threshold fallback.  One CTA per (segment, frame); a segment is a run of up to
+// kFastMaxSegCells horizontally adjacent cells of one cell row (FastSeg, built on the host).
 // Reproduces the cell loop of ComputeKeyPointsOctTree (OP_FtDtOrbSlam.cpp:751-818) and
 // cv::FAST(cell, th, nms=true): the corner score is threshold independent, a
 // keypoint at threshold t is a strict 3x3 local maximum of the score map with score >= t, the
-// detection domain is the cell minus a 3-px rim, and a cell with no survivor at iniThFAST is
-// redone at minThFAST.
+// detection domain is the cell minus a 3-px rim (so the interiors of adjacent cells tile the image and
+// only the rims overlap), scores outside the cell's own interior count as 0 in its NMS, and a cell
+// with no survivor at iniThFAST is redone at minThFAST.
+//   tile   : one TMA box (segment interior + rim), shared by the cells of the segment
+//   stage A: antipodal-pair rejection, 4 pixels per 32-bit op; a thread owns one word column and walks down
+//            its rows with the column's last seven words in registers (the +-3 row taps)
+//   stage B: exact score of the survivors, balanced over the CTA through a queue
+//   stage C: 3x3 NMS (cell-aware) -> bit mask in raster order; per-cell counts by one warp per cell
+//   emit   : one warp per cell, one lane per row; cells of the segment append with ONE global atomic
 // ------------------------------------------------------------------------------------------
 // Score of one pixel.  Ring differences are packed as biased u16x2 lanes (d+256, 256-d) by one IMAD;
 // min over an arc of 9 = min3 of three min3's (VIMNMX3.U16x2); max over the 16 arcs by max3.
@@ -217,50 +225,60 @@ __device__ __forceinline__ unsigned gt_bytes2(unsigned x1, unsigned x2, unsigned
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// set bits of kmask row `rowp` inside the column range [x0, x1): popcount
+__device__ __forceinline__ int mask_range_count(const unsigned* rowp, int x0, int x1) {
+    const int wlo = x0 >> 5, whi = (x1 - 1) >> 5;
+    int n = 0;
+    for (int w = wlo; w <= whi; ++w) {
+        unsigned m = rowp[w];
+        if (w == wlo) m &= 0xffffffffu << (x0 & 31);
+        if (w == whi) m &= 0xffffffffu >> (31 - ((x1 - 1) & 31));
+        n += __popc(m);
+    }
+    return n;
+}
+
 // Dynamic shared memory: [tile | score map | queue u16 | keypoint bit mask], sizes from FastSmem.
-__global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
-                                                         const __grid_constant__ TmaMaps maps, const FastSmem sm,
-                                                         int iniTh, int minTh) {
+__global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+                                                                 const __grid_constant__ TmaMaps maps, const FastSmem sm,
+                                                                 int iniTh, int minTh) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
     uint8_t* tile = s_dyn;
     uint8_t* smap = s_dyn + sm.offMap;
     unsigned short* queue = reinterpret_cast<unsigned short*>(s_dyn + sm.offQueue);
     unsigned* kmask = reinterpret_cast<unsigned*>(s_dyn + sm.offMask);
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ int s_q, s_cnt, s_base;
-    __shared__ int s_wsum[4];
+    __shared__ int s_q, s_base, s_empty;
+    __shared__ int s_cnt[kFastMaxSegCells], s_off[kFastMaxSegCells];
+    constexpr int NT = kFastThreads, NW = kFastThreads / 32;
 
-    const int tid = threadIdx.x, f = blockIdx.y, cell = blockIdx.x;
+    const int tid = threadIdx.x, f = blockIdx.y;
     const int lane = tid & 31, wid = tid >> 5;
-    int l = 0;
-    while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) ++l;
+    FastSeg sg;                                                      // 2 x 16 B, the same for all threads
+    {
+        const uint4* sp = reinterpret_cast<const uint4*>(p.segs + blockIdx.x);
+        uint4* dp = reinterpret_cast<uint4*>(&sg);
+        dp[0] = __ldg(sp); dp[1] = __ldg(sp + 1);
+    }
+    const int l = sg.level;
     const LevelGeom& L = g.lv[l];
-    const int c = cell - L.cellBase;
-    const int ci = c / L.nCols, cj = c - ci * L.nCols;
-    uint2* info = p.cellInfo + (long long)f * g.totalCells + cell;
-
-    const int iniY = kMinBorder + ci * L.hCell, iniX = kMinBorder + cj * L.wCell;
-    int maxY = iniY + L.hCell + 6, maxX = iniX + L.wCell + 6;
-    const bool skip = (iniY >= L.maxBY - 3) || (iniX >= L.maxBX - 6);      // :756, :765
-    if (maxY > L.maxBY) maxY = L.maxBY;
-    if (maxX > L.maxBX) maxX = L.maxBX;
-    const int cw = maxX - iniX, ch = maxY - iniY;
-    if (skip || cw < 7 || ch < 7) {
-        if (tid == 0) *info = make_uint2(0u, 0u);
+    uint2* info = p.cellInfo + (long long)f * g.totalCells + sg.cell0;
+    const int nv = sg.nv, ih = sg.ih, iw = sg.iw;
+    if (nv == 0) {
+        if (tid < sg.nc) info[tid] = make_uint2(0u, 0u);
         return;
     }
-    // TMA needs a 16-byte aligned start in x: the box starts at xa <= iniX-1, the interior at tile column o+4
+    const int wCell = L.wCell;
+    // TMA needs a 16-byte aligned start in x: the box starts at xa <= iniX0-1, the interior at tile column o+4
+    const int iniX = sg.iniX0, iniY = sg.iniY;
     const int xa = (iniX - 1) & ~15, o = iniX - 1 - xa;
     const int pitch = L.boxW;
     const unsigned barAddr = smem_u32(&bar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_q = 0; s_empty = 0;
     }
-    const int iw = cw - 6, ih = ch - 6;
-    for (int i = tid; i < (pitch * L.boxH + 64) / 16; i += 128) reinterpret_cast<uint4*>(smap)[i] = make_uint4(0, 0, 0, 0);
-    const int nmask = (iw * ih + 31) >> 5;
-    for (int i = tid; i < nmask; i += 128) kmask[i] = 0u;
     __syncthreads();
     if (tid == 0) {
         const unsigned bytes = (unsigned)(pitch * L.boxH);
@@ -271,6 +289,12 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
             "l"(&maps.m[l]), "r"(xa), "r"(iniY), "r"(f + p.frameBase), "r"(barAddr)
             : "memory");
     }
+    // while the tile is in flight: clear the score map and the bit mask
+    const int wpr = (iw + 31) >> 5;                  // mask words per interior row
+    const int nmask = wpr * ih;
+    for (int i = tid; i < (pitch * L.boxH + 64) / 16; i += NT) reinterpret_cast<uint4*>(smap)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < nmask; i += NT) kmask[i] = 0u;
+    if (tid < kFastMaxSegCells) s_cnt[tid] = 0;
     {
         unsigned done = 0;
         while (!done) {
@@ -281,142 +305,181 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(const __grid_constant__
                 : "memory");
         }
     }
+    __syncthreads();
 
     const int c_lo = o + 4, c_hi = o + 4 + iw;      // interior tile columns [c_lo, c_hi)
     const int gx0 = c_lo >> 2;
-    const int ngx = ((c_hi - 1) >> 2) - gx0 + 1, ngroups = ngx * ih;
-    const unsigned magicG = 0xFFFFFFFFu / (unsigned)ngx + 1u;      // exact floor(n / ngx) for n < 65536
-    const unsigned magicW = 0xFFFFFFFFu / (unsigned)iw + 1u;
+    const int ngx = ((c_hi - 1) >> 2) - gx0 + 1;    // word columns that hold interior pixels
     const unsigned* tile32 = reinterpret_cast<const unsigned*>(tile);
     const int pw = pitch >> 2;
+    // stage A work items: (word column, chunk of rows); the chunks make one round of the CTA's threads
+    const int nChunks = min(max(NT / ngx, 1), ih);
+    const int rc = (ih + nChunks - 1) / nChunks;
+    const int nItems = ngx * nChunks;
+    unsigned emptyCells = 0;                         // pass 1: cells without a keypoint at iniTh
 
-    int th = iniTh, total = 0;
+    int th = iniTh;
     for (int pass = 0; pass < 2; ++pass) {
         th = pass == 0 ? iniTh : minTh;
-        if (tid == 0) { s_q = 0; s_cnt = 0; }
-        __syncthreads();
-        // stage A: antipodal-pair rejection on 4 pixels at a time (necessary condition for score >= th);
-        // survivors are queued as (row << 7 | column)
         const unsigned kk = (unsigned)(0x7f - min(th, 127)) * 0x01010101u;
-        for (int base = 0; base < ngroups; base += 128) {
-            const int gi = base + tid;
-            unsigned alive = 0;
-            int row = 0, cb = 0;
-            if (gi < ngroups) {
-                const int yy = (int)__umulhi((unsigned)gi, magicG), gx = gi - yy * ngx;
-                row = yy + 3;
-                const int widx = row * pw + gx0 + gx;
-                const unsigned C = tile32[widx];
-                cb = 4 * (gx0 + gx);                                     // tile column of byte 0
-                const int first = max(c_lo - cb, 0), last = min(c_hi - cb, 4);     // valid bytes [first, last)
-                alive = (0x80808080u >> (8 * (4 - last))) & (0x80808080u << (8 * first));
-                if (th < 128) {
-                    const unsigned up = tile32[widx + 3 * pw], dn = tile32[widx - 3 * pw];
-                    alive &= gt_bytes2(__vabsdiffu4(up, C), __vabsdiffu4(dn, C), kk);
-                    if (alive) {
-                        const unsigned Lw = tile32[widx - 1], Rw = tile32[widx + 1];
-                        const unsigned left3 = __byte_perm(Lw, C, 0x4321), right3 = __byte_perm(C, Rw, 0x6543);
-                        alive &= gt_bytes2(__vabsdiffu4(left3, C), __vabsdiffu4(right3, C), kk);
-                    }
-                }
-            }
-            if (__ballot_sync(0xffffffffu, alive != 0u)) {
-                const int n = __popc(alive);
-                int incl = n;
+        const bool reject = th < 128;
+        for (int it = tid; it < nItems; it += NT) {
+            const int chunk = it / ngx, gx = it - chunk * ngx;
+            const int wc = gx0 + gx, cb = 4 * wc;                      // tile column of byte 0
+            const int first = max(c_lo - cb, 0), last = min(c_hi - cb, 4);      // interior bytes [first, last)
+            unsigned vmask = (0x80808080u >> (8 * (4 - last))) & (0x80808080u << (8 * first));
+            if (pass) {                                                // only the pixels of the cells that came out empty
+                unsigned m = 0;
 #pragma unroll
-                for (int ofs = 1; ofs < 32; ofs <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
-                    if (lane >= ofs) incl += t;
+                for (int b = 0; b < 4; ++b) {
+                    const int xx = min(max(cb + b - c_lo, 0), iw - 1);
+                    if ((emptyCells >> __umulhi((unsigned)xx, L.magicW)) & 1u) m |= 0x80u << (8 * b);
                 }
-                int wbase = 0;
-                if (lane == 31) wbase = atomicAdd(&s_q, incl);
-                wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                int pos = wbase + incl - n;
-                while (alive) {
-                    const int b = (__ffs(alive) - 1) >> 3;
-                    alive &= alive - 1;
-                    queue[pos++] = (unsigned short)((row << 7) | (cb + b));
-                }
+                vmask &= m;
             }
+            int r = 3 + chunk * rc;
+            const int rEnd = min(r + rc, 3 + ih);
+            if (vmask == 0u || r >= rEnd) continue;
+            const unsigned* tp = tile32 + (r - 3) * pw + wc;
+            unsigned w0 = tp[0], w1 = tp[pw], w2 = tp[2 * pw], w3 = tp[3 * pw], w4 = tp[4 * pw], w5 = tp[5 * pw], w6;
+            tp += 3 * pw;                                              // -> row r
+            // one row: the word entering the window is row r+3; (a0 .. a6) = rows r-3 .. r+3 of this column
+#define NAV24_STEP(a0, a1, a2, a3, a4, a5, a6)                                                             \
+            {                                                                                              \
+                a6 = tp[3 * pw];                                                                           \
+                const unsigned C = a3;                                                                     \
+                unsigned alive = vmask;                                                                    \
+                if (reject) {                                                                              \
+                    const unsigned Lw = tp[-1], Rw = tp[1];                                                \
+                    alive &= gt_bytes2(__vabsdiffu4(a0, C), __vabsdiffu4(a6, C), kk);                      \
+                    alive &= gt_bytes2(__vabsdiffu4(__byte_perm(Lw, C, 0x4321), C),                        \
+                                       __vabsdiffu4(__byte_perm(C, Rw, 0x6543), C), kk);                   \
+                }                                                                                          \
+                if (alive) {                                                                               \
+                    int pos = atomicAdd(&s_q, __popc(alive));                                              \
+                    const unsigned e = (unsigned)((r << 9) | cb);                                          \
+                    if (alive & 0x80u) queue[pos++] = (unsigned short)e;                                   \
+                    if (alive & 0x8000u) queue[pos++] = (unsigned short)(e + 1);                           \
+                    if (alive & 0x800000u) queue[pos++] = (unsigned short)(e + 2);                         \
+                    if (alive & 0x80000000u) queue[pos] = (unsigned short)(e + 3);                         \
+                }                                                                                          \
+                tp += pw;                                                                                  \
+                if (++r >= rEnd) break;                                                                    \
+            }
+            while (true) {
+                NAV24_STEP(w0, w1, w2, w3, w4, w5, w6)
+                NAV24_STEP(w1, w2, w3, w4, w5, w6, w0)
+                NAV24_STEP(w2, w3, w4, w5, w6, w0, w1)
+                NAV24_STEP(w3, w4, w5, w6, w0, w1, w2)
+                NAV24_STEP(w4, w5, w6, w0, w1, w2, w3)
+                NAV24_STEP(w5, w6, w0, w1, w2, w3, w4)
+                NAV24_STEP(w6, w0, w1, w2, w3, w4, w5)
+            }
+#undef NAV24_STEP
         }
         __syncthreads();
-        // stage B: exact score of the survivors, balanced over the CTA; stage C: 3x3 non-max suppression of the
-        // scored pixels -> bit (row-major interior index) in kmask
+        // stage B: exact score of the survivors, balanced over the CTA
         const int nq = s_q;
-        for (int qi = tid; qi < nq; qi += 128) {
+        for (int qi = tid; qi < nq; qi += NT) {
             const int e = queue[qi];
-            const int idx = (e >> 7) * pitch + (e & 127);
+            const int idx = (e >> 9) * pitch + (e & 511);
             const int s = fast_score(tile + idx, pitch);
             if (s >= th) smap[idx] = (uint8_t)s; else queue[qi] = 0xffffu;
         }
         __syncthreads();
-        for (int qi = tid; qi < nq; qi += 128) {
+        // stage C: 3x3 non-max suppression; the neighbours in the adjacent cell's interior count as 0
+        for (int qi = tid; qi < nq; qi += NT) {
             const int e = queue[qi];
             if (e == 0xffff) continue;
-            const int row = e >> 7, col = e & 127;
+            const int row = e >> 9, col = e & 511;
             const uint8_t* q = smap + row * pitch + col;
+            const int xx = col - c_lo;
+            const int cl = xx - (int)__umulhi((unsigned)xx, L.magicW) * wCell;      // column inside the cell's interior
             const int s = q[0];
-            if (s > q[-1] && s > q[1] && s > q[-pitch - 1] && s > q[-pitch] && s > q[-pitch + 1] && s > q[pitch - 1] &&
-                s > q[pitch] && s > q[pitch + 1]) {
-                const int bi = (row - 3) * iw + (col - c_lo);
+            int m = max((int)q[-pitch], (int)q[pitch]);
+            const int ml = max(max((int)q[-pitch - 1], (int)q[-1]), (int)q[pitch - 1]);
+            const int mr = max(max((int)q[-pitch + 1], (int)q[1]), (int)q[pitch + 1]);
+            if (cl > 0) m = max(m, ml);
+            if (cl < wCell - 1) m = max(m, mr);
+            if (s > m) {
+                const int bi = (row - 3) * (wpr << 5) + xx;
                 atomicOr(&kmask[bi >> 5], 1u << (bi & 31));
             }
         }
         __syncthreads();
-        int cnt = 0;
-        for (int i = tid; i < nmask; i += 128) cnt += __popc(kmask[i]);
+        // keypoints per cell: one warp per cell, lanes over the rows
+        for (int k = wid; k < nv; k += NW) {
+            if (pass && !((emptyCells >> k) & 1u)) continue;
+            const int x0 = k * wCell, x1 = min(x0 + wCell, iw);
+            int cnt = 0;
+            for (int row = lane; row < ih; row += 32) cnt += mask_range_count(kmask + row * wpr, x0, x1);
 #pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, ofs);
-        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+            for (int ofs = 16; ofs > 0; ofs >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, ofs);
+            if (lane == 0) {
+                s_cnt[k] = cnt;
+                if (cnt == 0 && pass == 0) atomicOr(&s_empty, 1 << k);
+            }
+        }
         __syncthreads();
-        total = s_cnt;
-        if (total > 0) break;                       // :787 "if(vKeysCell.empty())" -> retry at minThFAST
+        emptyCells = (unsigned)s_empty;
+        if (pass || emptyCells == 0u || minTh >= iniTh) break;      // :787 "if(vKeysCell.empty())" -> retry at minThFAST
+        if (tid == 0) s_q = 0;
         __syncthreads();
     }
 
     if (tid == 0) {
+        int total = 0;
+        for (int k = 0; k < nv; ++k) { s_off[k] = total; total += s_cnt[k]; }
         int base = 0;
         if (total > 0) {
             base = atomicAdd(p.rawCount + f * g.nlevels + l, total);
             if (base + total > L.rawCap) { atomicOr(p.err, ERR_RAW_OVERFLOW); base = -1; }
         }
         s_base = base;
-        *info = make_uint2((unsigned)max(base, 0), base < 0 ? 0u : (unsigned)total);
+        for (int k = 0; k < sg.nc; ++k)
+            info[k] = (k < nv && base >= 0) ? make_uint2((unsigned)(base + s_off[k]), (unsigned)s_cnt[k]) : make_uint2(0u, 0u);
     }
     __syncthreads();
-    if (total == 0 || s_base < 0) return;
-    RawRec* out = p.raw + (long long)f * g.rawPerFrame + L.rawOff + s_base;
+    if (s_base < 0) return;
+    RawRec* outL = p.raw + (long long)f * g.rawPerFrame + L.rawOff + s_base;
 
-    // ordered emit: bit order of kmask is the row-major order cv::FAST reports
-    int run = 0;
-    for (int base = 0; base < nmask; base += 128) {
-        const int wi = base + tid;
-        unsigned bits = wi < nmask ? kmask[wi] : 0u;
-        const int n = __popc(bits);
-        int incl = n;
+    // ordered emit: row-major inside each cell, the order cv::FAST reports
+    for (int k = wid; k < nv; k += NW) {
+        if (s_cnt[k] == 0) continue;
+        const int x0 = k * wCell, x1 = min(x0 + wCell, iw);
+        RawRec* out = outL + s_off[k];
+        const int xBase = 3 + sg.cj0 * wCell, yBase = 3 + sg.ci * L.hCell;      // :811-812, relative to (minBorderX, minBorderY)
+        int run = 0;
+        for (int r0 = 0; r0 < ih; r0 += 32) {
+            const int row = r0 + lane;
+            const unsigned* rowp = kmask + row * wpr;
+            const int n = row < ih ? mask_range_count(rowp, x0, x1) : 0;
+            int incl = n;
 #pragma unroll
-        for (int ofs = 1; ofs < 32; ofs <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
-            if (lane >= ofs) incl += t;
+            for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+                if (lane >= ofs) incl += t;
+            }
+            int pos = run + incl - n;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+            if (n) {
+                const int wlo = x0 >> 5, whi = (x1 - 1) >> 5;
+                for (int w = wlo; w <= whi; ++w) {
+                    unsigned bits = rowp[w];
+                    if (w == wlo) bits &= 0xffffffffu << (x0 & 31);
+                    if (w == whi) bits &= 0xffffffffu >> (31 - ((x1 - 1) & 31));
+                    while (bits) {
+                        const int xx = w * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        RawRec r;
+                        r.x = (unsigned short)(xx + xBase);
+                        r.y = (unsigned short)(row + yBase);
+                        r.score = smap[(row + 3) * pitch + c_lo + xx]; r.pad = 0;
+                        out[pos++] = r;
+                    }
+                }
+            }
         }
-        if (lane == 31) s_wsum[wid] = incl;
-        __syncthreads();
-        int wbase = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { const int v = s_wsum[w]; if (w < wid) wbase += v; tot += v; }
-        int pos = run + wbase + incl - n;
-        while (bits) {
-            const int bi = wi * 32 + __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int yy = (int)__umulhi((unsigned)bi, magicW), xx = bi - yy * iw;
-            RawRec r;
-            r.x = (unsigned short)(xx + 3 + cj * L.wCell);     // :811-812, relative to (minBorderX, minBorderY)
-            r.y = (unsigned short)(yy + 3 + ci * L.hCell);
-            r.score = smap[(yy + 3) * pitch + c_lo + xx]; r.pad = 0;
-            out[pos++] = r;
-        }
-        run += tot;
-        __syncthreads();
     }
 }
 
@@ -1051,23 +1114,25 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
     cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
     FastSmem sm{};
-    int tileBytes = 0, qcap = 0;
+    int tileBytes = 0, qcap = 0, mwords = 0;
     for (int l = 0; l < g.nlevels; ++l) {
-        tileBytes = max(tileBytes, g.lv[l].boxW * g.lv[l].boxH + 64);
-        qcap = max(qcap, g.lv[l].wCell * g.lv[l].hCell);
+        const LevelGeom& L = g.lv[l];
+        tileBytes = max(tileBytes, L.boxW * L.boxH + 64);
+        qcap = max(qcap, L.segCols * L.wCell * L.hCell);                      // every interior pixel may survive stage A
+        mwords = max(mwords, ((L.segCols * L.wCell + 31) / 32) * L.hCell);
     }
     tileBytes = (tileBytes + 127) / 128 * 128;
     sm.offMap = tileBytes;
     sm.offQueue = 2 * tileBytes;
     sm.offMask = sm.offQueue + (qcap * 2 + 15) / 16 * 16;
-    sm.total = sm.offMask + ((qcap + 31) / 32) * 4 + 16;
+    sm.total = sm.offMask + mwords * 4 + 16;
     static int attrSet = 0;
     if (sm.total > attrSet) {
-        cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
+        cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
         attrSet = max(sm.total, 48 * 1024);
     }
-    dim3 grid(g.totalCells, B);
-    fast_cells_kernel<<<grid, 128, sm.total, s>>>(g, p, maps, sm, iniTh, minTh);
+    dim3 grid(g.totalSegs, B);
+    fast_band_kernel<<<grid, kFastThreads, sm.total, s>>>(g, p, maps, sm, iniTh, minTh);
     return 1;
 }
 
