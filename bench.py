@@ -295,7 +295,7 @@ def main():
     alg_bytes_frame = pix + 12.0 * raw_per_frame            # B_pyrFAST
     pf_ms = float(stage[0] + stage[1]) / max(calls, 1)      # per step
     achieved = alg_bytes_frame * F / (pf_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pyramid (resize_kernel x7) + FAST (fast_cells_kernel)",
+    roofline = {"bound": "hbm", "kernel": "pyramid (resize_kernel x7) + FAST (fast_band_kernel)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_frame * F,
                 "avg_ms_per_step": pf_ms,

@@ -159,12 +159,11 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         if (L.wCell + 6 > kMaxCellTile || L.hCell + 6 > kMaxCellTile) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
         // FAST segments: runs of cells of one cell row whose tile (interior + 3-px rim + <= 16 px of alignment slack)
         // fits one TMA box (<= 256 px wide); the cells of a row are dealt evenly over the segments
-        const int fit = std::min(kFastMaxSegCells, (256 - 22) / L.wCell);
+        const int fit = std::min(kFastMaxSegCells, (kFastPitch - 22) / L.wCell);
         L.segsPerRow = (L.nCols + fit - 1) / fit;
         L.segCols = (L.nCols + L.segsPerRow - 1) / L.segsPerRow;
         L.segsPerRow = (L.nCols + L.segCols - 1) / L.segCols;
-        L.boxW = align_up(L.segCols * L.wCell + 7 + 15, 16);
-        if (((L.boxW / 16) & 1) == 0 && L.boxW + 16 <= 256) L.boxW += 16;     // 16 x odd: conflict-free over 8 rows
+        L.boxW = kFastPitch;
         L.boxH = L.hCell + 6;
         L.magicW = 0xFFFFFFFFu / (unsigned)L.wCell + 1u;
         L.cellBase = cellBase;
@@ -243,6 +242,13 @@ void build_fast_segments(const FrameGeom& g, std::vector<FastSeg>& segs) {
                     ++nv; iw += maxX - iniX - 6;
                 }
                 s.nv = (short)nv; s.iw = (short)iw; s.ih = (short)(nv ? maxY - iniY - 6 : 0);
+                if (nv) {
+                    const int o = (s.iniX0 - 1) & 15, c_lo = o + 4, c_hi = c_lo + iw;
+                    s.ngx = (short)(((c_hi - 1) >> 2) - (c_lo >> 2) + 1);
+                    s.nChunks = (short)std::min(std::max(kFastThreads / s.ngx, 1), (int)s.ih);
+                    s.rc = (short)((s.ih + s.nChunks - 1) / s.nChunks);
+                    s.magicG = 0xFFFFFFFFu / (unsigned)s.ngx + 1u;
+                }
                 segs.push_back(s);
             }
     }

@@ -21,6 +21,9 @@ constexpr int kBlurTileRows = NAV24_BLUR_ROWS;   // rows per warp tile of blur_k
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
 constexpr int kFastThreads = 256;   // threads per CTA of fast_band_kernel
 constexpr int kFastMaxSegCells = 8; // cells of one FAST segment (TMA boxes are <= 256 px wide, cells >= 35 px)
+constexpr int kFastQueueCap = 3072; // stage A survivors one CTA queues (typ. 700 of 8400 pixels); beyond: the dense path
+constexpr int kFastPitch = 256;     // row pitch of the FAST tile in shared memory = TMA box width, the same for every level, so
+                                    // that every tap of the kernel is an immediate offset
 
 // device error bits (ctx->d_err)
 enum : int { ERR_RAW_OVERFLOW = 1, ERR_ROOT_RANGE = 2, ERR_NODE_OVERFLOW = 4, ERR_CELL_SIZE = 8, ERR_KP_OVERFLOW = 16 };
@@ -33,7 +36,7 @@ struct LevelGeom {
     // FAST cell grid (OP_FtDtOrbSlam.cpp:735-768)
     int nCols, nRows, wCell, hCell, maxBX, maxBY;
     int segCols, segsPerRow; // FAST segment = segCols horizontally adjacent cells of one cell row (the last may hold fewer)
-    int boxW, boxH;          // TMA box of one FAST segment: 16*odd >= segCols*wCell+6+1+15 (<= 256) x (hCell+6)
+    int boxW, boxH;          // TMA box of one FAST segment: kFastPitch x (hCell+6)
     unsigned magicW;         // 0xFFFFFFFF / wCell + 1: floor(n / wCell) = umulhi(n, magicW) for n < 65536
     int cellBase;            // first cell id of this level inside the per-frame cell table
     int blurTileBase;        // first warp tile (128 px x kBlurTileRows rows) of this level in blur_kernel
@@ -73,8 +76,10 @@ struct RawRec {              // one FAST survivor, 8 bytes
 struct FastSeg {             // one CTA of fast_band_kernel: a run of cells of one cell row (host-built, 32 bytes)
     short level, ci, cj0, nc;       // nc cells [cj0, cj0+nc) of cell row ci (entries of the cell table, skipped ones included)
     short nv, iniX0, iniY, ih;      // nv valid cells (a prefix of the nc), image position of the tile, interior rows
-    short iw, pad0, pad1, pad2;     // interior columns of the nv cells together
-    int cell0, pad3;                // first cell of the segment in the per-frame cell table
+    short iw, ngx, nChunks, rc;     // interior columns of the nv cells together; stage A items: ngx word columns x
+                                    // nChunks chunks of rc rows (one round of the CTA's threads)
+    int cell0;                      // first cell of the segment in the per-frame cell table
+    unsigned magicG;                // 0xFFFFFFFF / ngx + 1
 };
 
 struct QNode {               // 12 bytes
@@ -120,7 +125,7 @@ struct DevPtrs {
 
 struct TmaMaps { CUtensorMap m[kMaxLevels]; };   // one 3-D (x, y, frame) u8 tensor map per pyramid level
 
-struct FastSmem { int offMap, offQueue, offMask, total; };   // dynamic shared memory layout of fast_band_kernel
+struct FastSmem { int offMap, offMask, offQueue, offWin, total; };   // dynamic shared memory layout of fast_band_kernel
 
 struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;

@@ -217,15 +217,15 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int pitch) {
     return (int)max(b0 & 0xffffu, b0 >> 16) - 257;
 }
 
-// per-byte (x > t) for t < 128: 0x80 in every byte that passes.  k = (0x7f - t) * 0x01010101
-__device__ __forceinline__ unsigned gt_bytes2(unsigned x1, unsigned x2, unsigned k) {
-    const unsigned s1 = (x1 & 0x7f7f7f7fu) + k, s2 = (x2 & 0x7f7f7f7fu) + k;
-    return (s1 | x1 | s2 | x2) & 0x80808080u;
-}
+// Conservative per-byte (x1 > t || x2 > t) for t < 128: 0x80 in every byte that passes.  k = (0x7f - t) * 0x01010101.
+// The adds run over the whole word: a byte >= 129 + t carries into its neighbour, which can only make the neighbour
+// pass when it equals t (a false positive of the FILTER, removed by the exact score), and the overflowing byte
+// itself has bit 7 set, so it passes through the "| x" term.
+__device__ __forceinline__ unsigned gt_any2(unsigned x1, unsigned x2, unsigned k) { return (x1 + k) | x1 | (x2 + k) | x2; }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// set bits of kmask row `rowp` inside the column range [x0, x1): popcount
+// set bits of kmask row `rowp` inside the column range [x0, x1), x1 > x0: popcount
 __device__ __forceinline__ int mask_range_count(const unsigned* rowp, int x0, int x1) {
     const int wlo = x0 >> 5, whi = (x1 - 1) >> 5;
     int n = 0;
@@ -238,19 +238,22 @@ __device__ __forceinline__ int mask_range_count(const unsigned* rowp, int x0, in
     return n;
 }
 
-// Dynamic shared memory: [tile | score map | queue u16 | keypoint bit mask], sizes from FastSmem.
+// Dynamic shared memory: [tile | score map | keypoint bit mask | queue u16 | winner list u16], sizes from FastSmem.
+// Queue and winner entries are the byte offset of the pixel inside the tile (row * kFastPitch + column).
 __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                                  const __grid_constant__ TmaMaps maps, const FastSmem sm,
                                                                  int iniTh, int minTh) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
     uint8_t* tile = s_dyn;
     uint8_t* smap = s_dyn + sm.offMap;
-    unsigned short* queue = reinterpret_cast<unsigned short*>(s_dyn + sm.offQueue);
     unsigned* kmask = reinterpret_cast<unsigned*>(s_dyn + sm.offMask);
+    unsigned short* queue = reinterpret_cast<unsigned short*>(s_dyn + sm.offQueue);
+    unsigned short* winners = reinterpret_cast<unsigned short*>(s_dyn + sm.offWin);
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ int s_q, s_base, s_empty;
-    __shared__ int s_cnt[kFastMaxSegCells], s_off[kFastMaxSegCells];
-    constexpr int NT = kFastThreads, NW = kFastThreads / 32;
+    __shared__ int s_q, s_nw, s_ovf, s_empty;
+    __shared__ int s_off[kFastMaxSegCells];
+    __shared__ unsigned short s_rowpre[kFastMaxSegCells][kMaxCellTile];      // keypoints of the cell above each row
+    constexpr int NT = kFastThreads, NW = kFastThreads / 32, P = kFastPitch, PW = kFastPitch / 4;
 
     const int tid = threadIdx.x, f = blockIdx.y;
     const int lane = tid & 31, wid = tid >> 5;
@@ -272,16 +275,16 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     // TMA needs a 16-byte aligned start in x: the box starts at xa <= iniX0-1, the interior at tile column o+4
     const int iniX = sg.iniX0, iniY = sg.iniY;
     const int xa = (iniX - 1) & ~15, o = iniX - 1 - xa;
-    const int pitch = L.boxW;
+    const int boxH = L.boxH;
     const unsigned barAddr = smem_u32(&bar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_q = 0; s_empty = 0;
+        s_q = 0; s_nw = 0; s_ovf = 0; s_empty = 0;
     }
     __syncthreads();
     if (tid == 0) {
-        const unsigned bytes = (unsigned)(pitch * L.boxH);
+        const unsigned bytes = (unsigned)(P * boxH);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -289,12 +292,14 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
             "l"(&maps.m[l]), "r"(xa), "r"(iniY), "r"(f + p.frameBase), "r"(barAddr)
             : "memory");
     }
-    // while the tile is in flight: clear the score map and the bit mask
+    // while the tile is in flight: clear the score map and the bit mask behind it (one range of 16-byte stores)
     const int wpr = (iw + 31) >> 5;                  // mask words per interior row
-    const int nmask = wpr * ih;
-    for (int i = tid; i < (pitch * L.boxH + 64) / 16; i += NT) reinterpret_cast<uint4*>(smap)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < nmask; i += NT) kmask[i] = 0u;
-    if (tid < kFastMaxSegCells) s_cnt[tid] = 0;
+    {
+        const int n16 = (sm.offMask - sm.offMap) / 16 + (wpr * ih + 3) / 4;
+        uint4* z = reinterpret_cast<uint4*>(smap);
+        for (int i = tid; i < n16; i += NT) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid >= nv && tid < sg.nc) info[tid] = make_uint2(0u, 0u);      // skipped cells (:756, :765)
     {
         unsigned done = 0;
         while (!done) {
@@ -309,13 +314,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
 
     const int c_lo = o + 4, c_hi = o + 4 + iw;      // interior tile columns [c_lo, c_hi)
     const int gx0 = c_lo >> 2;
-    const int ngx = ((c_hi - 1) >> 2) - gx0 + 1;    // word columns that hold interior pixels
-    const unsigned* tile32 = reinterpret_cast<const unsigned*>(tile);
-    const int pw = pitch >> 2;
-    // stage A work items: (word column, chunk of rows); the chunks make one round of the CTA's threads
-    const int nChunks = min(max(NT / ngx, 1), ih);
-    const int rc = (ih + nChunks - 1) / nChunks;
-    const int nItems = ngx * nChunks;
+    const int ngx = sg.ngx, rc = sg.rc;             // stage A work items: (word column, chunk of rc rows), one round
+    const int nItems = ngx * sg.nChunks;
     unsigned emptyCells = 0;                         // pass 1: cells without a keypoint at iniTh
 
     int th = iniTh;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
         const unsigned kk = (unsigned)(0x7f - min(th, 127)) * 0x01010101u;
         const bool reject = th < 128;
         for (int it = tid; it < nItems; it += NT) {
-            const int chunk = it / ngx, gx = it - chunk * ngx;
+            const int chunk = (int)__umulhi((unsigned)it, sg.magicG), gx = it - chunk * ngx;
             const int wc = gx0 + gx, cb = 4 * wc;                      // tile column of byte 0
             const int first = max(c_lo - cb, 0), last = min(c_hi - cb, 4);      // interior bytes [first, last)
             unsigned vmask = (0x80808080u >> (8 * (4 - last))) & (0x80808080u << (8 * first));
@@ -337,34 +337,41 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                 }
                 vmask &= m;
             }
-            int r = 3 + chunk * rc;
-            const int rEnd = min(r + rc, 3 + ih);
-            if (vmask == 0u || r >= rEnd) continue;
-            const unsigned* tp = tile32 + (r - 3) * pw + wc;
-            unsigned w0 = tp[0], w1 = tp[pw], w2 = tp[2 * pw], w3 = tp[3 * pw], w4 = tp[4 * pw], w5 = tp[5 * pw], w6;
-            tp += 3 * pw;                                              // -> row r
-            // one row: the word entering the window is row r+3; (a0 .. a6) = rows r-3 .. r+3 of this column
-#define NAV24_STEP(a0, a1, a2, a3, a4, a5, a6)                                                             \
-            {                                                                                              \
-                a6 = tp[3 * pw];                                                                           \
-                const unsigned C = a3;                                                                     \
-                unsigned alive = vmask;                                                                    \
-                if (reject) {                                                                              \
-                    const unsigned Lw = tp[-1], Rw = tp[1];                                                \
-                    alive &= gt_bytes2(__vabsdiffu4(a0, C), __vabsdiffu4(a6, C), kk);                      \
-                    alive &= gt_bytes2(__vabsdiffu4(__byte_perm(Lw, C, 0x4321), C),                        \
-                                       __vabsdiffu4(__byte_perm(C, Rw, 0x6543), C), kk);                   \
-                }                                                                                          \
-                if (alive) {                                                                               \
-                    int pos = atomicAdd(&s_q, __popc(alive));                                              \
-                    const unsigned e = (unsigned)((r << 9) | cb);                                          \
-                    if (alive & 0x80u) queue[pos++] = (unsigned short)e;                                   \
-                    if (alive & 0x8000u) queue[pos++] = (unsigned short)(e + 1);                           \
-                    if (alive & 0x800000u) queue[pos++] = (unsigned short)(e + 2);                         \
-                    if (alive & 0x80000000u) queue[pos] = (unsigned short)(e + 3);                         \
-                }                                                                                          \
-                tp += pw;                                                                                  \
-                if (++r >= rEnd) break;                                                                    \
+            const int r0 = 3 + chunk * rc, r1 = min(r0 + rc, 3 + ih);
+            if (vmask == 0u || r0 >= r1) continue;
+            const uint8_t* tp = tile + r0 * P + cb;                    // this column's word of row r
+            const uint8_t* tEnd = tile + r1 * P + cb;
+#define NAV24_W(dy) (*reinterpret_cast<const unsigned*>(tp + (dy) * P))
+            unsigned w0 = NAV24_W(-3), w1 = NAV24_W(-2), w2 = NAV24_W(-1), w3 = NAV24_W(0), w4 = NAV24_W(1), w5 = NAV24_W(2), w6;
+            // one row: the word entering the window is row r+3; (a0 .. a6) = rows r-3 .. r+3 of this column.
+            // (Collecting the survivors of seven rows in a register and queueing them with a per-lane loop measured
+            // slower: vertical edges put all of a column's survivors into one lane.)
+#define NAV24_STEP(a0, a1, a2, a3, a4, a5, a6)                                                                       \
+            {                                                                                                        \
+                a6 = NAV24_W(3);                                                                                     \
+                const unsigned C = a3;                                                                               \
+                unsigned alive = vmask;                                                                              \
+                if (reject) {                                                                                        \
+                    const unsigned Lw = *reinterpret_cast<const unsigned*>(tp - 4);                                  \
+                    const unsigned Rw = *reinterpret_cast<const unsigned*>(tp + 4);                                  \
+                    alive &= gt_any2(__vabsdiffu4(a0, C), __vabsdiffu4(a6, C), kk) &                                 \
+                             gt_any2(__vabsdiffu4(__byte_perm(Lw, C, 0x4321), C),                                    \
+                                     __vabsdiffu4(__byte_perm(C, Rw, 0x6543), C), kk);                               \
+                }                                                                                                    \
+                if (alive) {                                                                                         \
+                    int pos = atomicAdd(&s_q, __popc(alive));                                                        \
+                    const unsigned e = (unsigned)(tp - tile);                                                        \
+                    if (pos + 4 <= kFastQueueCap) {      /* else: s_q > cap -> the dense path below */                \
+                        if (alive & 0x80u) queue[pos++] = (unsigned short)e;                                         \
+                        if (alive & 0x8000u) queue[pos++] = (unsigned short)(e + 1);                                 \
+                        if (alive & 0x800000u) queue[pos++] = (unsigned short)(e + 2);                               \
+                        if (alive & 0x80000000u) queue[pos] = (unsigned short)(e + 3);                               \
+                    } else {                                                                                         \
+                        s_ovf = 1;                                                                                   \
+                    }                                                                                                \
+                }                                                                                                    \
+                tp += P;                                                                                             \
+                if (tp == tEnd) break;                                                                               \
             }
             while (true) {
                 NAV24_STEP(w0, w1, w2, w3, w4, w5, w6)
@@ -376,110 +383,127 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                 NAV24_STEP(w6, w0, w1, w2, w3, w4, w5)
             }
 #undef NAV24_STEP
+#undef NAV24_W
         }
         __syncthreads();
-        // stage B: exact score of the survivors, balanced over the CTA
-        const int nq = s_q;
-        for (int qi = tid; qi < nq; qi += NT) {
-            const int e = queue[qi];
-            const int idx = (e >> 9) * pitch + (e & 511);
-            const int s = fast_score(tile + idx, pitch);
-            if (s >= th) smap[idx] = (uint8_t)s; else queue[qi] = 0xffffu;
-        }
-        __syncthreads();
-        // stage C: 3x3 non-max suppression; the neighbours in the adjacent cell's interior count as 0
-        for (int qi = tid; qi < nq; qi += NT) {
-            const int e = queue[qi];
-            if (e == 0xffff) continue;
-            const int row = e >> 9, col = e & 511;
-            const uint8_t* q = smap + row * pitch + col;
-            const int xx = col - c_lo;
+        // stage C body: 3x3 non-max suppression of the corner at tile offset e; the neighbours in the adjacent cell's
+        // interior count as 0
+        auto nms = [&](int e) {
+            const uint8_t* q = smap + e;
+            const int xx = (e & (P - 1)) - c_lo;
             const int cl = xx - (int)__umulhi((unsigned)xx, L.magicW) * wCell;      // column inside the cell's interior
             const int s = q[0];
-            int m = max((int)q[-pitch], (int)q[pitch]);
-            const int ml = max(max((int)q[-pitch - 1], (int)q[-1]), (int)q[pitch - 1]);
-            const int mr = max(max((int)q[-pitch + 1], (int)q[1]), (int)q[pitch + 1]);
+            int m = max((int)q[-P], (int)q[P]);
+            const int ml = max(max((int)q[-P - 1], (int)q[-1]), (int)q[P - 1]);
+            const int mr = max(max((int)q[-P + 1], (int)q[1]), (int)q[P + 1]);
             if (cl > 0) m = max(m, ml);
             if (cl < wCell - 1) m = max(m, mr);
             if (s > m) {
-                const int bi = (row - 3) * (wpr << 5) + xx;
+                static_assert(kFastPitch == 256, "row = offset >> 8");
+                const int bi = ((e >> 8) - 3) * (wpr << 5) + xx;
                 atomicOr(&kmask[bi >> 5], 1u << (bi & 31));
+                winners[atomicAdd(&s_nw, 1)] = (unsigned short)e;
             }
+        };
+        if (!s_ovf) {
+            // stage B: exact score of the survivors.  Each warp owns a contiguous slice of the queue and compacts the
+            // pixels that reach the threshold to the front of its slice (no block barrier, no atomics), then runs
+            // stage C over them.
+            const int nq = s_q;
+            const int per = (nq + NW - 1) / NW, lo = wid * per, hi = min(lo + per, nq);
+            int wpos = lo;
+            for (int base = lo; base < hi; base += 32) {
+                const int qi = base + lane;
+                int e = 0;
+                bool ok = false;
+                if (qi < hi) {
+                    e = queue[qi];
+                    const int s = fast_score(tile + e, P);
+                    ok = s >= th;
+                    if (ok) smap[e] = (uint8_t)s;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);      // (orders the round's reads before its writes)
+                if (ok) queue[wpos + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
+                wpos += __popc(m);
+            }
+            __syncthreads();                                             // the score map is complete
+            for (int qi = lo + lane; qi < wpos; qi += 32) nms(queue[qi]);
+        } else {
+            // dense path (rare: the survivors of stage A did not fit the queue, e.g. an image of pure noise): score every
+            // interior pixel (in pass 2: of the empty cells), then NMS over the score map
+            for (int row = 3; row < 3 + ih; ++row)
+                for (int xx = tid; xx < iw; xx += NT) {
+                    if (pass && !((emptyCells >> __umulhi((unsigned)xx, L.magicW)) & 1u)) continue;
+                    const int e = row * P + c_lo + xx;
+                    const int s = fast_score(tile + e, P);
+                    if (s >= th) smap[e] = (uint8_t)s;
+                }
+            __syncthreads();
+            for (int row = 3; row < 3 + ih; ++row)
+                for (int xx = tid; xx < iw; xx += NT) {
+                    if (pass && !((emptyCells >> __umulhi((unsigned)xx, L.magicW)) & 1u)) continue;
+                    const int e = row * P + c_lo + xx;
+                    if (smap[e]) nms(e);
+                }
         }
         __syncthreads();
-        // keypoints per cell: one warp per cell, lanes over the rows
+        // keypoints per cell and above each row of the cell: one warp per cell, lanes over the rows.  A cell whose
+        // count is final appends to the level's raw list with one global atomic.
+        const bool lastPass = pass || minTh >= iniTh;
         for (int k = wid; k < nv; k += NW) {
             if (pass && !((emptyCells >> k) & 1u)) continue;
             const int x0 = k * wCell, x1 = min(x0 + wCell, iw);
-            int cnt = 0;
-            for (int row = lane; row < ih; row += 32) cnt += mask_range_count(kmask + row * wpr, x0, x1);
+            int run = 0;
+            for (int r0 = 0; r0 < ih; r0 += 32) {
+                const int row = r0 + lane;
+                const int n = row < ih ? mask_range_count(kmask + row * wpr, x0, x1) : 0;
+                int incl = n;
 #pragma unroll
-            for (int ofs = 16; ofs > 0; ofs >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, ofs);
+                for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
+                    if (lane >= ofs) incl += t;
+                }
+                if (row < ih) s_rowpre[k][row] = (unsigned short)(run + incl - n);
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
             if (lane == 0) {
-                s_cnt[k] = cnt;
-                if (cnt == 0 && pass == 0) atomicOr(&s_empty, 1 << k);
+                if (run == 0 && !lastPass) {
+                    atomicOr(&s_empty, 1 << k);      // :787 "if(vKeysCell.empty())" -> retry at minThFAST
+                } else {
+                    int base = 0;
+                    if (run > 0) {
+                        base = atomicAdd(p.rawCount + f * g.nlevels + l, run);
+                        if (base + run > L.rawCap) { atomicOr(p.err, ERR_RAW_OVERFLOW); base = -1; }
+                    }
+                    s_off[k] = base;
+                    info[k] = base >= 0 ? make_uint2((unsigned)base, (unsigned)run) : make_uint2(0u, 0u);
+                }
             }
         }
         __syncthreads();
         emptyCells = (unsigned)s_empty;
-        if (pass || emptyCells == 0u || minTh >= iniTh) break;      // :787 "if(vKeysCell.empty())" -> retry at minThFAST
-        if (tid == 0) s_q = 0;
+        if (lastPass || emptyCells == 0u) break;
+        if (tid == 0) { s_q = 0; s_ovf = 0; }
         __syncthreads();
     }
+    RawRec* outL = p.raw + (long long)f * g.rawPerFrame + L.rawOff;
 
-    if (tid == 0) {
-        int total = 0;
-        for (int k = 0; k < nv; ++k) { s_off[k] = total; total += s_cnt[k]; }
-        int base = 0;
-        if (total > 0) {
-            base = atomicAdd(p.rawCount + f * g.nlevels + l, total);
-            if (base + total > L.rawCap) { atomicOr(p.err, ERR_RAW_OVERFLOW); base = -1; }
-        }
-        s_base = base;
-        for (int k = 0; k < sg.nc; ++k)
-            info[k] = (k < nv && base >= 0) ? make_uint2((unsigned)(base + s_off[k]), (unsigned)s_cnt[k]) : make_uint2(0u, 0u);
-    }
-    __syncthreads();
-    if (s_base < 0) return;
-    RawRec* outL = p.raw + (long long)f * g.rawPerFrame + L.rawOff + s_base;
-
-    // ordered emit: row-major inside each cell, the order cv::FAST reports
-    for (int k = wid; k < nv; k += NW) {
-        if (s_cnt[k] == 0) continue;
-        const int x0 = k * wCell, x1 = min(x0 + wCell, iw);
-        RawRec* out = outL + s_off[k];
-        const int xBase = 3 + sg.cj0 * wCell, yBase = 3 + sg.ci * L.hCell;      // :811-812, relative to (minBorderX, minBorderY)
-        int run = 0;
-        for (int r0 = 0; r0 < ih; r0 += 32) {
-            const int row = r0 + lane;
-            const unsigned* rowp = kmask + row * wpr;
-            const int n = row < ih ? mask_range_count(rowp, x0, x1) : 0;
-            int incl = n;
-#pragma unroll
-            for (int ofs = 1; ofs < 32; ofs <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
-                if (lane >= ofs) incl += t;
-            }
-            int pos = run + incl - n;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-            if (n) {
-                const int wlo = x0 >> 5, whi = (x1 - 1) >> 5;
-                for (int w = wlo; w <= whi; ++w) {
-                    unsigned bits = rowp[w];
-                    if (w == wlo) bits &= 0xffffffffu << (x0 & 31);
-                    if (w == whi) bits &= 0xffffffffu >> (31 - ((x1 - 1) & 31));
-                    while (bits) {
-                        const int xx = w * 32 + __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        RawRec r;
-                        r.x = (unsigned short)(xx + xBase);
-                        r.y = (unsigned short)(row + yBase);
-                        r.score = smap[(row + 3) * pitch + c_lo + xx]; r.pad = 0;
-                        out[pos++] = r;
-                    }
-                }
-            }
-        }
+    // ordered emit: a keypoint's slot is its rank in the row-major order of its cell (the order cv::FAST reports) =
+    // keypoints of the cell above its row + keypoints of the cell to its left in the row
+    const int nw = s_nw;
+    const int xBase = 3 + sg.cj0 * wCell, yBase = 3 + sg.ci * L.hCell;      // :811-812, relative to (minBorderX, minBorderY)
+    for (int t = tid; t < nw; t += NT) {
+        const int e = winners[t];
+        const int row = (e >> 8) - 3, xx = (e & (P - 1)) - c_lo;
+        const int k = (int)__umulhi((unsigned)xx, L.magicW), x0 = k * wCell;
+        int rank = s_rowpre[k][row];
+        if (xx > x0) rank += mask_range_count(kmask + row * wpr, x0, xx);
+        RawRec r;
+        r.x = (unsigned short)(xx + xBase);
+        r.y = (unsigned short)(row + yBase);
+        r.score = smap[e]; r.pad = 0;
+        const int base = s_off[k];
+        if (base >= 0) outL[base + rank] = r;
     }
 }
 
@@ -1114,18 +1138,20 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
     cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
     FastSmem sm{};
-    int tileBytes = 0, qcap = 0, mwords = 0;
+    int tileBytes = 0, mwords = 0, wcap = 0;
+    const int qcap = kFastQueueCap;
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& L = g.lv[l];
         tileBytes = max(tileBytes, L.boxW * L.boxH + 64);
-        qcap = max(qcap, L.segCols * L.wCell * L.hCell);                      // every interior pixel may survive stage A
         mwords = max(mwords, ((L.segCols * L.wCell + 31) / 32) * L.hCell);
+        wcap = max(wcap, L.segCols * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2));      // strict 3x3 maxima inside a cell: one per 2x2 block
     }
     tileBytes = (tileBytes + 127) / 128 * 128;
     sm.offMap = tileBytes;
-    sm.offQueue = 2 * tileBytes;
-    sm.offMask = sm.offQueue + (qcap * 2 + 15) / 16 * 16;
-    sm.total = sm.offMask + mwords * 4 + 16;
+    sm.offMask = 2 * tileBytes;                                               // cleared together with the score map
+    sm.offQueue = sm.offMask + (mwords * 4 + 15) / 16 * 16;
+    sm.offWin = sm.offQueue + (qcap * 2 + 15) / 16 * 16;
+    sm.total = sm.offWin + (wcap * 2 + 15) / 16 * 16 + 16;
     static int attrSet = 0;
     if (sm.total > attrSet) {
         cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
