@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=512, help="stereo pairs per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -311,7 +311,7 @@ def main():
         "config": {"workload": f"KITTI-shaped stereo {W}x{H} pair, {NLEVELS} levels x1.2, {NFEAT} keypoints/image, "
                                "left-right windowed Hamming matching (BASELINE.json configs[1])",
                    "pairs_per_step_per_gpu": P, "frames_per_step_per_gpu": F, "parallelism": f"sequences sharded x{world}, no collective",
-                   "pipeline": "fused detect+match; resident: one launch set per step; host buffers: chunks of 64 frames, copies and two compute streams overlapped",
+                   "pipeline": "fused detect+match; resident: one launch set per step; host buffers: chunks of <= 64 frames (short first and last chunks), H2D / three compute streams / D2H overlapped, one host synchronisation per call",
                    "l2": f"two input sets alternate; per-step working set {(F * (pix * 2 + H * PITCH)) / 1e6:.0f} MB > 126 MB L2"},
         "stage_ms_per_step": {"pyramid": float(stage[0]) / max(calls, 1), "fast": float(stage[1]) / max(calls, 1),
                               "quadtree_order": float(stage[2]) / max(calls, 1),

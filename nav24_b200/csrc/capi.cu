@@ -4,6 +4,7 @@
 //   ctor / setNumFeatures   core/operators/objDetection/OP_FtDtOrbSlam.cpp:441-500, :962-976
 //   level sizes             :940        cell grid  :735-768      quadtree roots  :505-527
 // There is no CPU compute path: every entry point needs a CUDA device.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -48,16 +49,23 @@ struct nav24_orb {
     std::vector<float> scale, invScale;
     std::vector<int> quota;
     std::string err;
-    cudaStream_t stream = nullptr, stream2 = nullptr, copyStream = nullptr, outStream = nullptr;
+    static constexpr int kMaxStreams = 4;
+    cudaStream_t stream = nullptr, copyStream = nullptr, outStream = nullptr;
+    cudaStream_t xstream[kMaxStreams] = {nullptr, nullptr, nullptr, nullptr};      // [0] = stream; [1..] extra compute streams
+    cudaEvent_t evJoinX[kMaxStreams] = {nullptr, nullptr, nullptr, nullptr};
+    int nStreams = 3;                          // compute streams the chunks rotate over (NAV24_STREAMS)
+    int taper = 1;                             // host pipeline: short first and last chunks (NAV24_TAPER=0: uniform)
     std::vector<cudaEvent_t> evIn, evDone;      // per chunk of the host-buffer pipeline (no timing)
     cudaEvent_t evJoin = nullptr, evPrevEnd = nullptr, evPairs = nullptr;
+    bool trace = false;                      // NAV24_TRACE=1: per-chunk timeline of the host pipeline on stderr
+    cudaEvent_t evT0 = nullptr, evT1 = nullptr;
     bool prevEndValid = false;
     unsigned long long prevSig = 0;           // (B, chunk, pairs) signature of the previous chunked call
     int callParity = 0;                       // ping-pong index of the pair tables
     int lastP = 0, lastMatchCap = 0;          // pairs / row capacity of the match results left on the device
     int chunkFrames = 64;                      // frames per pipeline chunk of the host-buffer entry points
     int residentChunk = 0;                     // 0 = whole batch in one chunk for device-resident frames
-    int* hN = nullptr; int* hMono = nullptr; int* hErr = nullptr; int hCap = 0;   // pinned result scratch
+    int* hN = nullptr; int* hMono = nullptr; int* hNm = nullptr; int* hErr = nullptr; int hCap = 0;   // pinned result scratch
     static constexpr int kEvRing = 64;
     cudaEvent_t evRing[kEvRing][5]{};
     long long evCalls = 0;      // pipeline runs since the last stage-sum reset
@@ -85,9 +93,10 @@ struct nav24_orb {
     cudaError_t ensure_events(int n) {
         while ((int)evIn.size() < n) {
             cudaEvent_t a, b;
-            cudaError_t e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+            const unsigned fl = trace ? cudaEventDefault : cudaEventDisableTiming;
+            cudaError_t e = cudaEventCreateWithFlags(&a, fl);
             if (e != cudaSuccess) return e;
-            e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+            e = cudaEventCreateWithFlags(&b, fl);
             if (e != cudaSuccess) return e;
             evIn.push_back(a); evDone.push_back(b);
         }
@@ -98,9 +107,9 @@ struct nav24_orb {
         if (hN) cudaFreeHost(hN);
         hN = nullptr; hCap = 0;
         const int want = B + B / 2 + 16;
-        cudaError_t e = cudaHostAlloc((void**)&hN, sizeof(int) * (2 * (size_t)want + 4), cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc((void**)&hN, sizeof(int) * (3 * (size_t)want + 4), cudaHostAllocDefault);
         if (e != cudaSuccess) return e;
-        hMono = hN + want; hErr = hMono + want; hCap = want;
+        hMono = hN + want; hNm = hMono + want; hErr = hNm + want; hCap = want;
         return cudaSuccess;
     }
 
@@ -562,10 +571,19 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
     for (int i = 1; i < nl; ++i) ctx->scale[i] = ctx->scale[i - 1] * ctx->scaleFactorD;
     for (int i = 0; i < nl; ++i) ctx->invScale[i] = 1.0f / ctx->scale[i];
     ctx->compute_quota(params->n_features);
+    if (const char* e = getenv("NAV24_TRACE")) ctx->trace = atoi(e) != 0;
+    if (ctx->trace) { cudaEventCreate(&ctx->evT0); cudaEventCreate(&ctx->evT1); }
     if (const char* e = getenv("NAV24_CHUNK_FRAMES")) { const int v = atoi(e); if (v > 0) ctx->chunkFrames = v; }
+    if (const char* e = getenv("NAV24_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= nav24_orb::kMaxStreams) ctx->nStreams = v; }
+    if (const char* e = getenv("NAV24_TAPER")) ctx->taper = atoi(e);
     if (const char* e = getenv("NAV24_RESIDENT_CHUNK")) { const int v = atoi(e); if (v > 0) ctx->residentChunk = v; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->xstream[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->xstream[2], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->xstream[3], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evJoinX[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evJoinX[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evJoinX[3], cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->outStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
@@ -574,6 +592,7 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
         delete ctx;
         return NAV24_E_CUDA;
     }
+    ctx->xstream[0] = ctx->stream;
     for (auto& r : ctx->evRing) for (auto& e : r) cudaEventCreate(&e);
     for (auto& e : ctx->evT) cudaEventCreate(&e);
     *out = ctx;
@@ -601,7 +620,10 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     if (ctx->evPairs) cudaEventDestroy(ctx->evPairs);
     if (ctx->hN) cudaFreeHost(ctx->hN);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int i = 1; i < nav24_orb::kMaxStreams; ++i) {
+        if (ctx->xstream[i]) cudaStreamDestroy(ctx->xstream[i]);
+        if (ctx->evJoinX[i]) cudaEventDestroy(ctx->evJoinX[i]);
+    }
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->outStream) cudaStreamDestroy(ctx->outStream);
     delete ctx;
@@ -698,13 +720,33 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
     }
     int rc = encode_maps(ctx, B);
     if (rc != NAV24_OK) return rc;
+    // chunk schedule.  Host frames: the copy engine and the kernels run at about the same rate, so the call ends
+    // (first copy) + (all kernels) + (last copy back): a short first chunk starts the kernels early, short last
+    // chunks keep the tail after the last copy small, and the chunks in between are large enough to fill the GPU.
     const int C = std::max(1, std::min(chunkOverride > 0 ? chunkOverride : ctx->chunkFrames, B));
-    const int nChunks = (B + C - 1) / C;
+    std::vector<int> chunkStart;
+    if (fromHost && ctx->taper && chunkOverride <= 0 && C >= 8 && B >= 3 * C) {
+        const int head[2] = {C / 4, C / 2}, tail[2] = {C / 2, C / 4};
+        const int rem = B - head[0] - head[1] - tail[0] - tail[1], nMid = (rem + C - 1) / C;
+        int f = 0;
+        for (int v : head) { chunkStart.push_back(f); f += v; }
+        for (int i = 0; i < nMid; ++i) { chunkStart.push_back(f); f += rem / nMid + (i < rem % nMid ? 1 : 0); }
+        for (int v : tail) { chunkStart.push_back(f); f += v; }
+    } else {
+        for (int f = 0; f < B; f += C) chunkStart.push_back(f);
+    }
+    const int nChunks = (int)chunkStart.size();
+    chunkStart.push_back(B);
+    std::vector<int> chunkOfFrame(B);
+    for (int k = 0; k < nChunks; ++k)
+        for (int f = chunkStart[k]; f < chunkStart[k + 1]; ++f) chunkOfFrame[f] = k;
+    const int nS = std::max(1, std::min(ctx->nStreams, nChunks));
     CK(ctx->ensure_events(nChunks));
-    CK(ctx->ensure_host(B));
+    CK(ctx->ensure_host(std::max(B, mp ? mp->P : 0)));
     unsigned long long sig = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
     mix((unsigned long long)B); mix((unsigned long long)C); mix((unsigned long long)w); mix((unsigned long long)h);
+    mix((unsigned long long)nChunks); mix((unsigned long long)nS);
 
     // pairs grouped by chunk (pairs spanning chunks go last)
     MatchArgs ma{};
@@ -720,7 +762,7 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
         std::vector<int> chunkOf(P), order(P);
         for (int q = 0; q < 2 * P; ++q) mix((unsigned long long)(unsigned)mp->pairs[q]);
         for (int q = 0; q < P; ++q) {
-            const int ca = mp->pairs[2 * q] / C, cb = mp->pairs[2 * q + 1] / C;
+            const int ca = chunkOfFrame[mp->pairs[2 * q]], cb = chunkOfFrame[mp->pairs[2 * q + 1]];
             chunkOf[q] = ca == cb ? ca : nChunks;
             firstOfChunk[chunkOf[q] + 1]++;
         }
@@ -740,18 +782,22 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
     if (fromHost) CK(cudaStreamSynchronize(ctx->stream));      // an earlier asynchronous call may still use the workspace
     // The device error word is sticky: it is read and cleared by the synchronising calls, never by an asynchronous one
     // (a memset here could race with kernels of the previous asynchronous call).
+    const auto hostT0 = std::chrono::steady_clock::now();
+    if (ctx->trace) CK(cudaEventRecord(ctx->evT0, ctx->copyStream));
     CK(cudaEventRecord(ctx->evPairs, ctx->copyStream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->evPairs, 0));
-    CK(cudaStreamWaitEvent(ctx->stream2, ctx->evPairs, 0));
-    // stream2 may run ahead into this call only if every slab is touched by the same stream as in the previous call
-    // (same batch, chunking and pairs, and no pair spanning two chunks); otherwise it waits for the previous call's end
-    if (ctx->prevEndValid && (sig != ctx->prevSig || nLate > 0)) CK(cudaStreamWaitEvent(ctx->stream2, ctx->evPrevEnd, 0));
+    // the extra streams may run ahead into this call only if every slab is touched by the same stream as in the previous
+    // call (same batch, chunking and pairs, and no pair spanning two chunks); otherwise they wait for the previous call's end
+    for (int i = 1; i < nS; ++i) {
+        CK(cudaStreamWaitEvent(ctx->xstream[i], ctx->evPairs, 0));
+        if (ctx->prevEndValid && (sig != ctx->prevSig || nLate > 0)) CK(cudaStreamWaitEvent(ctx->xstream[i], ctx->evPrevEnd, 0));
+    }
     ctx->prevSig = sig;
     const int ccap = std::min(cap, g.outCap);
     const bool stages = nChunks == 1;      // per-stage events only make sense un-overlapped
     for (int k = 0; k < nChunks; ++k) {
-        const int f0 = k * C, c = std::min(C, B - f0);
-        cudaStream_t cs = (k & 1) ? ctx->stream2 : ctx->stream;
+        const int f0 = chunkStart[k], c = chunkStart[k + 1] - f0;
+        cudaStream_t cs = ctx->xstream[k % nS];
         if (fromHost) {
             if (tight) {
                 CK(cudaMemcpyAsync((uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, hostGray + f0 * tightFrame, c * tightFrame,
@@ -788,9 +834,9 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
                                      (size_t)g.outCap * 32, (size_t)ccap * 32, c, cudaMemcpyDeviceToHost, ctx->outStream));
         }
     }
-    if (nChunks > 1) {      // later work on ctx->stream must see the chunks that ran on stream2
-        CK(cudaEventRecord(ctx->evJoin, ctx->stream2));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+    for (int i = 1; i < nS; ++i) {      // later work on ctx->stream must see the chunks that ran on the other streams
+        CK(cudaEventRecord(ctx->evJoinX[i], ctx->xstream[i]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoinX[i], 0));
     }
     if (nLate > 0) {
         ma.pairBase = firstOfChunk[nChunks];
@@ -807,15 +853,28 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
     // host mode: bring the small tails back and synchronise once
     CK(cudaStreamWaitEvent(ctx->outStream, ctx->evPrevEnd, 0));
     CK(cudaMemcpyAsync(ctx->hErr, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->outStream));
-    std::vector<int> nm(std::max(P, 1));
+    int* nm = ctx->hNm;      // pinned: a pageable destination would make the copy below block the host
     if (P > 0) {
         if (matches12)
             CK(cudaMemcpy2DAsync(matches12, (size_t)mcap * 4, ma.matches12, (size_t)g.outCap * 4,
                                  (size_t)std::min(mcap, g.outCap) * 4, P, cudaMemcpyDeviceToHost, ctx->outStream));
-        CK(cudaMemcpyAsync(nm.data(), ma.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, ctx->outStream));
+        CK(cudaMemcpyAsync(nm, ma.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, ctx->outStream));
     }
     CK(cudaMemsetAsync(ctx->p.err, 0, sizeof(int), ctx->outStream));
+    const auto hostT1 = std::chrono::steady_clock::now();
+    if (ctx->trace) CK(cudaEventRecord(ctx->evT1, ctx->outStream));
     CK(cudaStreamSynchronize(ctx->outStream));
+    if (ctx->trace) {
+        float t = 0;
+        fprintf(stderr, "[nav24 trace] enqueue %.3f ms on the host;", std::chrono::duration<double, std::milli>(hostT1 - hostT0).count());
+        for (int k = 0; k < nChunks; ++k) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ctx->evT0, ctx->evIn[k]); cudaEventElapsedTime(&b, ctx->evT0, ctx->evDone[k]);
+            fprintf(stderr, " chunk %d: in %.3f done %.3f;", k, a, b);
+        }
+        cudaEventElapsedTime(&t, ctx->evT0, ctx->evT1);
+        fprintf(stderr, " end %.3f ms\n", t);
+    }
     rc = decode_device_error(ctx, *ctx->hErr);
     if (rc != NAV24_OK) { ctx->lastValid = false; return rc; }
     bool small = false;

@@ -1,0 +1,7 @@
+#!/bin/bash
+# e2e throughput vs host-pipeline chunk size
+for c in 16 32 64 128; do
+  NAV24_CHUNK_FRAMES=$c python bench.py --no-cpu-baseline --steps 10 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('chunk $c', 'resident %.0f e2e %.0f' % (d['value'], d['e2e']['value']))"
+done
