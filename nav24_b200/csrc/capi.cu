@@ -78,7 +78,10 @@ struct nav24_orb {
     FrameGeom g{};
     DevPtrs p{};
     std::vector<ResizeTab> tabs;
-    TmaMaps maps{};
+    TmaMaps maps{};           // FAST segment tiles over the un-blurred levels
+    TmaMaps mapsOri{};        // 48 x 31 orientation patches over the un-blurred levels (describe_kernel)
+    TmaMaps mapsBlur{};       // 64 x 37 descriptor patches over the blurred levels (describe_kernel)
+    const void* mapsBlurPtr = nullptr;
     int mapsB = 0;            // frame count the level>=1 maps were encoded for
     const void* mapsPyr = nullptr;
     DevBuf bL0Tight, bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
@@ -422,16 +425,29 @@ DevPtrs chunk_ptrs(const nav24_orb* ctx, int f0) {
 // (re)encode the tensor maps: levels >= 1 live in the workspace, level 0 is the caller's (or the staging) buffer
 int encode_maps(nav24_orb* ctx, int B) {
     const FrameGeom& g = ctx->g;
-    if (ctx->mapsB != ctx->wsB || ctx->mapsPyr != ctx->p.pyr) {
-        for (int l = 1; l < g.nlevels; ++l) {
-            int rc = encode_level_map(ctx, &ctx->maps.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
+    if (ctx->mapsB != ctx->wsB || ctx->mapsPyr != ctx->p.pyr || ctx->mapsBlurPtr != ctx->p.blur) {
+        for (int l = 0; l < g.nlevels; ++l) {
+            int rc = NAV24_OK;
+            if (l > 0) {
+                rc = encode_level_map(ctx, &ctx->maps.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
                                       g.lv[l].pitch, g.pyrFrameBytes, g.lv[l].boxW, g.lv[l].boxH);
+                if (rc != NAV24_OK) return rc;
+                rc = encode_level_map(ctx, &ctx->mapsOri.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
+                                      g.lv[l].pitch, g.pyrFrameBytes, kOriBoxW, kOriBoxH);
+                if (rc != NAV24_OK) return rc;
+            }
+            rc = encode_level_map(ctx, &ctx->mapsBlur.m[l], ctx->p.blur + g.lv[l].boff, g.lv[l].w, g.lv[l].h, ctx->wsB,
+                                  g.lv[l].pitch, g.blurFrameBytes, kDescBoxW, kDescBoxH);
             if (rc != NAV24_OK) return rc;
         }
-        ctx->mapsB = ctx->wsB; ctx->mapsPyr = ctx->p.pyr;
+        ctx->mapsB = ctx->wsB; ctx->mapsPyr = ctx->p.pyr; ctx->mapsBlurPtr = ctx->p.blur;
     }
-    return encode_level_map(ctx, &ctx->maps.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch,
-                            B > 1 ? ctx->p.l0Frame : ctx->p.l0Pitch * g.lv[0].h, g.lv[0].boxW, g.lv[0].boxH);
+    const long long l0Frame = B > 1 ? ctx->p.l0Frame : ctx->p.l0Pitch * g.lv[0].h;
+    int rc = encode_level_map(ctx, &ctx->mapsOri.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame, kOriBoxW,
+                              kOriBoxH);
+    if (rc != NAV24_OK) return rc;
+    return encode_level_map(ctx, &ctx->maps.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame, g.lv[0].boxW,
+                            g.lv[0].boxH);
 }
 
 // enqueue the per-frame chain for frames [f0, f0+C) on stream s; no host synchronisation.  With stages = true the
@@ -450,7 +466,7 @@ int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
     if (stages) CK(cudaEventRecord(ctx->ev[2], s));
     ctx->launches += launch_quadtree(g, q, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[3], s));
-    ctx->launches += launch_describe(g, q, C, s);
+    ctx->launches += launch_describe(g, q, ctx->mapsOri, ctx->mapsBlur, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaGetLastError());
     return NAV24_OK;

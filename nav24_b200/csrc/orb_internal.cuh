@@ -19,6 +19,8 @@ constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
 #endif
 constexpr int kBlurTileRows = NAV24_BLUR_ROWS;   // rows per warp tile of blur_kernel (multiple of 7)
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
+constexpr int kOriBoxW = 48, kOriBoxH = 31;    // TMA box of the orientation patch: 31 px + <= 15 px of alignment slack, 16-B multiple
+constexpr int kDescBoxW = 64, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px + <= 15 px of alignment slack
 constexpr int kFastThreads = 256;   // threads per CTA of fast_band_kernel
 constexpr int kFastMaxSegCells = 8; // cells of one FAST segment (TMA boxes are <= 256 px wide, cells >= 35 px)
 constexpr int kFastQueueCap = 3072; // stage A survivors one CTA queues (typ. 700 of 8400 pixels); beyond: the dense path
@@ -137,7 +139,7 @@ int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, in
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, int B, cudaStream_t s);
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
-int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
+int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, int B, cudaStream_t s);
 int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s);   // test hook (stdsort_warp.cuh)
 
 // matchers (match_kernels.cu)

@@ -77,22 +77,38 @@ __global__ void __launch_bounds__(256) repack_kernel(const uint8_t* __restrict__
 // ------------------------------------------------------------------------------------------
 // K1  pyramid level l-1 -> l.  cv::resize(INTER_LINEAR) on CV_8UC1 = 11-bit fixed-point separable
 // bilinear; replaces ComputePyramid (OP_FtDtOrbSlam.cpp:936-960).
-// One thread owns 4 horizontally adjacent destination pixels of `rows` consecutive rows (8 at scale 1.2).  Per SOURCE row it
-// loads the three aligned words that cover its <= 8-byte source window, shifts the window to byte 0 (2 SHF), picks
-// each pixel's two taps with one PRMT (selectors are per-thread constants) and forms S[s]*a0 + S[s+1]*a1 with one
-// DP2A; the horizontally interpolated rows are kept in registers and reused by the next destination row (the
-// source row index advances by 1 or 2 per destination row, a warp-uniform choice).
+// One WARP owns 128 destination columns x `rows` destination rows (8 at scale 1.2); a thread owns 4 adjacent columns.
+// Phase 1, per SOURCE row of the tile (<= kResizeSrcRows, all loads issued before the first use): the three aligned
+// words that cover the thread's <= 8-byte source window are shifted to byte 0 (2 SHF), each pixel's two taps are
+// picked by one PRMT (selectors are per-thread constants) and S[s]*a0 + S[s+1]*a1 is one DP2A; the four
+// horizontally interpolated values go to the warp's shared-memory strip as one 16-byte store.
+// Phase 2, per DESTINATION row (statically unrolled; row offset and coefficient pair are warp-uniform loads issued
+// up front): two 16-byte loads from the strip (a thread only ever reads its own columns, shared memory is used for the
+// dynamic ROW index), ((b0*top + 2^17) >> 16) + ((b1*bot) >> 16) as two multiply-highs by the coefficients
+// pre-shifted left by 16, >> 2, pack, one 32-bit store.
 // ------------------------------------------------------------------------------------------
-constexpr int kResizeSrcRows = 12;     // source rows whose words a thread keeps in flight
+constexpr int kResizeSrcRows = 12;     // source rows of one warp tile
+constexpr int kResizeDstRows = 8;      // destination rows of one warp tile (upper bound)
 
 __global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__ src, unsigned sPitch, long long sFrame,
                                                      int sw, int sh, uint8_t* __restrict__ dst, int dPitch,
                                                      long long dFrame, int dw, int dh, int rows, ResizeTab t) {
-    const int x4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
-    const int y0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * rows;
+    __shared__ uint4 sH[4][kResizeSrcRows][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x4 = (blockIdx.x * 32 + lane) * 4;
+    const int y0 = (blockIdx.y * 4 + wid) * rows;
     if (y0 >= dh) return;                                  // warp-uniform
-    const bool active = x4 < dw;
+    const int nrows = min(rows, dh - y0);
+    // warp-uniform vertical constants of the tile's destination rows
+    int yo[kResizeDstRows]; unsigned yc[kResizeDstRows];
+#pragma unroll
+    for (int j = 0; j < kResizeDstRows; ++j) {
+        const int y = y0 + min(j, nrows - 1);
+        yo[j] = __ldg(t.yofs + y);
+        yc[j] = __ldg(reinterpret_cast<const unsigned*>(t.yab) + y);      // b0 | b1 << 16, both in [0, 2048]
+    }
     // per-thread horizontal constants
+    const bool active = x4 < dw;
     const int s0 = t.xofs[min(x4, dw - 1)];
     const int sa = s0 & ~3;                                // aligned start of the source window
     const unsigned shift = (unsigned)(s0 & 3) * 8u;
@@ -109,65 +125,46 @@ __global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__
         sel[k] = (unsigned)d | ((unsigned)(d + 1) << 4);
         ab[k] = *reinterpret_cast<const unsigned*>(t.xab + x);  // (a0, a1) as two u16 (both in [0, 2048])
     }
-    uint8_t* dp = dst + (long long)blockIdx.z * dFrame + x4;
-
-    auto hsum = [&](unsigned w0, unsigned w1, unsigned w2, int h[4]) {     // horizontally interpolated row, >> 4
-        const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+    const int syBase = yo[0];
+    const int nsrc = min(yo[kResizeDstRows - 1] + 2 - syBase, kResizeSrcRows);      // warp-uniform (the host sizes `rows` for it)
+    // phase 1: every load of the tile is in flight before the first use
+    unsigned W[kResizeSrcRows][3];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = (int)(__dp2a_lo(ab[k], __byte_perm(lo, hi, sel[k]), 0u) >> 4);
-    };
-    auto hrow = [&](int sy, int h[4]) {
-        const unsigned long long ro = (unsigned long long)((unsigned)min(sy, sh - 1)) * sPitch;
-        hsum(__ldg(reinterpret_cast<const unsigned*>(q0 + ro)), __ldg(reinterpret_cast<const unsigned*>(q1 + ro)),
-             __ldg(reinterpret_cast<const unsigned*>(q2 + ro)), h);
-    };
-    const int yEnd = min(y0 + rows, dh);
-    int y = y0;
-    auto emit = [&](int sy, const int top[4], const int bot[4]) {      // every destination row whose first tap is row sy
-        while (y < yEnd && t.yofs[y] == sy) {
-            const int bpair = *reinterpret_cast<const int*>(t.yab + y);
-            const int b0 = (short)(bpair & 0xffff), b1 = bpair >> 16;
-            unsigned v[4];
+    for (int i = 0; i < kResizeSrcRows; ++i) {
+        const unsigned long long ro = (unsigned long long)((unsigned)min(syBase + min(i, nsrc - 1), sh - 1)) * sPitch;
+        W[i][0] = __ldg(reinterpret_cast<const unsigned*>(q0 + ro));
+        W[i][1] = __ldg(reinterpret_cast<const unsigned*>(q1 + ro));
+        W[i][2] = __ldg(reinterpret_cast<const unsigned*>(q2 + ro));
+    }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = (unsigned)((((b0 * top[k] + 0x20000) >> 16) + ((b1 * bot[k]) >> 16)) >> 2);
-            const unsigned out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-            if (active) *reinterpret_cast<unsigned*>(dp + (long long)y * dPitch) = out;
-            ++y;
+    for (int i = 0; i < kResizeSrcRows; ++i) {
+        if (i < nsrc) {                                    // warp-uniform
+            const unsigned lo = __funnelshift_r(W[i][0], W[i][1], shift), hi = __funnelshift_r(W[i][1], W[i][2], shift);
+            uint4 h;
+            h.x = __dp2a_lo(ab[0], __byte_perm(lo, hi, sel[0]), 0u) >> 4;
+            h.y = __dp2a_lo(ab[1], __byte_perm(lo, hi, sel[1]), 0u) >> 4;
+            h.z = __dp2a_lo(ab[2], __byte_perm(lo, hi, sel[2]), 0u) >> 4;
+            h.w = __dp2a_lo(ab[3], __byte_perm(lo, hi, sel[3]), 0u) >> 4;
+            sH[wid][i][lane] = h;
         }
-    };
-    // walk the SOURCE rows once: A/B alternate as (row sy, row sy+1); a destination row is emitted when both are there
-    int ha[4], hb[4];
-    const int syBase = t.yofs[y0];
-    const int nsrc = t.yofs[yEnd - 1] + 2 - syBase;        // warp-uniform
-    if (nsrc <= kResizeSrcRows) {
-        // the usual case: all loads of the tile are issued before the first use (the kernel is latency-bound otherwise)
-        unsigned W[kResizeSrcRows][3];
+    }
+    __syncwarp();
+    // phase 2
+    uint8_t* dp = dst + (long long)blockIdx.z * dFrame + (long long)y0 * dPitch + x4;
 #pragma unroll
-        for (int i = 0; i < kResizeSrcRows; ++i) {
-            const unsigned long long ro = (unsigned long long)((unsigned)min(syBase + min(i, nsrc - 1), sh - 1)) * sPitch;
-            W[i][0] = __ldg(reinterpret_cast<const unsigned*>(q0 + ro));
-            W[i][1] = __ldg(reinterpret_cast<const unsigned*>(q1 + ro));
-            W[i][2] = __ldg(reinterpret_cast<const unsigned*>(q2 + ro));
-        }
-        hsum(W[0][0], W[0][1], W[0][2], ha);
-#pragma unroll
-        for (int i = 1; i < kResizeSrcRows; ++i) {
-            if (y < yEnd) {                                // warp-uniform
-                if (i & 1) { hsum(W[i][0], W[i][1], W[i][2], hb); emit(syBase + i - 1, ha, hb); }
-                else       { hsum(W[i][0], W[i][1], W[i][2], ha); emit(syBase + i - 1, hb, ha); }
-            }
-        }
-    } else {
-        int sy = syBase;
-        hrow(sy, ha);
-        while (y < yEnd) {
-            hrow(sy + 1, hb);
-            emit(sy, ha, hb);
-            ++sy;
-            if (y >= yEnd) break;
-            hrow(sy + 1, ha);
-            emit(sy, hb, ha);
-            ++sy;
+    for (int j = 0; j < kResizeDstRows; ++j) {
+        if (j < nrows) {                                   // warp-uniform
+            const int i0 = yo[j] - syBase;
+            const uint4 top = sH[wid][i0][lane], bot = sH[wid][i0 + 1][lane];
+            const unsigned c0 = yc[j] << 16, c1 = yc[j] & 0xffff0000u;
+            // ((b0*top + 0x20000) >> 16) + ((b1*bot) >> 16)  ==  umulhi(top, b0 << 16) + 2 + umulhi(bot, b1 << 16)
+            const unsigned v0 = (__umulhi(top.x, c0) + 2u + __umulhi(bot.x, c1)) >> 2;
+            const unsigned v1 = (__umulhi(top.y, c0) + 2u + __umulhi(bot.y, c1)) >> 2;
+            const unsigned v2 = (__umulhi(top.z, c0) + 2u + __umulhi(bot.z, c1)) >> 2;
+            const unsigned v3 = (__umulhi(top.w, c0) + 2u + __umulhi(bot.w, c1)) >> 2;
+            const unsigned out = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+            if (active) *reinterpret_cast<unsigned*>(dp) = out;
+            dp += dPitch;
         }
     }
 }
@@ -969,118 +966,99 @@ constexpr PatternT make_pattern_t() {
 }
 __device__ const PatternT kPatternT = make_pattern_t();
 
-#ifndef NAV24_DESC_WARPS
-#define NAV24_DESC_WARPS 1
-#endif
-#ifndef NAV24_DESC_BATCH
-#define NAV24_DESC_BATCH 0
-#endif
-// keypoints (warps) per CTA of describe_kernel.  Measured on B200 (256 KITTI frames): 16 warps 0.80 ms, 8: 0.76, 4: 0.60,
-// 2: 0.53, 1: 0.48 — a CTA holds its registers and shared memory until its slowest warp's gathers return.
-constexpr int kDescWarps = NAV24_DESC_WARPS;
-
 // Orientation weights for the DP4A moments, [align 4][row 31][word 9][2]: for the aligned words that cover the 31-px
 // row segment of a keypoint whose left end sits `align` bytes into its first word, (x) the four signed u offsets of the
 // bytes inside the disc (0 outside), (y) their 0/1 mask.  m10 = sum dp4a(word, x), m01 = sum v * dp4a(word, y).
 // Built once per context on the host (capi.cu: build_orientation_table) from umax[] (OP_FtDtOrbSlam.cpp:484-499).
-
-__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
-    __shared__ unsigned s_patch[kDescWarps][372];
-    __shared__ int s_mom[kDescWarps][2];
-    __shared__ float s_rot[kDescWarps][3];      // angle, cos, sin
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int slot = blockIdx.x * kDescWarps + wid;
+//
+// One warp per CTA (measured on B200, 256 KITTI frames: 16 warps per CTA 0.80 ms, 4: 0.60, 1: 0.48 — a CTA holds its
+// resources until its slowest warp's gathers return).  Both patches of the keypoint — 31 rows of the un-blurred level
+// for the moments, 37 rows of the blurred level for the 512 samples — arrive in shared memory as two TMA boxes
+// (x start rounded down to 16 bytes, hence the 48- and 64-byte box widths): no per-thread address arithmetic, no
+// register staging, and the gathers index a power-of-two row pitch.
+__global__ void __launch_bounds__(32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+                                                      const __grid_constant__ TmaMaps mapsOri,
+                                                      const __grid_constant__ TmaMaps mapsBlur) {
+    __shared__ __align__(128) uint8_t s_blur[kDescBoxW * kDescBoxH];
+    __shared__ __align__(128) uint8_t s_ori[kOriBoxW * kOriBoxH];
+    __shared__ __align__(8) unsigned long long bar;
+    const int lane = threadIdx.x;
+    const int slot = blockIdx.x;
     const int f = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && slot >= g.lv[l + 1].kpOff) ++l;
     const LevelGeom& L = g.lv[l];
     const int i = slot - L.kpOff;
-    const bool live = slot < g.kpPerFrame && i < p.levelCount[f * g.nlevels + l];      // warp-uniform
+    if (!(slot < g.kpPerFrame && i < p.levelCount[f * g.nlevels + l])) return;      // warp-uniform
     LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + slot;
-    int cx = 0, cy = 0, align = 0;
-    const int bp = L.pitch;
-    unsigned pw[12];
-    if (live) {
-        cx = kp->x; cy = kp->y;
-        // issue the loads of the blurred 37 x 40 byte patch first (they do not depend on the angle): 12 words per lane
-        const int ax = (cx - 18) & ~3;
-        align = (cx - 18) - ax;
-        const uint8_t* bl = p.blur + (long long)f * g.blurFrameBytes + L.boff + (long long)(cy - 18) * bp + ax;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const int idx = k * 32 + lane;                  // word idx of the 37 x 10 patch
-            const int r = (idx * 205) >> 11, c = idx - r * 10;      // idx / 10 for idx < 1024
-            pw[k] = idx < 370 ? __ldg(reinterpret_cast<const unsigned*>(bl + r * bp) + c) : 0u;
-        }
-        // orientation on the un-blurred level: integer moments of the 31-px disc by DP4A over the aligned words of the
-        // 31 x 31 patch (279 words, 9 per lane) with the weight table; every load is in flight before the first use
-        const int pitch = (int)level_pitch(g, p, l);
-        const int ox = (cx - 15) & ~3, oal = (cx - 15) - ox;
-        const uint8_t* img = level_ptr(g, p, f, l) + (long long)(cy - 15) * pitch + ox;
-        const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + oal * 279;
-        unsigned ow[9];
-        uint2 wt[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int idx = min(k * 32 + lane, 278);
-            const int r = (idx * 57) >> 9, c = idx - r * 9;         // idx / 9 for idx < 288
-            ow[k] = __ldg(reinterpret_cast<const unsigned*>(img + r * pitch) + c);
-            wt[k] = __ldg(tab + idx);
-        }
-        int m10 = 0, m01 = 0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int idx = k * 32 + lane;
-            if (idx < 279) {
-                const int r = (idx * 57) >> 9;
-                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(ow[k]), "r"(wt[k].x));      // u8 pixels x s8 offsets
-                m01 += (r - 15) * (int)__dp4a(ow[k], wt[k].y, 0u);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        }
-#if NAV24_DESC_BATCH
-        if (lane == 0) { s_mom[wid][0] = m01; s_mom[wid][1] = m10; }
+    const int cx = kp->x, cy = kp->y;
+    const int xo = (cx - 15) & ~15, xb = (cx - 18) & ~15;
+    const unsigned barAddr = smem_u32(&bar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr),
+                     "r"((unsigned)(kDescBoxW * kDescBoxH + kOriBoxW * kOriBoxH))
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                smem_u32(s_ori)),
+            "l"(&mapsOri.m[l]), "r"(xo), "r"(cy - 15), "r"(f + p.frameBase), "r"(barAddr)
+            : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                smem_u32(s_blur)),
+            "l"(&mapsBlur.m[l]), "r"(xb), "r"(cy - 18), "r"(f + p.frameBase), "r"(barAddr)
+            : "memory");
     }
-    __syncthreads();
-    // the scalar float work (fastAtan2, sin/cos) of the CTA's keypoints runs once, one keypoint per lane of warp 0,
-    // instead of 32-fold redundantly in every warp
-    if (wid == 0 && lane < kDescWarps) {
-        const float angle = fast_atan2_deg((float)s_mom[lane][0], (float)s_mom[lane][1]);
-        const float factorPI = (float)(3.14159265358979323846 / 180.f);
-        float sn, cs;
-        sincosf(__fmul_rn(angle, factorPI), &sn, &cs);
-        s_rot[lane][0] = angle; s_rot[lane][1] = cs; s_rot[lane][2] = sn;
+    // while the patches are in flight: this lane's orientation weights and rBRIEF pattern entries
+    const int off = (cx - 15) - xo;                                  // 0..15
+    const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279;
+    uint2 wt[9];
+    int widx[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int idx = min(k * 32 + lane, 278);
+        const int r = (idx * 57) >> 9, c = idx - r * 9;             // idx / 9 for idx < 288
+        wt[k] = __ldg(tab + idx);
+        widx[k] = r * (kOriBoxW / 4) + (off >> 2) + c;
     }
-    __syncthreads();
-    if (!live) return;
-    const float angle = s_rot[wid][0], a = s_rot[wid][1], b = s_rot[wid][2];
-#else
-        s_mom[wid][0] = m01; s_mom[wid][1] = m10;      // (same value from every lane)
+    __syncwarp();
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(barAddr), "r"(0u)
+                : "memory");
+        }
     }
-    if (!live) return;
-    // (batching this scalar float work over the CTA's warps through two block barriers was measured slower: the
-    // barriers serialise the warps' memory latencies)
-    const float angle = fast_atan2_deg((float)s_mom[wid][0], (float)s_mom[wid][1]);
+    // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane)
+    const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori);
+    int m10 = 0, m01 = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int idx = k * 32 + lane;
+        if (idx < 279) {
+            const int r = (idx * 57) >> 9;
+            const unsigned w = ow[widx[k]];
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[k].x));      // u8 pixels x s8 offsets
+            m01 += (r - 15) * (int)__dp4a(w, wt[k].y, 0u);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float b, a;
     sincosf(__fmul_rn(angle, factorPI), &b, &a);
-    (void)s_rot;
-#endif
 
-    // descriptor on the blurred level.  The 512 sample points lie within +-18 px of the keypoint (pattern radius
-    // 18.38).  The warp stages that 37-row patch in shared memory with row-coalesced word loads (rows of 10 words
-    // starting at the aligned column ax <= cx-18) and gathers the samples from there: scattered byte gathers
-    // straight from global memory cost one L1 wavefront per touched line (~25 per load) and made this kernel L1-bound.
-    unsigned* patch = s_patch[wid];
-#pragma unroll
-    for (int k = 0; k < 12; ++k)
-        if (k * 32 + lane < 370) patch[k * 32 + lane] = pw[k];
-    __syncwarp();
-    const uint8_t* pc = reinterpret_cast<const uint8_t*>(patch) + 18 * 40 + 18 + align;      // the keypoint
+    // computeOrbDescriptor: the 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38)
+    const uint8_t* pc = s_blur + 18 * kDescBoxW + 18 + ((cx - 18) - xb);      // the keypoint
     const float4* pat = reinterpret_cast<const float4*>(kPatternT.v) + lane;
     unsigned val = 0;
 #pragma unroll
@@ -1090,7 +1068,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q4.x, a), __fmul_rn(q4.y, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q4.z, b), __fmul_rn(q4.w, a)));
         const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q4.z, a), __fmul_rn(q4.w, b)));
-        const int t0 = pc[r0 * 40 + q0], t1 = pc[r1 * 40 + q1];
+        const int t0 = pc[r0 * kDescBoxW + q0], t1 = pc[r1 * kDescBoxW + q1];
         val |= (unsigned)(t0 < t1) << j;
     }
     const int dst = kp->dst;
@@ -1205,15 +1183,16 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     return 2;
 }
 
-int launch_describe(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
+int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, int B,
+                    cudaStream_t s) {
     int n = 0;
     {
         dim3 grid((g.blurTiles + 3) / 4, B);
         blur_kernel<<<grid, 128, 0, s>>>(g, p);
         ++n;
     }
-    dim3 grid((g.kpPerFrame + kDescWarps - 1) / kDescWarps, B);
-    describe_kernel<<<grid, kDescWarps * 32, 0, s>>>(g, p);
+    dim3 grid(g.kpPerFrame, B);
+    describe_kernel<<<grid, 32, 0, s>>>(g, p, mapsOri, mapsBlur);
     return n + 1;
 }
 
