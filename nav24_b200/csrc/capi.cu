@@ -79,6 +79,7 @@ struct nav24_orb {
     DevPtrs p{};
     std::vector<ResizeTab> tabs;
     TmaMaps maps{};           // FAST segment tiles over the un-blurred levels
+    TmaMaps mapsRs{};         // m[l]: resize source tiles over level l-1 (resize_kernel producing level l)
     TmaMaps mapsOri{};        // 48 x 31 orientation patches over the un-blurred levels (describe_kernel)
     TmaMaps mapsBlur{};       // 64 x 37 descriptor patches over the blurred levels (describe_kernel)
     const void* mapsBlurPtr = nullptr;
@@ -330,7 +331,31 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
             CK(cudaStreamSynchronize(ctx->stream));
         }
         ctx->tabs.assign(nl, ResizeTab{});
-        for (int l = 1; l < nl; ++l) ctx->tabs[l] = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l]};
+        for (int l = 1; l < nl; ++l) {
+            ResizeTab& T = ctx->tabs[l];
+            T = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l], 0, 0, 0};
+            // warp tile: `rows` destination rows whose source rows fit the strip; CTA tile: 128 x 4*rows destination
+            // pixels; the TMA box over the source level covers the CTA tile (x start rounded down to 16 bytes, and the
+            // three aligned words each thread reads)
+            const int* xo = allOfs.data() + oX[l]; const int* yo = allOfs.data() + oY[l];
+            const int dw = g.lv[l].w, dh = g.lv[l].h;
+            const double sc = (double)g.lv[l - 1].h / dh;
+            T.rows = std::max(1, std::min(kResizeDstRows, (int)((kResizeSrcRows - 2) / sc)));
+            int needW = 0, needH = 0;
+            for (int x0 = 0; x0 < dw; x0 += 128) {
+                const int xl = std::min(x0 + 127, dw - 1) & ~3;
+                needW = std::max(needW, (xo[xl] & ~3) + 12 - (xo[x0] & ~15));
+            }
+            for (int y0 = 0; y0 < dh; y0 += T.rows) {
+                const int span = yo[std::min(y0 + T.rows - 1, dh - 1)] + 2 - yo[y0];
+                if (span > kResizeSrcRows) return ctx->fail(NAV24_E_GEOMETRY, "scale factor too large for the resize tile");
+            }
+            for (int y0 = 0; y0 < dh; y0 += 4 * T.rows)
+                needH = std::max(needH, yo[std::min(y0 + 4 * T.rows - 1, dh - 1)] + 2 - yo[y0]);
+            T.boxW = needW <= 192 ? 192 : 256;
+            T.boxH = needH;
+            if (needW > 256 || needH > 256) return ctx->fail(NAV24_E_GEOMETRY, "scale factor too large for the resize tile");
+        }
         std::vector<FastSeg> segs;
         build_fast_segments(g, segs);
         CK(ctx->bSegs.ensure(segs.size() * sizeof(FastSeg)));
@@ -435,6 +460,11 @@ int encode_maps(nav24_orb* ctx, int B) {
                 rc = encode_level_map(ctx, &ctx->mapsOri.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
                                       g.lv[l].pitch, g.pyrFrameBytes, kOriBoxW, kOriBoxH);
                 if (rc != NAV24_OK) return rc;
+                if (l + 1 < g.nlevels) {
+                    rc = encode_level_map(ctx, &ctx->mapsRs.m[l + 1], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
+                                          g.lv[l].pitch, g.pyrFrameBytes, ctx->tabs[l + 1].boxW, ctx->tabs[l + 1].boxH);
+                    if (rc != NAV24_OK) return rc;
+                }
             }
             rc = encode_level_map(ctx, &ctx->mapsBlur.m[l], ctx->p.blur + g.lv[l].boff, g.lv[l].w, g.lv[l].h, ctx->wsB,
                                   g.lv[l].pitch, g.blurFrameBytes, kDescBoxW, kDescBoxH);
@@ -446,6 +476,11 @@ int encode_maps(nav24_orb* ctx, int B) {
     int rc = encode_level_map(ctx, &ctx->mapsOri.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame, kOriBoxW,
                               kOriBoxH);
     if (rc != NAV24_OK) return rc;
+    if (g.nlevels > 1) {
+        rc = encode_level_map(ctx, &ctx->mapsRs.m[1], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame,
+                              ctx->tabs[1].boxW, ctx->tabs[1].boxH);
+        if (rc != NAV24_OK) return rc;
+    }
     return encode_level_map(ctx, &ctx->maps.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame, g.lv[0].boxW,
                             g.lv[0].boxH);
 }
@@ -460,7 +495,7 @@ int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
         ctx->evCalls++;
         CK(cudaEventRecord(ctx->ev[0], s));
     }
-    ctx->launches += launch_pyramid(g, q, ctx->tabs.data(), C, s);
+    ctx->launches += launch_pyramid(g, q, ctx->tabs.data(), ctx->mapsRs, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[1], s));
     ctx->launches += launch_fast(g, q, ctx->maps, C, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);
     if (stages) CK(cudaEventRecord(ctx->ev[2], s));

@@ -131,12 +131,17 @@ struct FastSmem { int offMap, offMask, offQueue, offWin, total; };   // dynamic 
 
 struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;
+    int rows;                // destination rows per warp tile (their source rows fit kResizeSrcRows)
+    int boxW, boxH;          // TMA box over the SOURCE level that covers one CTA tile (128 x 4*rows destination pixels)
 };
+
+constexpr int kResizeSrcRows = 12;     // source rows of one warp tile of resize_kernel
+constexpr int kResizeDstRows = 8;      // destination rows of one warp tile (upper bound)
 
 // launchers (orb_kernels.cu); each returns the number of kernels launched
 // tight (pitch = w) host-order frames -> 16-byte aligned pitch (TMA needs it); returns 1
 int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s);
-int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, int B, cudaStream_t s);
+int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s);
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
 int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, int B, cudaStream_t s);

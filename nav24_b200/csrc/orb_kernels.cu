@@ -48,6 +48,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /*
     return s_warp[wid] + incl - v;
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 // ------------------------------------------------------------------------------------------
 // K0  repack: frames arrive from the host as ONE contiguous copy (a strided cudaMemcpy2D of 1241-byte rows
 // runs at 10 GB/s, the contiguous copy at 55 GB/s) and are re-pitched on the device to the 16-byte
@@ -77,27 +79,47 @@ __global__ void __launch_bounds__(256) repack_kernel(const uint8_t* __restrict__
 // ------------------------------------------------------------------------------------------
 // K1  pyramid level l-1 -> l.  cv::resize(INTER_LINEAR) on CV_8UC1 = 11-bit fixed-point separable
 // bilinear; replaces ComputePyramid (OP_FtDtOrbSlam.cpp:936-960).
-// One WARP owns 128 destination columns x `rows` destination rows (8 at scale 1.2); a thread owns 4 adjacent columns.
-// Phase 1, per SOURCE row of the tile (<= kResizeSrcRows, all loads issued before the first use): the three aligned
-// words that cover the thread's <= 8-byte source window are shifted to byte 0 (2 SHF), each pixel's two taps are
-// picked by one PRMT (selectors are per-thread constants) and S[s]*a0 + S[s+1]*a1 is one DP2A; the four
-// horizontally interpolated values go to the warp's shared-memory strip as one 16-byte store.
+// One CTA = 128 destination columns x 4*rows destination rows; its source pixels arrive as ONE TMA box (x start rounded
+// down to 16 bytes; the box sizes come from the host, ResizeTab).  One WARP owns `rows` destination rows (8 at scale
+// 1.2), a thread 4 adjacent columns.
+// Phase 1, per SOURCE row of the warp tile (<= kResizeSrcRows): the three aligned words that cover the thread's
+// <= 8-byte source window are shifted to byte 0 (2 SHF), each pixel's two taps are picked by one PRMT (selectors are
+// per-thread constants) and S[s]*a0 + S[s+1]*a1 is one DP2A; the four horizontally interpolated values go to the
+// warp's shared-memory strip as one 16-byte store.
 // Phase 2, per DESTINATION row (statically unrolled; row offset and coefficient pair are warp-uniform loads issued
 // up front): two 16-byte loads from the strip (a thread only ever reads its own columns, shared memory is used for the
 // dynamic ROW index), ((b0*top + 2^17) >> 16) + ((b1*bot) >> 16) as two multiply-highs by the coefficients
 // pre-shifted left by 16, >> 2, pack, one 32-bit store.
 // ------------------------------------------------------------------------------------------
-constexpr int kResizeSrcRows = 12;     // source rows of one warp tile
-constexpr int kResizeDstRows = 8;      // destination rows of one warp tile (upper bound)
-
-__global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__ src, unsigned sPitch, long long sFrame,
-                                                     int sw, int sh, uint8_t* __restrict__ dst, int dPitch,
-                                                     long long dFrame, int dw, int dh, int rows, ResizeTab t) {
-    __shared__ uint4 sH[4][kResizeSrcRows][32];
+template <int BOXW>
+__global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUtensorMap srcMap, int frameBase,
+                                                     uint8_t* __restrict__ dst, int dPitch, long long dFrame, int dw, int dh,
+                                                     ResizeTab t) {
+    extern __shared__ __align__(128) uint8_t s_rs[];       // [boxH][BOXW] source tile | uint4 [4][kResizeSrcRows][32] strips
+    __shared__ __align__(8) unsigned long long bar;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int x4 = (blockIdx.x * 32 + lane) * 4;
-    const int y0 = (blockIdx.y * 4 + wid) * rows;
+    const int rows = t.rows;
+    const int x0c = blockIdx.x * 128, y0c = blockIdx.y * 4 * rows;
+    const int tileX0 = __ldg(t.xofs + x0c) & ~15, tileY0 = __ldg(t.yofs + y0c);
+    const unsigned barAddr = smem_u32(&bar);
+    const unsigned tileBytes = (unsigned)(BOXW * t.boxH);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(tileBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                smem_u32(s_rs)),
+            "l"(&srcMap), "r"(tileX0), "r"(tileY0), "r"((int)blockIdx.z + frameBase), "r"(barAddr)
+            : "memory");
+    }
+    const int x4 = x0c + lane * 4;
+    const int y0 = y0c + wid * rows;
     if (y0 >= dh) return;                                  // warp-uniform
+    uint4* sH = reinterpret_cast<uint4*>(s_rs + ((tileBytes + 127u) & ~127u)) + wid * (kResizeSrcRows * 32) + lane;
     const int nrows = min(rows, dh - y0);
     // warp-uniform vertical constants of the tile's destination rows
     int yo[kResizeDstRows]; unsigned yc[kResizeDstRows];
@@ -109,43 +131,42 @@ __global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__
     }
     // per-thread horizontal constants
     const bool active = x4 < dw;
-    const int s0 = t.xofs[min(x4, dw - 1)];
-    const int sa = s0 & ~3;                                // aligned start of the source window
+    const int s0 = __ldg(t.xofs + min(x4, dw - 1));
     const unsigned shift = (unsigned)(s0 & 3) * 8u;
-    const int lastW = (sw - 1) & ~3;                       // words beyond the row are never read (their taps weigh 0)
-    const uint8_t* sp = src + (long long)blockIdx.z * sFrame;
-    const uint8_t* q0 = sp + sa;
-    const uint8_t* q1 = sp + min(sa + 4, lastW);
-    const uint8_t* q2 = sp + min(sa + 8, lastW);
     unsigned sel[4], ab[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int x = min(x4 + k, dw - 1);
-        const int d = t.xofs[x] - s0;                      // 0..5
+        const int d = __ldg(t.xofs + x) - s0;              // 0..5
         sel[k] = (unsigned)d | ((unsigned)(d + 1) << 4);
-        ab[k] = *reinterpret_cast<const unsigned*>(t.xab + x);  // (a0, a1) as two u16 (both in [0, 2048])
+        ab[k] = __ldg(reinterpret_cast<const unsigned*>(t.xab) + x);      // (a0, a1) as two u16 (both in [0, 2048])
     }
     const int syBase = yo[0];
-    const int nsrc = min(yo[kResizeDstRows - 1] + 2 - syBase, kResizeSrcRows);      // warp-uniform (the host sizes `rows` for it)
-    // phase 1: every load of the tile is in flight before the first use
-    unsigned W[kResizeSrcRows][3];
-#pragma unroll
-    for (int i = 0; i < kResizeSrcRows; ++i) {
-        const unsigned long long ro = (unsigned long long)((unsigned)min(syBase + min(i, nsrc - 1), sh - 1)) * sPitch;
-        W[i][0] = __ldg(reinterpret_cast<const unsigned*>(q0 + ro));
-        W[i][1] = __ldg(reinterpret_cast<const unsigned*>(q1 + ro));
-        W[i][2] = __ldg(reinterpret_cast<const unsigned*>(q2 + ro));
+    const int nsrc = min(yo[kResizeDstRows - 1] + 2 - syBase, kResizeSrcRows);      // warp-uniform (the host sized `rows` for it)
+    const uint8_t* rp = s_rs + (syBase - tileY0) * BOXW + ((s0 & ~3) - tileX0);      // the thread's window in the tile
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(barAddr), "r"(0u)
+                : "memory");
+        }
     }
+    // phase 1 (bytes beyond the source image are zero-filled by TMA; their taps weigh 0)
 #pragma unroll
     for (int i = 0; i < kResizeSrcRows; ++i) {
         if (i < nsrc) {                                    // warp-uniform
-            const unsigned lo = __funnelshift_r(W[i][0], W[i][1], shift), hi = __funnelshift_r(W[i][1], W[i][2], shift);
+            const unsigned* wp = reinterpret_cast<const unsigned*>(rp + i * BOXW);
+            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
             uint4 h;
             h.x = __dp2a_lo(ab[0], __byte_perm(lo, hi, sel[0]), 0u) >> 4;
             h.y = __dp2a_lo(ab[1], __byte_perm(lo, hi, sel[1]), 0u) >> 4;
             h.z = __dp2a_lo(ab[2], __byte_perm(lo, hi, sel[2]), 0u) >> 4;
             h.w = __dp2a_lo(ab[3], __byte_perm(lo, hi, sel[3]), 0u) >> 4;
-            sH[wid][i][lane] = h;
+            sH[i * 32] = h;
         }
     }
     __syncwarp();
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(128) resize_kernel(const uint8_t* __restrict__
     for (int j = 0; j < kResizeDstRows; ++j) {
         if (j < nrows) {                                   // warp-uniform
             const int i0 = yo[j] - syBase;
-            const uint4 top = sH[wid][i0][lane], bot = sH[wid][i0 + 1][lane];
+            const uint4 top = sH[i0 * 32], bot = sH[i0 * 32 + 32];
             const unsigned c0 = yc[j] << 16, c1 = yc[j] & 0xffff0000u;
             // ((b0*top + 0x20000) >> 16) + ((b1*bot) >> 16)  ==  umulhi(top, b0 << 16) + 2 + umulhi(bot, b1 << 16)
             const unsigned v0 = (__umulhi(top.x, c0) + 2u + __umulhi(bot.x, c1)) >> 2;
@@ -219,8 +240,6 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int pitch) {
 // pass when it equals t (a false positive of the FILTER, removed by the exact score), and the overflowing byte
 // itself has bit 7 set, so it passes through the "| x" term.
 __device__ __forceinline__ unsigned gt_any2(unsigned x1, unsigned x2, unsigned k) { return (x1 + k) | x1 | (x2 + k) | x2; }
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // set bits of kmask row `rowp` inside the column range [x0, x1), x1 > x0: popcount
 __device__ __forceinline__ int mask_range_count(const unsigned* rowp, int x0, int x1) {
@@ -1094,20 +1113,23 @@ int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, in
     return 1;
 }
 
-int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, int B, cudaStream_t s) {
+int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s) {
     int n = 0;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(resize_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(resize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr = true;
+    }
     for (int l = 1; l < g.nlevels; ++l) {
-        const LevelGeom& S = g.lv[l - 1];
         const LevelGeom& D = g.lv[l];
-        const uint8_t* src = (l == 1) ? p.l0 : p.pyr + S.off;
-        const unsigned sPitch = (unsigned)((l == 1) ? p.l0Pitch : S.pitch);
-        const long long sFrame = (l == 1) ? p.l0Frame : g.pyrFrameBytes;
-        // destination rows per thread such that their source rows (rows * scale + 2) fit the in-flight window
-        const double sc = (double)S.h / D.h;
-        const int rows = std::max(1, std::min(8, (int)((kResizeSrcRows - 2) / sc)));
-        dim3 grid((D.w + 127) / 128, (D.h + 4 * rows - 1) / (4 * rows), B);
-        resize_kernel<<<grid, 128, 0, s>>>(src, sPitch, sFrame, S.w, S.h, p.pyr + D.off, D.pitch, g.pyrFrameBytes,
-                                             D.w, D.h, rows, tabs[l]);
+        const ResizeTab& T = tabs[l];
+        dim3 grid((D.w + 127) / 128, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
+        const size_t smem = (size_t)((T.boxW * T.boxH + 127) / 128 * 128) + 4 * kResizeSrcRows * 32 * sizeof(uint4);
+        if (T.boxW == 192)
+            resize_kernel<192><<<grid, 128, smem, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
+        else
+            resize_kernel<256><<<grid, 128, smem, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
         ++n;
     }
     return n;
