@@ -80,6 +80,7 @@ struct nav24_orb {
     std::vector<ResizeTab> tabs;
     TmaMaps maps{};           // FAST segment tiles over the un-blurred levels
     TmaMaps mapsRs{};         // m[l]: resize source tiles over level l-1 (resize_kernel producing level l)
+    TmaMaps mapsBlurSrc{};    // 160 x 146 source tiles of blur_kernel over the un-blurred levels
     TmaMaps mapsOri{};        // 48 x 31 orientation patches over the un-blurred levels (describe_kernel)
     TmaMaps mapsBlur{};       // 64 x 37 descriptor patches over the blurred levels (describe_kernel)
     const void* mapsBlurPtr = nullptr;
@@ -181,7 +182,7 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         L.magicW = 0xFFFFFFFFu / (unsigned)L.wCell + 1u;
         L.cellBase = cellBase;
         L.blurTileBase = stripBase;
-        stripBase += ((L.w + 127) / 128) * ((L.h + kBlurTileRows - 1) / kBlurTileRows);
+        stripBase += ((L.w + 127) / 128) * ((L.h + kBlurCtaRows - 1) / kBlurCtaRows);
         cellBase += L.nCols * L.nRows;
         long long cap = ((long long)L.w * L.h * rawPerKpx + 999) / 1000 + 64;
         if (cap >= (1 << 19)) cap = (1 << 19) - 1;      // sort key packs count into 19 bits
@@ -460,6 +461,9 @@ int encode_maps(nav24_orb* ctx, int B) {
                 rc = encode_level_map(ctx, &ctx->mapsOri.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
                                       g.lv[l].pitch, g.pyrFrameBytes, kOriBoxW, kOriBoxH);
                 if (rc != NAV24_OK) return rc;
+                rc = encode_level_map(ctx, &ctx->mapsBlurSrc.m[l], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
+                                      g.lv[l].pitch, g.pyrFrameBytes, kBlurBoxW, kBlurBoxH);
+                if (rc != NAV24_OK) return rc;
                 if (l + 1 < g.nlevels) {
                     rc = encode_level_map(ctx, &ctx->mapsRs.m[l + 1], ctx->p.pyr + g.lv[l].off, g.lv[l].w, g.lv[l].h, ctx->wsB,
                                           g.lv[l].pitch, g.pyrFrameBytes, ctx->tabs[l + 1].boxW, ctx->tabs[l + 1].boxH);
@@ -475,6 +479,9 @@ int encode_maps(nav24_orb* ctx, int B) {
     const long long l0Frame = B > 1 ? ctx->p.l0Frame : ctx->p.l0Pitch * g.lv[0].h;
     int rc = encode_level_map(ctx, &ctx->mapsOri.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame, kOriBoxW,
                               kOriBoxH);
+    if (rc != NAV24_OK) return rc;
+    rc = encode_level_map(ctx, &ctx->mapsBlurSrc.m[0], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame, kBlurBoxW,
+                          kBlurBoxH);
     if (rc != NAV24_OK) return rc;
     if (g.nlevels > 1) {
         rc = encode_level_map(ctx, &ctx->mapsRs.m[1], ctx->p.l0, g.lv[0].w, g.lv[0].h, B, ctx->p.l0Pitch, l0Frame,
@@ -501,7 +508,7 @@ int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
     if (stages) CK(cudaEventRecord(ctx->ev[2], s));
     ctx->launches += launch_quadtree(g, q, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[3], s));
-    ctx->launches += launch_describe(g, q, ctx->mapsOri, ctx->mapsBlur, C, s);
+    ctx->launches += launch_describe(g, q, ctx->mapsBlurSrc, ctx->mapsOri, ctx->mapsBlur, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaGetLastError());
     return NAV24_OK;

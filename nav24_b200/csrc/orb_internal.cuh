@@ -11,13 +11,9 @@ namespace nav24 {
 constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;           // EDGE_THRESHOLD (OP_FtDtOrbSlam.cpp:14)
 constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
-#ifndef NAV24_BLUR_ROWS
-#define NAV24_BLUR_ROWS 35
-#endif
-#ifndef NAV24_BLUR_MINB
-#define NAV24_BLUR_MINB 6
-#endif
-constexpr int kBlurTileRows = NAV24_BLUR_ROWS;   // rows per warp tile of blur_kernel (multiple of 7)
+constexpr int kBlurTileRows = 35;                    // rows per warp tile of blur_kernel (multiple of 7)
+constexpr int kBlurCtaRows = 4 * kBlurTileRows;     // rows per CTA tile (four warp tiles stacked)
+constexpr int kBlurBoxW = 160, kBlurBoxH = kBlurCtaRows + 6;   // TMA box: 128 px + 16-byte aligned halos, 3 halo rows each side
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
 constexpr int kOriBoxW = 48, kOriBoxH = 31;    // TMA box of the orientation patch: 31 px + <= 15 px of alignment slack, 16-B multiple
 constexpr int kDescBoxW = 64, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px + <= 15 px of alignment slack
@@ -41,7 +37,7 @@ struct LevelGeom {
     int boxW, boxH;          // TMA box of one FAST segment: kFastPitch x (hCell+6)
     unsigned magicW;         // 0xFFFFFFFF / wCell + 1: floor(n / wCell) = umulhi(n, magicW) for n < 65536
     int cellBase;            // first cell id of this level inside the per-frame cell table
-    int blurTileBase;        // first warp tile (128 px x kBlurTileRows rows) of this level in blur_kernel
+    int blurTileBase;        // first CTA tile (128 px x kBlurCtaRows rows) of this level in blur_kernel
     int rawCap;              // raw-corner capacity of this level (records)
     int rawOff;              // record offset of the level inside one frame's raw slab
     // quadtree (:502-725)
@@ -64,7 +60,7 @@ struct FrameGeom {
     int nodesPerFrame;
     int kpPerFrame;          // level-keypoint slab size (sum of kpCap)
     int outCap;              // output capacity per frame
-    int blurTiles;           // warp tiles of blur_kernel per frame
+    int blurTiles;           // CTA tiles of blur_kernel per frame
     long long pyrFrameBytes, blurFrameBytes;
     LevelGeom lv[kMaxLevels];
 };
@@ -144,7 +140,8 @@ int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, in
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s);
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
-int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, int B, cudaStream_t s);
+int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, const TmaMaps& mapsOri, const TmaMaps& mapsBlur,
+                    int B, cudaStream_t s);
 int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s);   // test hook (stdsort_warp.cuh)
 
 // matchers (match_kernels.cu)

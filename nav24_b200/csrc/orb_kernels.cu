@@ -846,21 +846,20 @@ __device__ __forceinline__ int reflect101(int v, int n) {
     return v;
 }
 
-// One WARP owns a 128-pixel-wide, kBlurRows-high tile; lane i owns pixels [4i, 4i+4) of every row.  Per input
-// row a lane loads ONE aligned word, gets its neighbours' words by shuffle (lanes 0/31 load the halo word of the
-// adjacent tile), forms the four horizontal 7-tap sums with two DP4A each (coefficients (18,34,48,56 | 48,34,18,0)),
-// keeps the last seven rows of sums in registers and emits one 32-bit word of output per row.  Loads of seven rows
-// are issued back to back before they are consumed.  BORDER_REFLECT_101: rows by index math (uniform per warp);
-// the left edge by one PRMT; the right edge by PRMTs on the words of the two lanes to the left (selectors depend
-// only on w & 3), so no byte loads and no divergent code.  One code path, 7 row bodies: the body must stay small,
-// the first version of this kernel (two template paths, 34 KB of SASS) stalled on instruction fetch.
-// All levels and frames in one launch; the warp tiles of a frame are numbered level by level (blurTileBase).
-constexpr int kBlurRows = kBlurTileRows;
-
-__global__ void __launch_bounds__(128, NAV24_BLUR_MINB) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (t >= g.blurTiles) return;
+// One CTA owns a 128-pixel-wide, kBlurCtaRows-high tile whose source pixels (3-px halo, x start rounded down to 16 bytes)
+// arrive as ONE TMA box; out-of-image bytes come back as zeros and BORDER_REFLECT_101 is restored by patching the few
+// halo columns / rows of the tile in shared memory (uniform branches, edge tiles only), so the main loop has a single
+// branch-free body.  One WARP owns kBlurTileRows rows of the tile, lane i the pixels [4i, 4i+4) of every row: per row
+// three words from shared memory (immediate offsets), the four horizontal 7-tap sums with two DP4A each
+// (coefficients (18,34,48,56 | 48,34,18,0)), the last seven rows of sums in a register ring, one 32-bit store.
+// All levels and frames in one launch; the CTA tiles of a frame are numbered level by level (blurTileBase).
+__global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+                                                   const __grid_constant__ TmaMaps maps) {
+    __shared__ __align__(128) uint8_t tile[kBlurBoxW * kBlurBoxH];
+    __shared__ __align__(8) unsigned long long bar;
+    constexpr int P = kBlurBoxW;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = blockIdx.x, f = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && t >= g.lv[l + 1].blurTileBase) ++l;
     const LevelGeom& L = g.lv[l];
@@ -868,60 +867,79 @@ __global__ void __launch_bounds__(128, NAV24_BLUR_MINB) blur_kernel(const __grid
     const int tilesX = (w + 127) >> 7;
     const int tt = t - L.blurTileBase;
     const int ty = tt / tilesX, tx = tt - ty * tilesX;
-    const int x4 = tx * 128 + lane * 4;
-    const int y0 = ty * kBlurRows, yEnd = min(y0 + kBlurRows, h);
-    const long long pitch = level_pitch(g, p, l);
-    const uint8_t* img = level_ptr(g, p, blockIdx.y, l) + x4;
-    uint8_t* dst = p.blur + (long long)blockIdx.y * g.blurFrameBytes + L.boff + x4;
-    const int dPitch = L.pitch;
+    const int tileX = tx * 128, rowBase = ty * kBlurCtaRows;
+    const unsigned barAddr = smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"((unsigned)(P * kBlurBoxH)) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                smem_u32(tile)),
+            "l"(&maps.m[l]), "r"(tileX - 16), "r"(rowBase - 3), "r"(f + p.frameBase), "r"(barAddr)
+            : "memory");
+    }
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(barAddr), "r"(0u)
+                : "memory");
+        }
+    }
+    // BORDER_REFLECT_101.  Tile column of image column x: x - tileX + 16; tile row of image row y: y - rowBase + 3.
+    const int rowsIn = min(h - rowBase, kBlurCtaRows + 3) + min(rowBase, 3);      // tile rows that hold image rows ...
+    const int rFirst = rowBase == 0 ? 3 : 0;                                      // ... starting at this tile row
+    const bool leftEdge = tx == 0, rightEdge = w < tileX + 131;
+    if (leftEdge || rightEdge) {
+        for (int r = threadIdx.x; r < rowsIn; r += 128) {
+            uint8_t* row = tile + (rFirst + r) * P + 16 - tileX;                  // row[x] = image column x
+            if (leftEdge) { row[-1] = row[1]; row[-2] = row[2]; row[-3] = row[3]; }
+            if (rightEdge)
+                for (int c = w; c < min(tileX + 131, w + 3); ++c) row[c] = row[2 * (w - 1) - c];
+        }
+        __syncthreads();
+    }
+    if (rowBase == 0) {                                                           // rows -1, -2, -3 = rows 1, 2, 3
+        for (int i = threadIdx.x; i < 3 * (P / 4); i += 128) {
+            const int k = i / (P / 4), c = i - k * (P / 4);
+            reinterpret_cast<unsigned*>(tile + (2 - k) * P)[c] = reinterpret_cast<const unsigned*>(tile + (4 + k) * P)[c];
+        }
+    }
+    if (h - rowBase < kBlurCtaRows + 3) {                                          // rows h, h+1, h+2 = rows h-2, h-3, h-4
+        const int rh = h - rowBase + 3;                                           // tile row of image row h
+        for (int i = threadIdx.x; i < 3 * (P / 4); i += 128) {
+            const int k = i / (P / 4), c = i - k * (P / 4);
+            if (rh + k < kBlurBoxH)
+                reinterpret_cast<unsigned*>(tile + (rh + k) * P)[c] = reinterpret_cast<const unsigned*>(tile + (rh - 2 - k) * P)[c];
+        }
+    }
+    __syncthreads();
 
+    const int y0 = rowBase + wid * kBlurTileRows, yEnd = min(y0 + kBlurTileRows, h);
+    const int x4 = tileX + lane * 4;
+    if (y0 >= h) return;
     const bool active = x4 < w;
-    const int lastWord = (w - 1) & ~3, valid = w - lastWord;            // valid bytes of the last word: 1..4
-    const bool edgeTile = tx * 128 + 128 >= lastWord;                   // warp-uniform: owns or borders the last word
-    const bool isLast = x4 == lastWord;
-    // warp-uniform and rare: the last word sits in lane 0 or 1 and its mirror reaches two words to the left of it, i.e.
-    // beyond lane 0's halo word.  Lane 31 (idle in such a tile) fetches that word into its halo register instead.
-    const bool needHm = edgeTile && valid <= 2 && lastWord - tx * 128 <= 4;
-    const bool haloL = lane == 0 && x4 > 0, haloR = lane == 31 && (x4 + 4 <= lastWord || needHm);
-    const int xh = haloL ? -4 : (needHm ? -8 - 124 : 4);
-    const bool fixHalo = lane == 31 && x4 + 4 == lastWord;
-    const unsigned selA = valid == 4 ? 0x7654u : valid == 3 ? 0x5654u : valid == 2 ? 0x3454u : 0x1234u;
-    const unsigned selB = (valid & 1) ? 0x0234u : 0x0456u;
+    uint8_t* dp = p.blur + (long long)f * g.blurFrameBytes + L.boff + (long long)y0 * L.pitch + x4;
+    const int dPitch = L.pitch;
     unsigned half;
     asm("mov.u32 %0, 32768;" : "=r"(half));      // kept in a register: IMAD has one immediate slot
-
+    // word 0 of the lane's window (pixels x4-4 .. x4-1) in the row that enters the ring first (image row y0 - 3)
+    const uint8_t* rp = tile + (y0 - rowBase) * P + 12 + lane * 4;
     unsigned hr[7][4];
     for (int yy = y0 - 6; yy < yEnd; yy += 7) {
-        unsigned a[7], hl[7];
-#pragma unroll
-        for (int s = 0; s < 7; ++s) {
-            int r = min(yy + s + 3, yEnd + 2);
-            r = r < 0 ? -r : r;
-            r = r >= h ? 2 * h - 2 - r : r;
-            const uint8_t* rp = img + (long long)r * pitch;
-            a[s] = active ? __ldg(reinterpret_cast<const unsigned*>(rp)) : 0u;
-            hl[s] = (haloL || haloR) ? __ldg(reinterpret_cast<const unsigned*>(rp + xh)) : 0u;
-        }
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
             const int y = yy + s;                   // output row; the row entering the window is y + 3
-            if (y >= yEnd) continue;                // uniform
-            unsigned w1 = a[s], halo = hl[s];
-            unsigned w0 = __shfl_up_sync(0xffffffffu, w1, 1);
-            if (lane == 0) w0 = x4 > 0 ? halo : __byte_perm(w1, w1, 0x1230);      // pixels -3,-2,-1 = 3,2,1
-            unsigned wm = 0u;
-            if (edgeTile) {
-                wm = __shfl_up_sync(0xffffffffu, w0, 1);
-                if (needHm) {
-                    const unsigned far = __shfl_sync(0xffffffffu, halo, 31);
-                    if (lane == 0) wm = far;
-                }
-                if (isLast) w1 = __byte_perm(w0, w1, selA);
-                if (fixHalo) halo = __byte_perm(w1, halo, selA);
-            }
-            unsigned w2 = __shfl_down_sync(0xffffffffu, w1, 1);
-            if (lane == 31) w2 = halo;
-            if (edgeTile && isLast) w2 = valid >= 3 ? __byte_perm(w0, w1, selB) : __byte_perm(wm, w0, selB);
+            if (y >= yEnd) break;                   // uniform
+            const unsigned w0 = *reinterpret_cast<const unsigned*>(rp), w1 = *reinterpret_cast<const unsigned*>(rp + 4),
+                           w2 = *reinterpret_cast<const unsigned*>(rp + 8);
+            rp += P;
             unsigned* o = hr[(s + 6) % 7];
             const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
             o[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
@@ -935,7 +953,8 @@ __global__ void __launch_bounds__(128, NAV24_BLUR_MINB) blur_kernel(const __grid
                     v[i] = 18u * (hr[s % 7][i] + hr[(s + 6) % 7][i]) + (34u * (hr[(s + 1) % 7][i] + hr[(s + 5) % 7][i]) +
                            (48u * (hr[(s + 2) % 7][i] + hr[(s + 4) % 7][i]) + (56u * hr[(s + 3) % 7][i] + half)));
                 const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
-                if (active) *reinterpret_cast<unsigned*>(dst + (long long)y * dPitch) = word;
+                if (active) *reinterpret_cast<unsigned*>(dp) = word;
+                dp += dPitch;
             }
         }
     }
@@ -1205,12 +1224,12 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     return 2;
 }
 
-int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, int B,
-                    cudaStream_t s) {
+int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, const TmaMaps& mapsOri, const TmaMaps& mapsBlur,
+                    int B, cudaStream_t s) {
     int n = 0;
     {
-        dim3 grid((g.blurTiles + 3) / 4, B);
-        blur_kernel<<<grid, 128, 0, s>>>(g, p);
+        dim3 grid(g.blurTiles, B);
+        blur_kernel<<<grid, 128, 0, s>>>(g, p, mapsBlurSrc);
         ++n;
     }
     dim3 grid(g.kpPerFrame, B);
