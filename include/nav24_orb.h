@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NAV24_ABI_VERSION 1
+#define NAV24_ABI_VERSION 2
 
 /* error codes */
 #define NAV24_OK 0
@@ -68,6 +68,21 @@ typedef struct nav24_grid_cfg {
     int32_t cols, rows;
     float min_x, max_x, min_y, max_y;
 } nav24_grid_cfg;
+
+/* Camera model of Calibration::undistort (core/sensor/camera/Calibration.cpp:135-149), the step between detect and
+ * matchV (core/frontEnd/FE_SlamMonoV.cpp:104-122).  K and D are the float matrices the reference hands to OpenCV
+ * (models/GeometricCamera.h:62-66: K = (fx 0 cx; 0 fy cy; 0 0 1), D = 4 coefficients, R = I, P = K):
+ *   NAV24_CAM_PINHOLE  identity                                   (models/Pinhole.hpp:75-78)
+ *   NAV24_CAM_RADTAN   cv::undistortPoints, d = k1 k2 p1 p2         (models/PinholeRadTan.cpp:11-25)
+ *   NAV24_CAM_KB8      cv::fisheye::undistortPoints, d = k1..k4     (models/KannalaBrandt8.cpp:231-243) */
+#define NAV24_CAM_PINHOLE 0
+#define NAV24_CAM_RADTAN 1
+#define NAV24_CAM_KB8 2
+typedef struct nav24_camera {
+    int32_t model;
+    float fx, fy, cx, cy;
+    float d[4];
+} nav24_camera;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
 int nav24_abi_version(void);
@@ -169,6 +184,19 @@ int nav24_match_window_batch(nav24_orb* ctx, int n_pairs, int cap, const nav24_k
 int nav24_match_window_frames(nav24_orb* ctx, int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid,
                               float window, float nnratio, int th_low, int check_ori, int32_t* matches12,
                               int cap, int* n_matches);
+
+/* ---- undistortion (keeps the frame on the device between detect and matchV) ------------- */
+/* Replaces Calibration::undistort / GeometricCamera::UndistortKeyPoints for n points in host memory: xy and ud_xy are
+ * n x (x, y) floats (may alias).  Double-precision restatement of the OpenCV routines, results rounded to float like
+ * cv::Point2f.  Also what Calibration::computeImageBounds (Calibration.cpp:196-228) feeds the four image corners to. */
+int nav24_undistort_points(nav24_orb* ctx, const nav24_camera* cam, const float* xy, int n, float* ud_xy);
+/* Camera of the fused detect + match entry points and of nav24_match_window_frames: with a model other than pinhole
+ * every detect call also undistorts its keypoints on the device and the matchers consume those coordinates (grid
+ * cells, window test), exactly like matchV reading getPointUd().  cam == NULL resets to pinhole. */
+int nav24_orb_set_camera(nav24_orb* ctx, const nav24_camera* cam);
+/* Undistorted coordinates of the last detect batch: ud_xy is [n_frames][cap][2] floats (cap >= keypoints per frame;
+ * rows beyond a frame's count are left untouched).  Synchronises. */
+int nav24_orb_fetch_undistorted(nav24_orb* ctx, float* ud_xy, int cap);
 
 /* Intended semantics of FtAssocOCV::match (OP_FtAssoc.cpp:63-99): brute-force kNN-2 + ratio test.
  * norm 0 = Hamming (popcount), 1 = L2 on the u8 bytes (cv::DescriptorMatcher::BRUTEFORCE default, :20).

@@ -19,6 +19,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
 
 OK, E_BADARG, E_GEOMETRY, E_CAPACITY, E_OVERFLOW, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 NORM_HAMMING, NORM_L2_U8 = 0, 1
+CAM_PINHOLE, CAM_RADTAN, CAM_KB8 = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -29,6 +30,16 @@ class Params(C.Structure):
 class GridCfg(C.Structure):
     _fields_ = [("cols", C.c_int32), ("rows", C.c_int32), ("min_x", C.c_float), ("max_x", C.c_float),
                 ("min_y", C.c_float), ("max_y", C.c_float)]
+
+
+class Camera(C.Structure):
+    """nav24_camera: model + K (fx fy cx cy) + 4 distortion coefficients, all float like the reference's cv::Mat."""
+    _fields_ = [("model", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("d", C.c_float * 4)]
+
+    @staticmethod
+    def make(model, K4=(1, 1, 0, 0), D4=(0, 0, 0, 0)):
+        return Camera(model, K4[0], K4[1], K4[2], K4[3], (C.c_float * 4)(*D4))
 
 
 class Nav24Error(RuntimeError):
@@ -89,6 +100,9 @@ def lib():
                                            C.c_float, C.c_int, C.c_int, vp, vp]
     L.nav24_match_window_frames.argtypes = [vp, C.c_int, vp, C.POINTER(GridCfg), C.c_float, C.c_float, C.c_int, C.c_int, vp,
                                             C.c_int, vp]
+    L.nav24_undistort_points.argtypes = [vp, C.POINTER(Camera), vp, C.c_int, vp]
+    L.nav24_orb_set_camera.argtypes = [vp, C.POINTER(Camera)]
+    L.nav24_orb_fetch_undistorted.argtypes = [vp, vp, C.c_int]
     L.nav24_match_bf_knn2.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp]
     L.nav24_debug_sort_u32.argtypes = [vp, vp, C.c_int, vp]
     L.nav24_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -108,6 +122,15 @@ def grid_for(W, H, bounds=None):
     """FeatureGrid::setImageBounds (FeatureGrid.cpp:100-113) for a pinhole camera."""
     b = bounds or (0.0, float(W), 0.0, float(H))
     return GridCfg(W // 10, H // 10, b[0], b[1], b[2], b[3])
+
+
+def image_bounds(undistort, W, H, calibrated):
+    """Calibration::computeImageBounds (Calibration.cpp:196-228): the undistorted image corners for a distorted camera,
+    the image rectangle otherwise.  undistort: callable xy[n,2] -> ud[n,2].  Returns (minX, maxX, minY, maxY)."""
+    if calibrated:
+        return (0.0, float(W), 0.0, float(H))
+    c = undistort(np.array([[0, 0], [W, 0], [0, H], [W, H]], np.float32)).reshape(-1)
+    return (float(min(c[0], c[4])), float(max(c[2], c[6])), float(min(c[1], c[3])), float(max(c[5], c[7])))
 
 
 def pinned_empty(shape, dtype=np.uint8):
@@ -283,6 +306,22 @@ class OrbContext:
 
     def launch_count(self):
         return int(self.L.nav24_orb_launch_count(self.h))
+
+    # ---- camera ----
+    def undistort_points(self, cam, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.zeros_like(xy)
+        self._check(self.L.nav24_undistort_points(self.h, C.byref(cam), _p(xy), len(xy), _p(out)))
+        return out
+
+    def set_camera(self, cam):
+        self._check(self.L.nav24_orb_set_camera(self.h, C.byref(cam) if cam is not None else None))
+
+    def fetch_undistorted(self, B, cap=None):
+        cap = cap or self.max_keypoints()
+        ud = np.zeros((B, cap, 2), np.float32)
+        self._check(self.L.nav24_orb_fetch_undistorted(self.h, _p(ud), cap))
+        return ud
 
     # ---- matchers ----
     def match_window(self, k1, ud1, d1, k2, ud2, d2, grid, window=100.0, nnratio=0.6, th_low=50, check_ori=True):

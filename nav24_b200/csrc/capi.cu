@@ -78,6 +78,7 @@ struct nav24_orb {
     FrameGeom g{};
     DevPtrs p{};
     std::vector<ResizeTab> tabs;
+    nav24_camera cam{};       // camera of the fused paths (model 0 = pinhole: identity undistortion)
     TmaMaps maps{};           // FAST segment tiles over the un-blurred levels
     TmaMaps mapsRs{};         // m[l]: resize source tiles over level l-1 (resize_kernel producing level l)
     TmaMaps mapsBlurSrc{};    // 160 x 146 source tiles of blur_kernel over the un-blurred levels
@@ -87,7 +88,7 @@ struct nav24_orb {
     int mapsB = 0;            // frame count the level>=1 maps were encoded for
     const void* mapsPyr = nullptr;
     DevBuf bL0Tight, bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
-        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs, bOriTab, bSegs;
+        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs, bOriTab, bSegs, bOutUd, bUdTmp;
     // matcher scratch
     DevBuf mK1, mK2, mU1, mU2, mD1, mD2, mN1, mN2, mCellOf, mCellStart, mCellFill, mCellItems, mCand, mCandCnt, mDist2,
         mM21, mBins, mMatches, mNMatches, mPairs, mPairOrder, mI0, mI1, mF0, mF1, mPass;
@@ -388,6 +389,7 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         CK(ctx->bRawTotal.ensure(b * g.nlevels * sizeof(int)));
         CK(ctx->bOutKp.ensure(b * g.outCap * sizeof(nav24_kp)));
         CK(ctx->bOutDesc.ensure(b * g.outCap * 32));
+        CK(ctx->bOutUd.ensure(b * g.outCap * 2 * sizeof(float)));
         CK(ctx->bNOut.ensure(b * sizeof(int)));
         CK(ctx->bMono.ensure(b * sizeof(int)));
         if (!ctx->bErr.ptr) {      // the device error word is sticky (cleared when read), so it starts at zero
@@ -422,7 +424,7 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         p.nodeAux = (int*)ctx->bAux.ptr; p.best = (unsigned long long*)ctx->bBest.ptr;
         p.sortRec = (unsigned long long*)ctx->bSort.ptr; p.lkp = (LevelKp*)ctx->bLkp.ptr;
         p.levelCount = (int*)ctx->bLevelCount.ptr; p.rawTotal = (int*)ctx->bRawTotal.ptr;
-        p.outKp = (nav24_kp*)ctx->bOutKp.ptr; p.outDesc = (uint8_t*)ctx->bOutDesc.ptr;
+        p.outKp = (nav24_kp*)ctx->bOutKp.ptr; p.outDesc = (uint8_t*)ctx->bOutDesc.ptr; p.outUd = (float*)ctx->bOutUd.ptr;
         p.nOut = (int*)ctx->bNOut.ptr; p.monoOut = (int*)ctx->bMono.ptr; p.err = (int*)ctx->bErr.ptr;
         p.oriTab = (const unsigned*)ctx->bOriTab.ptr;
         p.segs = (const FastSeg*)ctx->bSegs.ptr;
@@ -442,7 +444,7 @@ DevPtrs chunk_ptrs(const nav24_orb* ctx, int f0) {
     q.raw += f * g.rawPerFrame; q.keys += f * g.rawPerFrame; q.nodeOfKey += f * g.rawPerFrame;
     q.nodesA += f * g.nodesPerFrame; q.nodesB += f * g.nodesPerFrame; q.childCnt += 4 * f * g.nodesPerFrame;
     q.nodeAux += f * g.nodesPerFrame; q.best += f * g.nodesPerFrame; q.sortRec += f * g.nodesPerFrame;
-    q.lkp += f * g.kpPerFrame; q.outKp += f * g.outCap; q.outDesc += f * g.outCap * 32;
+    q.lkp += f * g.kpPerFrame; q.outKp += f * g.outCap; q.outDesc += f * g.outCap * 32; q.outUd += f * g.outCap * 2;
     q.nOut += f; q.monoOut += f;
     q.frameBase = f0;
     return q;
@@ -509,6 +511,8 @@ int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
     ctx->launches += launch_quadtree(g, q, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[3], s));
     ctx->launches += launch_describe(g, q, ctx->mapsBlurSrc, ctx->mapsOri, ctx->mapsBlur, C, s);
+    if (ctx->cam.model != NAV24_CAM_PINHOLE)      // Calibration::undistort between detect and matchV (FE_SlamMonoV.cpp:115)
+        ctx->launches += launch_undistort_frames(ctx->cam, q.outKp, q.nOut, g.outCap, C, q.outUd, s);
     if (stages) CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaGetLastError());
     return NAV24_OK;
@@ -664,7 +668,7 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     DevBuf* bufs[] = {&ctx->bL0Tight, &ctx->bL0, &ctx->bPyr, &ctx->bBlur, &ctx->bCell, &ctx->bCellDst, &ctx->bRawCount, &ctx->bRaw, &ctx->bKeys,
                       &ctx->bNodeOfKey, &ctx->bNodesA, &ctx->bNodesB, &ctx->bChild, &ctx->bAux, &ctx->bBest, &ctx->bSort,
                       &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
-                      &ctx->bErr, &ctx->bTabs, &ctx->bOriTab, &ctx->bSegs, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
+                      &ctx->bErr, &ctx->bTabs, &ctx->bOriTab, &ctx->bSegs, &ctx->bOutUd, &ctx->bUdTmp, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
                       &ctx->mN2, &ctx->mCellOf, &ctx->mCellStart, &ctx->mCellFill, &ctx->mCellItems, &ctx->mCand, &ctx->mCandCnt,
                       &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mPairOrder, &ctx->mI0, &ctx->mI1,
                       &ctx->mF0, &ctx->mF1, &ctx->mPass};
@@ -831,7 +835,8 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
         CK(cudaMemcpyAsync(dPairs, mp->pairs, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->copyStream));
         CK(cudaMemcpyAsync(dOrder, order.data(), (size_t)P * 4, cudaMemcpyHostToDevice, ctx->copyStream));
         fill_match_args(ctx, ma, mp->grid, mp->window, mp->nnratio, mp->thLow, mp->checkOri, g.outCap);
-        ma.k1 = ma.k2 = ctx->p.outKp; ma.ud1 = ma.ud2 = nullptr; ma.d1 = ma.d2 = ctx->p.outDesc;
+        ma.k1 = ma.k2 = ctx->p.outKp; ma.d1 = ma.d2 = ctx->p.outDesc;
+        ma.ud1 = ma.ud2 = ctx->cam.model != NAV24_CAM_PINHOLE ? ctx->p.outUd : nullptr;
         ma.n1 = ma.n2 = ctx->p.nOut; ma.stride1 = ma.stride2 = g.outCap;
         ma.pairs = dPairs; ma.pairOrder = dOrder;
     }
@@ -1217,7 +1222,8 @@ int nav24_match_window_frames(nav24_orb* ctx, int P, const int* pairs_ab, const 
     CK(cudaMemcpyAsync(ctx->mPairs.ptr, pairs_ab, (size_t)P * 8, cudaMemcpyHostToDevice, s));
     MatchArgs a{};
     fill_match_args(ctx, a, grid, window, nnratio, th_low, check_ori, oc);
-    a.k1 = a.k2 = ctx->p.outKp; a.ud1 = a.ud2 = nullptr; a.d1 = a.d2 = ctx->p.outDesc;
+    a.k1 = a.k2 = ctx->p.outKp; a.d1 = a.d2 = ctx->p.outDesc;
+    a.ud1 = a.ud2 = ctx->cam.model != NAV24_CAM_PINHOLE ? ctx->p.outUd : nullptr;
     a.n1 = a.n2 = ctx->p.nOut; a.stride1 = a.stride2 = oc; a.pairs = (const int*)ctx->mPairs.ptr;
     ctx->launches += launch_match_window(a, P, s);
     CK(cudaGetLastError());
@@ -1230,6 +1236,58 @@ int nav24_match_window_frames(nav24_orb* ctx, int P, const int* pairs_ab, const 
     int total = 0;
     for (int p = 0; p < P; ++p) { if (n_matches) n_matches[p] = nm[p]; total += nm[p]; }
     return total;
+}
+
+static bool camera_ok(const nav24_camera* c) {
+    return c && c->model >= NAV24_CAM_PINHOLE && c->model <= NAV24_CAM_KB8 && (c->model == NAV24_CAM_PINHOLE || (c->fx != 0.f && c->fy != 0.f));
+}
+
+int nav24_undistort_points(nav24_orb* ctx, const nav24_camera* cam, const float* xy, int n, float* ud_xy) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!camera_ok(cam) || n < 0 || (n > 0 && (!xy || !ud_xy))) return ctx->fail(NAV24_E_BADARG, "bad undistort argument");
+    if (n == 0) return NAV24_OK;
+    cudaSetDevice(ctx->device);
+    CK(ctx->bUdTmp.ensure((size_t)n * 16));
+    float* dIn = (float*)ctx->bUdTmp.ptr; float* dOut = dIn + 2 * (size_t)n;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(dIn, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    ctx->launches += launch_undistort_points(*cam, dIn, n, dOut, s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ud_xy, dOut, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return NAV24_OK;
+}
+
+int nav24_orb_set_camera(nav24_orb* ctx, const nav24_camera* cam) {
+    if (!ctx) return NAV24_E_BADARG;
+    if (!cam) { ctx->cam = nav24_camera{}; return NAV24_OK; }
+    if (!camera_ok(cam)) return ctx->fail(NAV24_E_BADARG, "bad camera model");
+    ctx->cam = *cam;
+    ctx->lastValid = false;      // coordinates on the device belong to the previous camera
+    return NAV24_OK;
+}
+
+int nav24_orb_fetch_undistorted(nav24_orb* ctx, float* ud_xy, int cap) {
+    if (!ctx || !ud_xy) return NAV24_E_BADARG;
+    if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results on the device");
+    cudaSetDevice(ctx->device);
+    int rc = check_device_error(ctx);      // synchronises ctx->stream (which joined the other compute streams)
+    if (rc != NAV24_OK) return rc;
+    const int oc = ctx->g.outCap, c = std::min(cap, oc), B = ctx->lastB;
+    if (ctx->cam.model != NAV24_CAM_PINHOLE) {
+        CK(cudaMemcpy2D(ud_xy, (size_t)cap * 8, ctx->p.outUd, (size_t)oc * 8, (size_t)c * 8, B, cudaMemcpyDeviceToHost));
+    } else {                             // identity: the detected coordinates
+        std::vector<nav24_kp> k((size_t)B * oc);
+        CK(cudaMemcpy(k.data(), ctx->p.outKp, k.size() * sizeof(nav24_kp), cudaMemcpyDeviceToHost));
+        std::vector<int> n(B);
+        CK(cudaMemcpy(n.data(), ctx->p.nOut, (size_t)B * 4, cudaMemcpyDeviceToHost));
+        for (int f = 0; f < B; ++f)
+            for (int i = 0; i < std::min(n[f], c); ++i) {
+                ud_xy[((size_t)f * cap + i) * 2] = k[(size_t)f * oc + i].x;
+                ud_xy[((size_t)f * cap + i) * 2 + 1] = k[(size_t)f * oc + i].y;
+            }
+    }
+    return NAV24_OK;
 }
 
 int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio,

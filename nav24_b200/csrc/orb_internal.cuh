@@ -112,6 +112,7 @@ struct DevPtrs {
     LevelKp* lkp;            // [B][kpPerFrame]
     int* levelCount;         // [B][nlevels] keypoints per level after the quadtree
     int* rawTotal;           // [B][nlevels] raw keys per level
+    float* outUd;            // [B][outCap][2] undistorted keypoint coordinates (camera model != pinhole)
     nav24_kp* outKp;         // [B][outCap]
     uint8_t* outDesc;        // [B][outCap][32]
     int* nOut; int* monoOut; // [B]
@@ -163,5 +164,9 @@ struct MatchArgs {
 int launch_match_window(const MatchArgs& a, int P, cudaStream_t s);
 int launch_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio, int* idx0, int* idx1,
                    float* dist0, float* dist1, uint8_t* pass, cudaStream_t s);
+
+// camera models (camera_kernels.cu): Calibration::undistort on the device
+int launch_undistort_points(const nav24_camera& cam, const float* xy, int n, float* out, cudaStream_t s);
+int launch_undistort_frames(const nav24_camera& cam, const nav24_kp* kps, const int* nOut, int cap, int B, float* ud, cudaStream_t s);
 
 }  // namespace nav24

@@ -16,9 +16,11 @@
 //   OB::MatchedObs      sensorData/observation/MatchedFeatures.hpp    OB::MatchedObs
 //   FrameMonoGrid       dataTypes/frame/Frame.hpp:59-74               FrameMonoGrid (image view instead of ImagePtr)
 //   OB::FeatureGrid cfg sensorData/observation/FeatureGrid.cpp:100    FeatureGridCfg (explicit, not process-global)
+//   Calibration         sensor/camera/Calibration.cpp:135-233         CalibrationB200 (undistort, computeImageBounds)
 //
 // There is no CPU fallback: constructing FtDtOrbB200 without a CUDA device throws std::runtime_error.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -241,6 +243,51 @@ private:
     std::vector<float> mU1, mU2;
     std::vector<uint8_t> mD1, mD2;
 };
+
+}  // namespace OP
+
+// ---- camera -----------------------------------------------------------------------------------------------
+// The part of Calibration the front end runs between detect and matchV (FE_SlamMonoV.cpp:115): undistort every
+// observation and, once per sequence, the image bounds of the feature grid.  distType as in the reference's YAML:
+// "radial-tangential" (cv::undistortPoints), "kannala-brandt8" (cv::fisheye::undistortPoints), anything else = calibrated
+// input, identity (Calibration::isCalibrated, Calibration.cpp:230-233).
+class CalibrationB200 {
+public:
+    CalibrationB200(const std::shared_ptr<OP::FtDtOrbB200>& ctxOwner, const std::string& distType, float fx, float fy, float cx,
+                    float cy, const std::vector<float>& distCoefs = {})
+        : mpOwner(ctxOwner), mDistType(distType) {
+        mCam.model = distType == "radial-tangential" ? NAV24_CAM_RADTAN : distType == "kannala-brandt8" ? NAV24_CAM_KB8 : NAV24_CAM_PINHOLE;
+        mCam.fx = fx; mCam.fy = fy; mCam.cx = cx; mCam.cy = cy;
+        for (int i = 0; i < 4; ++i) mCam.d[i] = i < (int)distCoefs.size() ? distCoefs[i] : 0.f;      // mD_cv is 4x1 (GeometricCamera.h:64)
+    }
+    bool isCalibrated() const { return mCam.model == NAV24_CAM_PINHOLE; }
+    const nav24_camera& camera() const { return mCam; }
+    // Calibration::undistort(vector<ObsPtr>) (Calibration.cpp:135-159): sets every observation's undistorted point
+    std::vector<OB::ObsPtr> undistort(const std::vector<OB::ObsPtr>& vpObs) {
+        const size_t n = vpObs.size();
+        mXY.resize(2 * n);
+        for (size_t i = 0; i < n; ++i) { const OB::Point2f p = vpObs[i]->getPoint(); mXY[2 * i] = p.x; mXY[2 * i + 1] = p.y; }
+        if (n && nav24_undistort_points(mpOwner->handle(), &mCam, mXY.data(), (int)n, mXY.data()) != NAV24_OK)
+            throw std::runtime_error(nav24_last_error_string(mpOwner->handle()));
+        for (size_t i = 0; i < n; ++i) vpObs[i]->setPointUd({mXY[2 * i], mXY[2 * i + 1]});
+        return vpObs;
+    }
+    // Calibration::computeImageBounds (Calibration.cpp:196-228): {minX, maxX, minY, maxY}
+    std::vector<float> computeImageBounds(int cols, int rows) {
+        if (isCalibrated()) return {0.f, (float)cols, 0.f, (float)rows};
+        float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+        if (nav24_undistort_points(mpOwner->handle(), &mCam, c, 4, c) != NAV24_OK)
+            throw std::runtime_error(nav24_last_error_string(mpOwner->handle()));
+        return {std::min(c[0], c[4]), std::max(c[2], c[6]), std::min(c[1], c[3]), std::max(c[5], c[7])};
+    }
+private:
+    std::shared_ptr<OP::FtDtOrbB200> mpOwner;
+    std::string mDistType;
+    nav24_camera mCam{};
+    std::vector<float> mXY;
+};
+
+namespace OP {
 
 // Intended semantics of FtAssocOCV::match (OP_FtAssoc.cpp:63-99): kNN-2 + ratio 0.7, lowest train index wins ties.
 class FtAssocBfB200 {

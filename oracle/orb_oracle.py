@@ -71,6 +71,8 @@ def lib():
                                      C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_match_bf_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_undistort_radtan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_undistort_kb8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -223,3 +225,18 @@ def match_bf_knn2(d1, d2, norm=0, ratio=0.7):
     f0 = np.zeros(n1, np.float32); f1 = np.zeros(n1, np.float32); ps = np.zeros(n1, np.uint8)
     lib().orc_match_bf_knn2(_p(d1), n1, _p(d2), len(d2), norm, ratio, _p(i0), _p(i1), _p(f0), _p(f1), _p(ps))
     return i0, i1, f0, f1, ps
+
+
+CAM_PINHOLE, CAM_RADTAN, CAM_KB8 = 0, 1, 2
+
+
+def undistort(model, K4, D4, xy):
+    """Calibration::undistort restatement: model 0 identity, 1 cv::undistortPoints (RadTan, P = K), 2 cv::fisheye (KB8)."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    if model == CAM_PINHOLE:
+        return xy.copy()
+    K4 = np.ascontiguousarray(K4, np.float32); D4 = np.ascontiguousarray(D4, np.float32)
+    out = np.zeros_like(xy)
+    fn = lib().orc_undistort_radtan if model == CAM_RADTAN else lib().orc_undistort_kb8
+    fn(_p(K4), _p(D4), _p(xy), len(xy), _p(out))
+    return out

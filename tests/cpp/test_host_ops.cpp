@@ -56,6 +56,24 @@ int main(int argc, char** argv) {
     FramePtr empty = std::make_shared<FrameMonoGrid>(0.0, nullptr, 0, 0, 0);
     const int rcEmpty = pOrbDetector->detect(empty);
     std::fwrite(&rcEmpty, 4, 1, fo);
+
+    // the distorted-camera form of the same loop (FE_SlamMonoV.cpp:104-122): detect -> Calibration::undistort ->
+    // grid bounds from the undistorted image corners -> matchV on the undistorted points
+    CalibrationB200 calib(pOrbDetector, "radial-tangential", 458.654f, 457.296f, 367.215f, 248.375f,
+                          {-0.28340811f, 0.07395907f, 0.00019359f, 1.76187114e-05f});
+    const std::vector<float> b = calib.computeImageBounds(w, h);
+    std::fwrite(b.data(), 4, 4, fo);
+    for (int f = 0; f < 2 && f < n; ++f) {
+        calib.undistort(frames[f]->getObservations());
+        for (const auto& o : frames[f]->getObservations()) { const OB::Point2f p = o->getPointUd(); std::fwrite(&p, 4, 2, fo); }
+    }
+    if (n >= 2) {
+        OP::FtAssocB200 udMatcher(pOrbDetector, FeatureGridCfg(w, h, b[0], b[1], b[2], b[3]));
+        const std::vector<int> m = udMatcher.matchV(frames[0], frames[1]);
+        const int n1 = (int)m.size();
+        std::fwrite(&n1, 4, 1, fo);
+        std::fwrite(m.data(), 4, n1, fo);
+    }
     std::fclose(fo);
     return 0;
 }

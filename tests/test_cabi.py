@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 25
     missing = [s for s in syms if not hasattr(L, s)]
     assert not missing, missing
-    assert L.nav24_abi_version() == 1
+    assert L.nav24_abi_version() == 2
 
 
 def test_header_is_plain_c():

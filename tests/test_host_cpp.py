@@ -77,3 +77,20 @@ def test_host_ops_match_oracle(tmp_path, cuda_required, H, W, nf, scale):
             assert np.array_equal(m, mref)
         assert (m >= 0).sum() > 20
     assert int(take(np.int32, 1)[0]) == -1          # empty image -> -1, like the reference
+    # CalibrationB200: bounds, undistorted points and matchV on them against the oracle (RadTan, EuRoC cam0 numbers)
+    K4 = [458.654, 457.296, 367.215, 248.375]; D4 = [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]
+    from nav24_b200 import capi
+    b = take(np.float32, 4)
+    bref = capi.image_bounds(lambda p: oo.undistort(oo.CAM_RADTAN, K4, D4, p), W, H, calibrated=False)
+    assert np.array_equal(b, np.array(bref, np.float32))
+    uds = []
+    for f in range(2):
+        ko = ref[f][0]
+        ud = take(np.float32, 2 * len(ko)).reshape(-1, 2)
+        assert ud.tobytes() == oo.undistort(oo.CAM_RADTAN, K4, D4, np.stack([ko["x"], ko["y"]], 1)).tobytes()
+        uds.append(ud)
+    n1 = int(take(np.int32, 1)[0]); m = take(np.int32, n1)
+    (k1, d1, e1), (k2, d2, e2) = ref[0], ref[1]
+    mref = oo.match_window(k1, uds[0], d1, k2, uds[1], d2, oo.grid_for(W, H, tuple(float(x) for x in b)))
+    if e1 and e2:
+        assert np.array_equal(m, mref)
