@@ -17,6 +17,7 @@
 //   FrameMonoGrid       dataTypes/frame/Frame.hpp:59-74               FrameMonoGrid (image view instead of ImagePtr)
 //   OB::FeatureGrid cfg sensorData/observation/FeatureGrid.cpp:100    FeatureGridCfg (explicit, not process-global)
 //   Calibration         sensor/camera/Calibration.cpp:135-233         CalibrationB200 (undistort, computeImageBounds)
+//   vector<ObsPtr>      OP_FtDtOrbSlam.cpp:925-931, Point2D.hpp:37-69 OB::ObservationStore (struct of arrays, same accessors)
 //
 // There is no CPU fallback: constructing FtDtOrbB200 without a CUDA device throws std::runtime_error.
 #pragma once
@@ -57,6 +58,44 @@ private:
 };
 typedef std::shared_ptr<KeyPoint2D> ObsPtr;
 
+// Struct-of-arrays observation store.  The reference materialises every keypoint as a
+// make_shared<KeyPoint2D> holding a cloned 1x32 cv::Mat (OP_FtDtOrbSlam.cpp:925-931, Point2D.hpp:39-40): N small
+// allocations per frame, which dominate the host time once detection runs on the GPU.  The store keeps the three
+// arrays the C ABI reads and writes (nav24_kp, 32-byte descriptors, undistorted points) and hands out per-observation
+// views with KeyPoint2D's accessors, so detect writes into it and undistort / matchV read it without any copy.
+class ObservationStore {
+public:
+    class View {      // the accessors of OB::KeyPoint2D on element i
+    public:
+        View(const ObservationStore* s, size_t i) : mS(s), mI(i) {}
+        const nav24_kp& getKeyPoint() const { return mS->mKps[mI]; }
+        const uint8_t* getDescriptor() const { return &mS->mDesc[32 * mI]; }
+        Point2f getPoint() const { return {mS->mKps[mI].x, mS->mKps[mI].y}; }
+        Point2f getPointUd() const { return {mS->mUd[2 * mI], mS->mUd[2 * mI + 1]}; }
+    private:
+        const ObservationStore* mS; size_t mI;
+    };
+    size_t size() const { return mN; }
+    View operator[](size_t i) const { return View(this, i); }
+    void reserve(size_t cap) { if (mKps.size() < cap) { mKps.resize(cap); mDesc.resize(32 * cap); mUd.resize(2 * cap); } }
+    void setSize(size_t n) {      // after the detector filled keypoints(): undistorted point = detected point (Point2D ctor)
+        mN = n;
+        for (size_t i = 0; i < n; ++i) { mUd[2 * i] = mKps[i].x; mUd[2 * i + 1] = mKps[i].y; }
+    }
+    nav24_kp* keypoints() { return mKps.data(); }
+    const nav24_kp* keypoints() const { return mKps.data(); }
+    uint8_t* descriptors() { return mDesc.data(); }
+    const uint8_t* descriptors() const { return mDesc.data(); }
+    float* pointsUd() { return mUd.data(); }
+    const float* pointsUd() const { return mUd.data(); }
+private:
+    size_t mN = 0;
+    std::vector<nav24_kp> mKps;
+    std::vector<uint8_t> mDesc;
+    std::vector<float> mUd;
+};
+typedef std::shared_ptr<ObservationStore> ObsStorePtr;
+
 }  // namespace OB
 
 class FrameMonoGrid;
@@ -90,6 +129,8 @@ public:
     size_t stride() const { return mStride; }
     const std::vector<OB::ObsPtr>& getObservations() const { return mvpObservations; }
     void setObservations(const std::vector<OB::ObsPtr>& v) { mvpObservations = v; }
+    const OB::ObsStorePtr& getObservationStore() const { return mpStore; }      // struct-of-arrays form (detectSoA)
+    void setObservationStore(const OB::ObsStorePtr& s) { mpStore = s; }
     void setMatches(const OB::MatchedObsPtr& m) { mpMatches12 = m; }
     OB::MatchedObsPtr getMatches() const { return mpMatches12; }
 private:
@@ -98,6 +139,7 @@ private:
     int mW, mH;
     size_t mStride;
     std::vector<OB::ObsPtr> mvpObservations;
+    OB::ObsStorePtr mpStore;
     OB::MatchedObsPtr mpMatches12;
 };
 
@@ -155,6 +197,26 @@ public:
         return rc;      // monoIndex
     }
 
+    // Same contract as detect(), but the frame receives a struct-of-arrays OB::ObservationStore that the library
+    // writes directly (no per-keypoint allocation; the store of a recycled frame is reused).
+    int detectSoA(FramePtr& pFrame) {
+        if (!pFrame || !pFrame->image() || pFrame->width() <= 0 || pFrame->height() <= 0) return -1;
+        OB::ObsStorePtr st = pFrame->getObservationStore();
+        if (!st) { st = std::make_shared<OB::ObservationStore>(); pFrame->setObservationStore(st); }
+        int cap = nav24_orb_max_keypoints(mCtx), n = 0;
+        st->reserve(cap);
+        int rc = nav24_orb_detect(mCtx, pFrame->image(), pFrame->width(), pFrame->height(), pFrame->stride(), st->keypoints(),
+                                  st->descriptors(), cap, &n);
+        if (rc == NAV24_E_CAPACITY) {
+            cap = n; st->reserve(cap);
+            rc = nav24_orb_detect(mCtx, pFrame->image(), pFrame->width(), pFrame->height(), pFrame->stride(), st->keypoints(),
+                                  st->descriptors(), cap, &n);
+        }
+        if (rc < 0) { st->setSize(0); mLastError = nav24_last_error_string(mCtx); return rc == NAV24_E_BADARG ? -1 : rc; }
+        st->setSize(n);
+        return rc;      // monoIndex
+    }
+
     int GetLevels() const { return mnLevels; }
     float GetScaleFactor() const { return mvScaleFactor.size() > 1 ? mvScaleFactor[1] : 1.f; }
     const std::vector<float>& GetScaleFactors() const { return mvScaleFactor; }
@@ -199,6 +261,17 @@ public:
     // frame 2; {} if a frame is missing (the reference returns {} + LOG(WARNING) when f2 has no grid, :103-107).
     std::vector<int> matchV(const FramePtr& pFrame1, const FramePtr& pFrame2) override {
         if (!pFrame1 || !pFrame2) return {};
+        if (pFrame1->getObservationStore() && pFrame2->getObservationStore()) {      // struct-of-arrays frames: no packing
+            const OB::ObservationStore& s1 = *pFrame1->getObservationStore();
+            const OB::ObservationStore& s2 = *pFrame2->getObservationStore();
+            std::vector<int> m12(s1.size(), -1);
+            if (s1.size() == 0) return m12;
+            const int rcS = nav24_match_window(mpOwner->handle(), s1.keypoints(), s1.pointsUd(), s1.descriptors(), (int)s1.size(),
+                                               s2.keypoints(), s2.pointsUd(), s2.descriptors(), (int)s2.size(), &mGrid, windowSize,
+                                               mfNNratio, TH_LOW, mbCheckOrientation ? 1 : 0, m12.data());
+            if (rcS < 0) return {};
+            return m12;
+        }
         const auto& o1 = pFrame1->getObservations();
         const auto& o2 = pFrame2->getObservations();
         const int n1 = (int)o1.size(), n2 = (int)o2.size();
@@ -271,6 +344,14 @@ public:
             throw std::runtime_error(nav24_last_error_string(mpOwner->handle()));
         for (size_t i = 0; i < n; ++i) vpObs[i]->setPointUd({mXY[2 * i], mXY[2 * i + 1]});
         return vpObs;
+    }
+    // the struct-of-arrays form: undistorted points written in place into the store
+    void undistort(OB::ObservationStore& st) {
+        const size_t n = st.size();
+        mXY.resize(2 * n);
+        for (size_t i = 0; i < n; ++i) { mXY[2 * i] = st.keypoints()[i].x; mXY[2 * i + 1] = st.keypoints()[i].y; }
+        if (n && nav24_undistort_points(mpOwner->handle(), &mCam, mXY.data(), (int)n, st.pointsUd()) != NAV24_OK)
+            throw std::runtime_error(nav24_last_error_string(mpOwner->handle()));
     }
     // Calibration::computeImageBounds (Calibration.cpp:196-228): {minX, maxX, minY, maxY}
     std::vector<float> computeImageBounds(int cols, int rows) {

@@ -3,6 +3,7 @@
 // FtAssoc::match(firstFrame, currFrame); with scaleNumFeatures(5.f) before the first frame like initOperators (:247).
 // Input : raw file  [int32 n, h, w, nFeatures] + n*h*w bytes.   Output: raw file read back by tests/test_host_cpp.py
 //         per frame: int32 monoIndex, int32 nObs, nObs*(nav24_kp 28 B), nObs*32 B; then per frame>0: int32 n1, n1*int32.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -74,6 +75,53 @@ int main(int argc, char** argv) {
         std::fwrite(&n1, 4, 1, fo);
         std::fwrite(m.data(), 4, n1, fo);
     }
+    // struct-of-arrays observation store: same detector, undistortion and matcher, no per-keypoint
+    // allocation; results must equal the object form above.  Host time of both forms is printed for the record.
+    int soaOk = 1;
+    {
+        std::vector<FramePtr> soa;
+        for (int f = 0; f < n; ++f) {
+            FramePtr pFrame = std::make_shared<FrameMonoGrid>(f * 0.05, img.data() + (size_t)f * h * w, w, h, (size_t)w);
+            pOrbDetector->detectSoA(pFrame);
+            calib.undistort(*pFrame->getObservationStore());
+            soa.push_back(pFrame);
+            const auto& obs = frames[f]->getObservations();
+            const OB::ObservationStore& st = *pFrame->getObservationStore();
+            if (st.size() != obs.size()) soaOk = 0;
+            for (size_t i = 0; i < st.size() && soaOk; ++i) {
+                if (std::memcmp(&st[i].getKeyPoint(), &obs[i]->getKeyPoint(), sizeof(nav24_kp)) != 0) soaOk = 0;
+                if (std::memcmp(st[i].getDescriptor(), obs[i]->getDescriptor().data(), 32) != 0) soaOk = 0;
+                if (f < 2 && (st[i].getPointUd().x != obs[i]->getPointUd().x || st[i].getPointUd().y != obs[i]->getPointUd().y)) soaOk = 0;
+            }
+        }
+        if (n >= 2) {
+            OP::FtAssocB200 udMatcher(pOrbDetector, FeatureGridCfg(w, h, b[0], b[1], b[2], b[3]));
+            if (udMatcher.matchV(soa[0], soa[1]) != udMatcher.matchV(frames[0], frames[1])) soaOk = 0;
+        }
+        // host-side materialisation cost per frame, object form vs store (the device work is identical)
+        const int reps = 200;
+        const OB::ObservationStore& st0 = *soa[0]->getObservationStore();
+        auto t0 = std::chrono::steady_clock::now();
+        size_t sink = 0;
+        for (int r = 0; r < reps; ++r) {
+            std::vector<OB::ObsPtr> v(st0.size());
+            for (size_t i = 0; i < st0.size(); ++i) v[i] = std::make_shared<OB::KeyPoint2D>(st0.keypoints()[i], st0.descriptors() + 32 * i);
+            sink += v.size();
+        }
+        auto t1 = std::chrono::steady_clock::now();
+        OB::ObservationStore tmp; tmp.reserve(st0.size());
+        for (int r = 0; r < reps; ++r) {
+            std::memcpy(tmp.keypoints(), st0.keypoints(), st0.size() * sizeof(nav24_kp));
+            std::memcpy(tmp.descriptors(), st0.descriptors(), st0.size() * 32);
+            tmp.setSize(st0.size());
+            sink += tmp.size();
+        }
+        auto t2 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[host] %zu keypoints/frame: KeyPoint2D objects %.1f us/frame, ObservationStore %.1f us/frame (%zu)\n",
+                     st0.size(), std::chrono::duration<double, std::micro>(t1 - t0).count() / reps,
+                     std::chrono::duration<double, std::micro>(t2 - t1).count() / reps, sink);
+    }
+    std::fwrite(&soaOk, 4, 1, fo);
     std::fclose(fo);
     return 0;
 }

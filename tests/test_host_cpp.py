@@ -94,3 +94,4 @@ def test_host_ops_match_oracle(tmp_path, cuda_required, H, W, nf, scale):
     mref = oo.match_window(k1, uds[0], d1, k2, uds[1], d2, oo.grid_for(W, H, tuple(float(x) for x in b)))
     if e1 and e2:
         assert np.array_equal(m, mref)
+    assert int(take(np.int32, 1)[0]) == 1           # the struct-of-arrays store gives identical observations and matches
