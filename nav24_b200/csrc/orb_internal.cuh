@@ -124,7 +124,7 @@ struct DevPtrs {
 
 struct TmaMaps { CUtensorMap m[kMaxLevels]; };   // one 3-D (x, y, frame) u8 tensor map per pyramid level
 
-struct FastSmem { int offMap, offMask, offQueue, offWin, total; };   // dynamic shared memory layout of fast_band_kernel
+struct FastSmem { int offMap, offMask, offQueue, total; };   // dynamic shared memory layout of fast_band_kernel
 
 struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;

@@ -4,6 +4,7 @@
 // float work uses explicit round-to-nearest intrinsics so that nvcc cannot contract mul+add
 // into FMA (the reference is built without contraction).
 #include <algorithm>
+#include <cstdlib>
 
 #include "orb_internal.cuh"
 #include "stdsort_warp.cuh"
@@ -254,7 +255,7 @@ __device__ __forceinline__ int mask_range_count(const unsigned* rowp, int x0, in
     return n;
 }
 
-// Dynamic shared memory: [tile | score map | keypoint bit mask | queue u16 | winner list u16], sizes from FastSmem.
+// Dynamic shared memory: [tile | score map | keypoint bit mask | queue u16], sizes from FastSmem.
 // Queue and winner entries are the byte offset of the pixel inside the tile (row * kFastPitch + column).
 __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                                  const __grid_constant__ TmaMaps maps, const FastSmem sm,
@@ -264,7 +265,6 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     uint8_t* smap = s_dyn + sm.offMap;
     unsigned* kmask = reinterpret_cast<unsigned*>(s_dyn + sm.offMask);
     unsigned short* queue = reinterpret_cast<unsigned short*>(s_dyn + sm.offQueue);
-    unsigned short* winners = reinterpret_cast<unsigned short*>(s_dyn + sm.offWin);
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_q, s_nw, s_ovf, s_empty;
     __shared__ int s_off[kFastMaxSegCells];
@@ -333,6 +333,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     const int ngx = sg.ngx, rc = sg.rc;             // stage A work items: (word column, chunk of rc rows), one round
     const int nItems = ngx * sg.nChunks;
     unsigned emptyCells = 0;                         // pass 1: cells without a keypoint at iniTh
+    RawRec* outL = p.raw + (long long)f * g.rawPerFrame + L.rawOff;
+    const int xBase = 3 + sg.cj0 * wCell, yBase = 3 + sg.ci * L.hCell;      // :811-812, relative to (minBorderX, minBorderY)
 
     int th = iniTh;
     for (int pass = 0; pass < 2; ++pass) {
@@ -418,10 +420,27 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                 static_assert(kFastPitch == 256, "row = offset >> 8");
                 const int bi = ((e >> 8) - 3) * (wpr << 5) + xx;
                 atomicOr(&kmask[bi >> 5], 1u << (bi & 31));
-                winners[atomicAdd(&s_nw, 1)] = (unsigned short)e;
+                return true;
             }
+            return false;
         };
-        if (!s_ovf) {
+        // ordered emit of one keypoint: its slot is its rank in the row-major order of its cell (the order cv::FAST
+        // reports) = keypoints of the cell above its row + keypoints of the cell to its left in the row
+        auto emit = [&](int e) {
+            const int row = (e >> 8) - 3, xx = (e & (P - 1)) - c_lo;
+            const int k = (int)__umulhi((unsigned)xx, L.magicW), x0 = k * wCell;
+            int rank = s_rowpre[k][row];
+            if (xx > x0) rank += mask_range_count(kmask + row * wpr, x0, xx);
+            RawRec r;
+            r.x = (unsigned short)(xx + xBase);
+            r.y = (unsigned short)(row + yBase);
+            r.score = smap[e]; r.pad = 0;
+            const int base = s_off[k];
+            if (base >= 0) outL[base + rank] = r;
+        };
+        int wlo = 0, wwin = 0;                       // this warp's keypoints of the pass: queue[wlo, wwin)
+        const bool dense = s_ovf != 0;
+        if (!dense) {
             // stage B: exact score of the survivors.  Each warp owns a contiguous slice of the queue and compacts the
             // pixels that reach the threshold to the front of its slice (no block barrier, no atomics), then runs
             // stage C over them.
@@ -443,7 +462,16 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                 wpos += __popc(m);
             }
             __syncthreads();                                             // the score map is complete
-            for (int qi = lo + lane; qi < wpos; qi += 32) nms(queue[qi]);
+            // stage C over the warp's corners; the keypoints are compacted to the front of the slice the same way
+            wlo = wwin = lo;
+            for (int base = lo; base < wpos; base += 32) {
+                const int qi = base + lane;
+                const int e = qi < wpos ? queue[qi] : 0;
+                const bool win = qi < wpos && nms(e);
+                const unsigned m = __ballot_sync(0xffffffffu, win);
+                if (win) queue[wwin + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
+                wwin += __popc(m);
+            }
         } else {
             // dense path (rare: the survivors of stage A did not fit the queue, e.g. an image of pure noise): score every
             // interior pixel (in pass 2: of the empty cells), then NMS over the score map
@@ -454,12 +482,13 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                     const int s = fast_score(tile + e, P);
                     if (s >= th) smap[e] = (uint8_t)s;
                 }
+            if (tid == 0) s_nw = 0;
             __syncthreads();
             for (int row = 3; row < 3 + ih; ++row)
                 for (int xx = tid; xx < iw; xx += NT) {
                     if (pass && !((emptyCells >> __umulhi((unsigned)xx, L.magicW)) & 1u)) continue;
                     const int e = row * P + c_lo + xx;
-                    if (smap[e]) nms(e);
+                    if (smap[e] && nms(e)) queue[atomicAdd(&s_nw, 1)] = (unsigned short)e;      // (the queue holds >= wcap entries)
                 }
         }
         __syncthreads();
@@ -497,29 +526,18 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
             }
         }
         __syncthreads();
+        // every keypoint of this pass lies in a cell whose count became final in this pass: write them out
+        if (!dense) {
+            for (int qi = wlo + lane; qi < wwin; qi += 32) emit(queue[qi]);
+        } else {
+            const int nw = s_nw;
+            for (int t = tid; t < nw; t += NT) emit(queue[t]);
+        }
         emptyCells = (unsigned)s_empty;
         if (lastPass || emptyCells == 0u) break;
+        __syncthreads();                             // the queue is refilled by the next pass
         if (tid == 0) { s_q = 0; s_ovf = 0; }
         __syncthreads();
-    }
-    RawRec* outL = p.raw + (long long)f * g.rawPerFrame + L.rawOff;
-
-    // ordered emit: a keypoint's slot is its rank in the row-major order of its cell (the order cv::FAST reports) =
-    // keypoints of the cell above its row + keypoints of the cell to its left in the row
-    const int nw = s_nw;
-    const int xBase = 3 + sg.cj0 * wCell, yBase = 3 + sg.ci * L.hCell;      // :811-812, relative to (minBorderX, minBorderY)
-    for (int t = tid; t < nw; t += NT) {
-        const int e = winners[t];
-        const int row = (e >> 8) - 3, xx = (e & (P - 1)) - c_lo;
-        const int k = (int)__umulhi((unsigned)xx, L.magicW), x0 = k * wCell;
-        int rank = s_rowpre[k][row];
-        if (xx > x0) rank += mask_range_count(kmask + row * wpr, x0, xx);
-        RawRec r;
-        r.x = (unsigned short)(xx + xBase);
-        r.y = (unsigned short)(row + yBase);
-        r.score = smap[e]; r.pad = 0;
-        const int base = s_off[k];
-        if (base >= 0) outL[base + rank] = r;
     }
 }
 
@@ -1023,8 +1041,10 @@ __global__ void __launch_bounds__(32) describe_kernel(const __grid_constant__ Fr
     const int lane = threadIdx.x;
     const int slot = blockIdx.x;
     const int f = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && slot >= g.lv[l + 1].kpOff) ++l;
+    int l = 0;                                      // level of the slot: binary search over kpOff (kMaxLevels = 16)
+#pragma unroll
+    for (int step = 8; step > 0; step >>= 1)
+        if (l + step < g.nlevels && slot >= g.lv[l + step].kpOff) l += step;
     const LevelGeom& L = g.lv[l];
     const int i = slot - L.kpOff;
     if (!(slot < g.kpPerFrame && i < p.levelCount[f * g.nlevels + l])) return;      // warp-uniform
@@ -1169,8 +1189,7 @@ int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B
     sm.offMap = tileBytes;
     sm.offMask = 2 * tileBytes;                                               // cleared together with the score map
     sm.offQueue = sm.offMask + (mwords * 4 + 15) / 16 * 16;
-    sm.offWin = sm.offQueue + (qcap * 2 + 15) / 16 * 16;
-    sm.total = sm.offWin + (wcap * 2 + 15) / 16 * 16 + 16;
+    sm.total = sm.offQueue + (max(qcap, wcap) * 2 + 15) / 16 * 16 + 16;      // (the dense path lists its keypoints in the queue)
     static int attrSet = 0;
     if (sm.total > attrSet) {
         cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
@@ -1219,7 +1238,9 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
         attr_done = true;
     }
     dim3 grid(g.nlevels, B);
-    quadtree_kernel<<<grid, 256, smem, s>>>(g, p, cap);
+    static int qtThreads = 0;
+    if (!qtThreads) { const char* e = getenv("NAV24_QT_THREADS"); qtThreads = e ? atoi(e) : 256; if (qtThreads < 32 || qtThreads > 256 || (qtThreads & 31)) qtThreads = 256; }
+    quadtree_kernel<<<grid, qtThreads, smem, s>>>(g, p, cap);
     order_kernel<<<B, 256, 0, s>>>(g, p);
     return 2;
 }

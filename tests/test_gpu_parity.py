@@ -25,6 +25,7 @@ CASES = [  # H, W, nFeatures, seed, lowtex
     (480, 640, 1000, 7, False),       # config 3 (TUM)
     (260, 340, 300, 5, True),         # near the minimum size
     (300, 900, 700, 9, False),        # 3:1 panorama, nIni = 3
+    (2160, 3840, 8000, 24, False),    # config 4 (4K stress): 108 x 60 cells at level 0, 18 FAST segments per cell row
 ]
 
 
