@@ -509,11 +509,8 @@ int launch_match_window(const MatchArgs& a, int P, cudaStream_t s) {
     const int capR = (a.cap + 3) & ~3;
     if ((1 + kAccSlots) * capR <= budget - used) { sm.acc = capR; used += (1 + kAccSlots) * capR; }
     sm.total = used * 4;
-    static int attrSet = 0;
-    if (sm.total > attrSet) {
-        cudaFuncSetAttribute(match_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
-        attrSet = max(sm.total, 48 * 1024);
-    }
+    // (function attributes are per device and this library serves several devices and host threads: set on every launch)
+    cudaFuncSetAttribute(match_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
     match_window_kernel<<<P, 1024, sm.total, s>>>(a, sm);
     return 1;
 }

@@ -1154,12 +1154,9 @@ int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, in
 
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s) {
     int n = 0;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(resize_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(resize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr = true;
-    }
+    // (function attributes are per device and this library serves several devices and host threads: set on every call)
+    cudaFuncSetAttribute(resize_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(resize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& D = g.lv[l];
         const ResizeTab& T = tabs[l];
@@ -1190,11 +1187,7 @@ int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B
     sm.offMask = 2 * tileBytes;                                               // cleared together with the score map
     sm.offQueue = sm.offMask + (mwords * 4 + 15) / 16 * 16;
     sm.total = sm.offQueue + (max(qcap, wcap) * 2 + 15) / 16 * 16 + 16;      // (the dense path lists its keypoints in the queue)
-    static int attrSet = 0;
-    if (sm.total > attrSet) {
-        cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
-        attrSet = max(sm.total, 48 * 1024);
-    }
+    cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
     dim3 grid(g.totalSegs, B);
     fast_band_kernel<<<grid, kFastThreads, sm.total, s>>>(g, p, maps, sm, iniTh, minTh);
     return 1;
@@ -1232,15 +1225,9 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     for (int l = 0; l < g.nlevels; ++l) maxNode = max(maxNode, g.lv[l].nodeCap);
     int cap = (min(maxNode, 12000) + 3) & ~3;      // records sorted in shared memory; larger levels sort in global memory
     size_t smem = quadtree_smem_bytes(cap);
-    static bool attr_done = false;
-    if (smem > 48 * 1024 || !attr_done) {
-        cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
+    cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid(g.nlevels, B);
-    static int qtThreads = 0;
-    if (!qtThreads) { const char* e = getenv("NAV24_QT_THREADS"); qtThreads = e ? atoi(e) : 256; if (qtThreads < 32 || qtThreads > 256 || (qtThreads & 31)) qtThreads = 256; }
-    quadtree_kernel<<<grid, qtThreads, smem, s>>>(g, p, cap);
+    quadtree_kernel<<<grid, 256, smem, s>>>(g, p, cap);      // (128 threads: 5 % faster alone, slower in the chunked host pipeline)
     order_kernel<<<B, 256, 0, s>>>(g, p);
     return 2;
 }

@@ -267,6 +267,62 @@ def test_fused_detect_match_chunked(ctxs, monkeypatch):
             ctx.close()
 
 
+def test_batch_schedule_invariance_at_bench_scale(ctxs, monkeypatch):
+    """A bench-sized batch (96 KITTI frames, 48 stereo pairs + pairs that span chunks): the result must not depend on
+    how the host pipeline cuts it (tapered chunks on three streams vs one uniform chunk), and sampled frames / pairs
+    must equal the oracle."""
+    import threading
+    H, W, nf = 376, 1241, 2000
+    fr = sequence(H, W, 31, 96, step=(5, 1))
+    pairs = [(2 * i, 2 * i + 1) for i in range(48)] + [(0, 95), (7, 40), (30, 31)]
+    res = {}
+    for name, env in (("taper", {"NAV24_CHUNK_FRAMES": "16", "NAV24_STREAMS": "3", "NAV24_TAPER": "1"}),
+                      ("uniform", {"NAV24_CHUNK_FRAMES": "96", "NAV24_STREAMS": "1", "NAV24_TAPER": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = capi.OrbContext(nf)
+        try:
+            res[name] = ctx.detect_match_batch(fr, pairs, capi.grid_for(W, H))
+        finally:
+            ctx.close()
+    (n, mono, kps, desc, m, nm), (n2, mono2, kps2, desc2, m2, nm2) = res["taper"], res["uniform"]
+    assert np.array_equal(n, n2) and np.array_equal(mono, mono2) and np.array_equal(nm, nm2)
+    for f in range(len(fr)):
+        assert kps[f, :n[f]].tobytes() == kps2[f, :n[f]].tobytes() and np.array_equal(desc[f, :n[f]], desc2[f, :n[f]])
+    for q, (a, b) in enumerate(pairs):
+        assert np.array_equal(m[q, :n[a]], m2[q, :n[a]])
+    o = oo.OrbOracle(nf)
+    ref = {f: o.detect(fr[f]) for f in (0, 7, 40, 95)}
+    for f, (mo, ko, do) in ref.items():
+        assert mono[f] == mo and kps[f, :n[f]].tobytes() == ko.tobytes()
+    for q, (a, b) in ((48, (0, 95)), (49, (7, 40))):
+        (_, k1, d1), (_, k2, d2) = ref[a], ref[b]
+        if np.array_equal(desc[a, :n[a]], d1) and np.array_equal(desc[b, :n[b]], d2):
+            mref = oo.match_window(k1, np.stack([k1["x"], k1["y"]], 1), d1, k2, np.stack([k2["x"], k2["y"]], 1), d2, oo.grid_for(W, H))
+            assert np.array_equal(m[q, :n[a]], mref)
+
+    # two contexts driven from two host threads at once (bench.py's e2e loop) give the same answers
+    out = [None, None]
+
+    def work(i):
+        c = capi.OrbContext(nf)
+        try:
+            for _ in range(2):
+                out[i] = c.detect_match_batch(fr[:32], pairs[:16], capi.grid_for(W, H))
+        finally:
+            c.close()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for i in range(2):
+        ni, _, ki, di, mi, nmi = out[i]
+        assert np.array_equal(ni, n[:32]) and np.array_equal(nmi, nm[:16])
+        for f in range(32):
+            assert ki[f, :ni[f]].tobytes() == kps[f, :n[f]].tobytes() and np.array_equal(di[f, :ni[f]], desc[f, :n[f]])
+
+
 def test_warp_sort_equals_std_sort(ctxs):
     """The warp-parallel introsort must leave the exact permutation libstdc++'s std::sort leaves (ties included)."""
     ctx = _ctx(ctxs, 1000)
