@@ -1027,117 +1027,162 @@ __device__ const PatternT kPatternT = make_pattern_t();
 // bytes inside the disc (0 outside), (y) their 0/1 mask.  m10 = sum dp4a(word, x), m01 = sum v * dp4a(word, y).
 // Built once per context on the host (capi.cu: build_orientation_table) from umax[] (OP_FtDtOrbSlam.cpp:484-499).
 //
-// One warp per CTA (measured on B200, 256 KITTI frames: 16 warps per CTA 0.80 ms, 4: 0.60, 1: 0.48 — a CTA holds its
-// resources until its slowest warp's gathers return).  Both patches of the keypoint — 31 rows of the un-blurred level
-// for the moments, 37 rows of the blurred level for the 512 samples — arrive in shared memory as two TMA boxes
-// (x start rounded down to 16 bytes, hence the 48- and 64-byte box widths): no per-thread address arithmetic, no
-// register staging, and the gathers index a power-of-two row pitch.
-__global__ void __launch_bounds__(32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
-                                                      const __grid_constant__ TmaMaps mapsOri,
-                                                      const __grid_constant__ TmaMaps mapsBlur) {
-    __shared__ __align__(128) uint8_t s_blur[kDescBoxW * kDescBoxH];
-    __shared__ __align__(128) uint8_t s_ori[kOriBoxW * kOriBoxH];
-    __shared__ __align__(8) unsigned long long bar;
-    const int lane = threadIdx.x;
-    const int slot = blockIdx.x;
+// A warp walks kDescSlots consecutive keypoint slots of one frame (warps never synchronise with each other: the first
+// multi-warp version of this kernel was slower because a CTA held its resources until its slowest warp finished; here
+// every warp has the same amount of work).  Both patches of a keypoint — 31 rows of the un-blurred level for the
+// moments, 37 rows of the blurred level for the 512 samples — arrive in shared memory as two TMA boxes (x start rounded
+// down to 16 bytes, hence the 48- and 64-byte box widths): no per-thread address arithmetic, no register staging, and
+// the gathers index a power-of-two row pitch.  The boxes are double-buffered: while keypoint k is computed the boxes
+// of keypoint k+1 are in flight and the LevelKp record of keypoint k+2 is being loaded.
+constexpr int kDescWarps = 4;                  // warps per CTA
+constexpr int kDescSlots = 16;                 // keypoint slots per warp
+constexpr int kDescOriOff = (kDescBoxW * kDescBoxH + 127) / 128 * 128;      // TMA destinations are 128-byte aligned
+constexpr int kDescStage = (kDescOriOff + kOriBoxW * kOriBoxH + 127) / 128 * 128;      // bytes per stage
+
+__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+                                                                   const __grid_constant__ TmaMaps mapsOri,
+                                                                   const __grid_constant__ TmaMaps mapsBlur) {
+    __shared__ __align__(128) uint8_t s_buf[kDescWarps][2][kDescStage];
+    __shared__ __align__(8) unsigned long long s_bar[kDescWarps][2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int f = blockIdx.y;
-    int l = 0;                                      // level of the slot: binary search over kpOff (kMaxLevels = 16)
-#pragma unroll
-    for (int step = 8; step > 0; step >>= 1)
-        if (l + step < g.nlevels && slot >= g.lv[l + step].kpOff) l += step;
-    const LevelGeom& L = g.lv[l];
-    const int i = slot - L.kpOff;
-    if (!(slot < g.kpPerFrame && i < p.levelCount[f * g.nlevels + l])) return;      // warp-uniform
-    LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + slot;
-    const int cx = kp->x, cy = kp->y;
-    const int xo = (cx - 15) & ~15, xb = (cx - 18) & ~15;
-    const unsigned barAddr = smem_u32(&bar);
+    const int slot0 = (blockIdx.x * kDescWarps + wid) * kDescSlots;
+    const int slotEnd = min(slot0 + kDescSlots, g.kpPerFrame);
+    if (slot0 >= slotEnd) return;
+    // lane j holds the slot range of level j: [kpOff, kpOff + count)
+    const int myOff = lane < g.nlevels ? g.lv[lane].kpOff : 0x7fffffff;
+    const int myCnt = lane < g.nlevels ? p.levelCount[f * g.nlevels + lane] : 0;
+    const LevelKp* lkp = p.lkp + (long long)f * g.kpPerFrame;
+    // next live slot >= s (and its level), or slotEnd: the dead slots are the tail of every level's range
+    auto next_live = [&](int s, int& l) {
+        while (s < slotEnd) {
+            const unsigned below = __ballot_sync(0xffffffffu, myOff <= s);      // levels that start at or before s
+            l = 31 - __clz(below);
+            const int off = __shfl_sync(0xffffffffu, myOff, l), cnt = __shfl_sync(0xffffffffu, myCnt, l);
+            if (s - off < cnt) return s;
+            s = l + 1 < g.nlevels ? __shfl_sync(0xffffffffu, myOff, l + 1) : slotEnd;      // skip to the next level
+        }
+        return slotEnd;
+    };
+    const unsigned bar0 = smem_u32(&s_bar[wid][0]);
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr),
+    }
+    __syncwarp();
+    // lane 0: both boxes of the keypoint at level l, level coordinates (cx, cy) -> stage st
+    auto issue = [&](int l, int cx, int cy, int st) {
+        const unsigned bar = bar0 + 8 * st, dst = smem_u32(&s_buf[wid][st][0]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
                      "r"((unsigned)(kDescBoxW * kDescBoxH + kOriBoxW * kOriBoxH))
                      : "memory");
         asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                smem_u32(s_ori)),
-            "l"(&mapsOri.m[l]), "r"(xo), "r"(cy - 15), "r"(f + p.frameBase), "r"(barAddr)
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+            "l"(&mapsBlur.m[l]), "r"((cx - 18) & ~15), "r"(cy - 18), "r"(f + p.frameBase), "r"(bar)
             : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                smem_u32(s_blur)),
-            "l"(&mapsBlur.m[l]), "r"(xb), "r"(cy - 18), "r"(f + p.frameBase), "r"(barAddr)
+                dst + kDescOriOff),
+            "l"(&mapsOri.m[l]), "r"((cx - 15) & ~15), "r"(cy - 15), "r"(f + p.frameBase), "r"(bar)
             : "memory");
-    }
-    // while the patches are in flight: this lane's orientation weights and rBRIEF pattern entries
-    const int off = (cx - 15) - xo;                                  // 0..15
-    const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279;
-    uint2 wt[9];
-    int widx[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int idx = min(k * 32 + lane, 278);
-        const int r = (idx * 57) >> 9, c = idx - r * 9;             // idx / 9 for idx < 288
-        wt[k] = __ldg(tab + idx);
-        widx[k] = r * (kOriBoxW / 4) + (off >> 2) + c;
-    }
-    __syncwarp();
-    {
-        unsigned done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done)
-                : "r"(barAddr), "r"(0u)
-                : "memory");
-        }
-    }
-    // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane)
-    const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori);
-    int m10 = 0, m01 = 0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int idx = k * 32 + lane;
-        if (idx < 279) {
-            const int r = (idx * 57) >> 9;
-            const unsigned w = ow[widx[k]];
-            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[k].x));      // u8 pixels x s8 offsets
-            m01 += (r - 15) * (int)__dp4a(w, wt[k].y, 0u);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-    const float factorPI = (float)(3.14159265358979323846 / 180.f);
-    float b, a;
-    sincosf(__fmul_rn(angle, factorPI), &b, &a);
-
-    // computeOrbDescriptor: the 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38)
-    const uint8_t* pc = s_blur + 18 * kDescBoxW + 18 + ((cx - 18) - xb);      // the keypoint
+    };
+    // (keeping the lane's eight test pairs in registers across keypoints was measured slower: 96 registers per thread
+    // cost more in occupancy than the 32 L1 wavefronts per keypoint cost in the load pipe)
     const float4* pat = reinterpret_cast<const float4*>(kPatternT.v) + lane;
-    unsigned val = 0;
+
+    int lCur = 0, lNext = 0, lNext2 = 0;
+    int sCur = next_live(slot0, lCur);
+    if (sCur >= slotEnd) return;
+    unsigned kpCur = *reinterpret_cast<const unsigned*>(lkp + sCur);                // x | y << 16
+    int sNext = next_live(sCur + 1, lNext);
+    unsigned kpNext = sNext < slotEnd ? *reinterpret_cast<const unsigned*>(lkp + sNext) : 0u;
+    if (lane == 0) issue(lCur, (int)(kpCur & 0xffffu), (int)(kpCur >> 16), 0);
+    unsigned phase = 0;                                                             // bit st: parity of stage st's next wait
+    for (int st = 0; sCur < slotEnd; st ^= 1) {
+        // prefetch: boxes of the next keypoint, record of the one after it
+        if (sNext < slotEnd && lane == 0) issue(lNext, (int)(kpNext & 0xffffu), (int)(kpNext >> 16), st ^ 1);
+        const int sNext2 = sNext < slotEnd ? next_live(sNext + 1, lNext2) : slotEnd;
+        const unsigned kpNext2 = sNext2 < slotEnd ? *reinterpret_cast<const unsigned*>(lkp + sNext2) : 0u;
+
+        const int l = lCur, cx = (int)(kpCur & 0xffffu), cy = (int)(kpCur >> 16);
+        const LevelGeom& L = g.lv[l];
+        const uint8_t* s_blur = &s_buf[wid][st][0];
+        const uint8_t* s_ori = s_blur + kDescOriOff;
+        // this lane's orientation weights while the boxes land
+        const int off = (cx - 15) & 15;                                            // 0..15
+        const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279;
+        uint2 wt[9];
+        int widx[9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 q4 = __ldg(pat + j * 32);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q4.x, b), __fmul_rn(q4.y, a)));
-        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q4.x, a), __fmul_rn(q4.y, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q4.z, b), __fmul_rn(q4.w, a)));
-        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q4.z, a), __fmul_rn(q4.w, b)));
-        const int t0 = pc[r0 * kDescBoxW + q0], t1 = pc[r1 * kDescBoxW + q1];
-        val |= (unsigned)(t0 < t1) << j;
-    }
-    const int dst = kp->dst;
-    p.outDesc[((long long)f * g.outCap + dst) * 32 + lane] = (uint8_t)val;
-    if (lane == 0) {
-        kp->angle = angle;
-        nav24_kp o;
-        o.x = l ? __fmul_rn((float)cx, L.scale) : (float)cx;
-        o.y = l ? __fmul_rn((float)cy, L.scale) : (float)cy;
-        o.size = L.patch; o.angle = angle; o.response = (float)kp->score; o.octave = l; o.class_id = -1;
-        p.outKp[(long long)f * g.outCap + dst] = o;
+        for (int k = 0; k < 9; ++k) {
+            const int idx = min(k * 32 + lane, 278);
+            const int r = (idx * 57) >> 9, c = idx - r * 9;             // idx / 9 for idx < 288
+            wt[k] = __ldg(tab + idx);
+            widx[k] = r * (kOriBoxW / 4) + (off >> 2) + c;
+        }
+        {
+            unsigned done = 0;
+            const unsigned bar = bar0 + 8 * st, par = (phase >> st) & 1u;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar), "r"(par)
+                    : "memory");
+            }
+            phase ^= 1u << st;
+        }
+        // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane)
+        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori);
+        int m10 = 0, m01 = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int idx = k * 32 + lane;
+            if (idx < 279) {
+                const int r = (idx * 57) >> 9;
+                const unsigned w = ow[widx[k]];
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[k].x));      // u8 pixels x s8 offsets
+                m01 += (r - 15) * (int)__dp4a(w, wt[k].y, 0u);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        float b, a;
+        sincosf(__fmul_rn(angle, factorPI), &b, &a);
+
+        // computeOrbDescriptor: the 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38)
+        const uint8_t* pc = s_blur + 18 * kDescBoxW + 18 + ((cx - 18) & 15);      // the keypoint
+        unsigned val = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q4 = __ldg(pat + j * 32);
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q4.x, b), __fmul_rn(q4.y, a)));
+            const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q4.x, a), __fmul_rn(q4.y, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q4.z, b), __fmul_rn(q4.w, a)));
+            const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q4.z, a), __fmul_rn(q4.w, b)));
+            const int t0 = pc[r0 * kDescBoxW + q0], t1 = pc[r1 * kDescBoxW + q1];
+            val |= (unsigned)(t0 < t1) << j;
+        }
+        LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + sCur;
+        const int dst = kp->dst;
+        p.outDesc[((long long)f * g.outCap + dst) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            kp->angle = angle;
+            nav24_kp o;
+            o.x = l ? __fmul_rn((float)cx, L.scale) : (float)cx;
+            o.y = l ? __fmul_rn((float)cy, L.scale) : (float)cy;
+            o.size = L.patch; o.angle = angle; o.response = (float)kp->score; o.octave = l; o.class_id = -1;
+            p.outKp[(long long)f * g.outCap + dst] = o;
+        }
+        __syncwarp();                               // every lane is done with stage st before it is refilled
+        sCur = sNext; lCur = lNext; kpCur = kpNext;
+        sNext = sNext2; lNext = lNext2; kpNext = kpNext2;
     }
 }
 
@@ -1240,8 +1285,8 @@ int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlu
         blur_kernel<<<grid, 128, 0, s>>>(g, p, mapsBlurSrc);
         ++n;
     }
-    dim3 grid(g.kpPerFrame, B);
-    describe_kernel<<<grid, 32, 0, s>>>(g, p, mapsOri, mapsBlur);
+    dim3 grid((g.kpPerFrame + kDescWarps * kDescSlots - 1) / (kDescWarps * kDescSlots), B);
+    describe_kernel<<<grid, kDescWarps * 32, 0, s>>>(g, p, mapsOri, mapsBlur);
     return n + 1;
 }
 
