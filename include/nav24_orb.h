@@ -206,6 +206,8 @@ int nav24_orb_fetch_undistorted(nav24_orb* ctx, float* ud_xy, int cap);
 int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm,
                         float ratio, int32_t* idx0, int32_t* idx1, float* dist0, float* dist1, uint8_t* pass);
 
+/* Device time (CUDA events) of the kernels of the last nav24_match_bf_knn2 call, for tools/bench_bf.py. */
+int nav24_debug_last_kernel_ms(nav24_orb* ctx, float* ms);
 /* Test hook for the quadtree's "largest first" ordering (std::sort at OP_FtDtOrbSlam.cpp:646, comparator :358-373):
  * sorts n records by key with the device restatement of libstdc++'s introsort and returns the permutation
  * (perm[i] = original index of the record at sorted position i).  Equal keys are "equivalent": their order is

@@ -105,6 +105,7 @@ def lib():
     L.nav24_orb_fetch_undistorted.argtypes = [vp, vp, C.c_int]
     L.nav24_match_bf_knn2.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp]
     L.nav24_debug_sort_u32.argtypes = [vp, vp, C.c_int, vp]
+    L.nav24_debug_last_kernel_ms.argtypes = [vp, vp]
     L.nav24_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.nav24_host_free.argtypes = [vp]
     L.nav24_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]

@@ -1303,9 +1303,12 @@ int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(ctx->mD1.ptr, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
     if (n2) CK(cudaMemcpyAsync(ctx->mD2.ptr, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    CK(ctx->bUdTmp.ensure((size_t)bf_knn2_segments(n1, n2) * n1 * sizeof(int4)));      // (scratch shared with nav24_undistort_points)
+    CK(cudaEventRecord(ctx->evT[0], s));
     ctx->launches += launch_bf_knn2((const uint8_t*)ctx->mD1.ptr, n1, (const uint8_t*)ctx->mD2.ptr, n2, norm, ratio,
                                     (int*)ctx->mI0.ptr, (int*)ctx->mI1.ptr, (float*)ctx->mF0.ptr, (float*)ctx->mF1.ptr,
-                                    (uint8_t*)ctx->mPass.ptr, s);
+                                    (uint8_t*)ctx->mPass.ptr, (int4*)ctx->bUdTmp.ptr, s);
+    CK(cudaEventRecord(ctx->evT[1], s));      // nav24_debug_last_kernel_ms: device time of the two kernels
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(idx0, ctx->mI0.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(idx1, ctx->mI1.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
@@ -1316,6 +1319,14 @@ int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t
     int np = 0;
     for (int i = 0; i < n1; ++i) np += pass[i];
     return np;
+}
+
+int nav24_debug_last_kernel_ms(nav24_orb* ctx, float* ms) {
+    if (!ctx || !ms) return NAV24_E_BADARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventSynchronize(ctx->evT[1]));
+    CK(cudaEventElapsedTime(ms, ctx->evT[0], ctx->evT[1]));
+    return NAV24_OK;
 }
 
 int nav24_debug_sort_u32(nav24_orb* ctx, const uint32_t* keys, int n, int32_t* perm) {

@@ -3,6 +3,8 @@
 //   window matcher  : FtAssocOrbSlam::matchV  core/operators/objAssoc/OP_FtAssocOrbSlam.cpp:91-223
 //                     + FeatureGrid           core/sensorData/observation/FeatureGrid.cpp:20-152
 //   brute force     : intended semantics of FtAssocOCV::match  core/operators/objAssoc/OP_FtAssoc.cpp:63-99
+#include <algorithm>
+
 #include "orb_internal.cuh"
 
 namespace nav24 {
@@ -447,16 +449,20 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
 // tiles (every thread reads the same address -> broadcast).  Strict '<' keeps the lowest train
 // index on ties, like cv::BFMatcher.
 // ------------------------------------------------------------------------------------------
+// The train set is cut into gridDim.y segments so that a 2000 x 2000 problem fills the GPU (16 query blocks alone would
+// use 16 of 148 SMs); every (query, segment) writes its best two as (d0, j0, d1, j1) and bf_merge_kernel folds the
+// segments.  "Best two" of the sequential scan = the two smallest (distance, index) pairs in lexicographic order (strict
+// '<' keeps the earlier index on ties), so merging per-segment results in that order is exact.
 __global__ void __launch_bounds__(128) bf_knn2_kernel(const uint4* __restrict__ d1, int n1, const uint4* __restrict__ d2,
-                                                      int n2, int norm, float ratio, int* idx0, int* idx1, float* dist0,
-                                                      float* dist1, uint8_t* pass) {
+                                                      int n2, int norm, int segLen, int4* __restrict__ part) {
     __shared__ uint4 s_t[128 * 2];
     const int q = blockIdx.x * 128 + threadIdx.x;
     uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
     if (q < n1) { qa = d1[2 * q]; qb = d1[2 * q + 1]; }
     int b0 = 0x7fffffff, b1 = 0x7fffffff, j0 = -1, j1 = -1;
-    for (int base = 0; base < n2; base += 128) {
-        const int nt = min(128, n2 - base);
+    const int segBeg = blockIdx.y * segLen, segEnd = min(segBeg + segLen, n2);
+    for (int base = segBeg; base < segEnd; base += 128) {
+        const int nt = min(128, segEnd - base);
         __syncthreads();
         for (int k = threadIdx.x; k < nt * 2; k += 128) s_t[k] = d2[2 * base + k];
         __syncthreads();
@@ -483,13 +489,29 @@ __global__ void __launch_bounds__(128) bf_knn2_kernel(const uint4* __restrict__ 
             else if (d < b1) { b1 = d; j1 = j; }
         }
     }
-    if (q < n1) {
-        idx0[q] = j0; idx1[q] = j1;
-        const float f0 = j0 < 0 ? 0.f : (norm == NAV24_NORM_HAMMING ? (float)b0 : __fsqrt_rn((float)b0));
-        const float f1 = j1 < 0 ? 0.f : (norm == NAV24_NORM_HAMMING ? (float)b1 : __fsqrt_rn((float)b1));
-        dist0[q] = f0; dist1[q] = f1;
-        pass[q] = (j0 >= 0 && j1 >= 0 && f0 < __fmul_rn(ratio, f1)) ? 1 : 0;
+    if (q < n1) part[(size_t)blockIdx.y * n1 + q] = make_int4(b0, j0, b1, j1);
+}
+
+// folds the segments of one query in ascending train order (so equal distances keep the earlier index), then applies
+// the ratio test of FtAssocOCV::match (OP_FtAssoc.cpp:73-85)
+__global__ void __launch_bounds__(128) bf_merge_kernel(const int4* __restrict__ part, int n1, int nSeg, int norm, float ratio,
+                                                       int* idx0, int* idx1, float* dist0, float* dist1, uint8_t* pass) {
+    const int q = blockIdx.x * 128 + threadIdx.x;
+    if (q >= n1) return;
+    int b0 = 0x7fffffff, b1 = 0x7fffffff, j0 = -1, j1 = -1;
+    for (int sgm = 0; sgm < nSeg; ++sgm) {
+        const int4 c = part[(size_t)sgm * n1 + q];
+        if (c.y >= 0) {
+            if (c.x < b0) { b1 = b0; j1 = j0; b0 = c.x; j0 = c.y; }
+            else if (c.x < b1) { b1 = c.x; j1 = c.y; }
+        }
+        if (c.w >= 0 && c.z < b1) { b1 = c.z; j1 = c.w; }
     }
+    idx0[q] = j0; idx1[q] = j1;
+    const float f0 = j0 < 0 ? 0.f : (norm == NAV24_NORM_HAMMING ? (float)b0 : __fsqrt_rn((float)b0));
+    const float f1 = j1 < 0 ? 0.f : (norm == NAV24_NORM_HAMMING ? (float)b1 : __fsqrt_rn((float)b1));
+    dist0[q] = f0; dist1[q] = f1;
+    pass[q] = (j0 >= 0 && j1 >= 0 && f0 < __fmul_rn(ratio, f1)) ? 1 : 0;
 }
 
 }  // namespace
@@ -515,11 +537,21 @@ int launch_match_window(const MatchArgs& a, int P, cudaStream_t s) {
     return 1;
 }
 
+int bf_knn2_segments(int n1, int n2) {      // train segments such that query blocks x segments cover the 148 SMs about twice
+    const int qb = (n1 + 127) / 128;
+    const int want = (2 * 148 + qb - 1) / qb;
+    return std::max(1, std::min(want, (n2 + 127) / 128));
+}
+
 int launch_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio, int* idx0, int* idx1,
-                   float* dist0, float* dist1, uint8_t* pass, cudaStream_t s) {
-    bf_knn2_kernel<<<(n1 + 127) / 128, 128, 0, s>>>(reinterpret_cast<const uint4*>(d1), n1, reinterpret_cast<const uint4*>(d2),
-                                                    n2, norm, ratio, idx0, idx1, dist0, dist1, pass);
-    return 1;
+                   float* dist0, float* dist1, uint8_t* pass, int4* part, cudaStream_t s) {
+    const int nSeg = bf_knn2_segments(n1, n2);
+    const int segLen = std::max(128, ((n2 + nSeg - 1) / nSeg + 127) / 128 * 128);
+    dim3 grid((n1 + 127) / 128, nSeg);
+    bf_knn2_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const uint4*>(d1), n1, reinterpret_cast<const uint4*>(d2), n2, norm,
+                                        segLen, part);
+    bf_merge_kernel<<<(n1 + 127) / 128, 128, 0, s>>>(part, n1, nSeg, norm, ratio, idx0, idx1, dist0, dist1, pass);
+    return 2;
 }
 
 }  // namespace nav24

@@ -162,8 +162,9 @@ struct MatchArgs {
     int* matches12; int* nMatches;
 };
 int launch_match_window(const MatchArgs& a, int P, cudaStream_t s);
+int bf_knn2_segments(int n1, int n2);      // rows of the [segments][n1] int4 scratch launch_bf_knn2 needs
 int launch_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio, int* idx0, int* idx1,
-                   float* dist0, float* dist1, uint8_t* pass, cudaStream_t s);
+                   float* dist0, float* dist1, uint8_t* pass, int4* part, cudaStream_t s);
 
 // camera models (camera_kernels.cu): Calibration::undistort on the device
 int launch_undistort_points(const nav24_camera& cam, const float* xy, int n, float* out, cudaStream_t s);
