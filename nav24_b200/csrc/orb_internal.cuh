@@ -16,7 +16,7 @@ constexpr int kBlurCtaRows = 4 * kBlurTileRows;     // rows per CTA tile (four w
 constexpr int kBlurBoxW = 160, kBlurBoxH = kBlurCtaRows + 6;   // TMA box: 128 px + 16-byte aligned halos, 3 halo rows each side
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
 constexpr int kOriBoxW = 48, kOriBoxH = 31;    // TMA box of the orientation patch: 31 px + <= 15 px of alignment slack, 16-B multiple
-constexpr int kDescBoxW = 64, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px + <= 15 px of alignment slack
+constexpr int kDescBoxW = 80, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px + <= 15 px of alignment slack = 52 -> 64 would do, but a 20-word row pitch spreads the hot central columns over all 32 banks (16 words: 5.2 wavefronts per gather)
 constexpr int kFastThreads = 256;   // threads per CTA of fast_band_kernel
 constexpr int kFastMaxSegCells = 8; // cells of one FAST segment (TMA boxes are <= 256 px wide, cells >= 35 px)
 constexpr int kFastQueueCap = 3072; // stage A survivors one CTA queues (typ. 700 of 8400 pixels); beyond: the dense path
