@@ -274,17 +274,24 @@ def main():
         return nn, nmt
 
     def run_e2e(n_steps):
+        errs = []
+
         def work(c):
-            for i in range(c, n_steps, n_ctx):
-                step_e2e(c, i)
+            try:
+                for i in range(c, n_steps, n_ctx):
+                    step_e2e(c, i)
+            except BaseException as e:      # a failed call must fail the bench, not shorten the timed region
+                errs.append(e)
         if n_ctx == 1:
             work(0)
-            return
-        ths = [threading.Thread(target=work, args=(c,)) for c in range(n_ctx)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
+        else:
+            ths = [threading.Thread(target=work, args=(c,)) for c in range(n_ctx)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        if errs:
+            raise errs[0]
 
     run_e2e(max(args.warmup, n_ctx))
     barrier()

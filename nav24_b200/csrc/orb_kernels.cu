@@ -155,39 +155,53 @@ __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUt
                 : "memory");
         }
     }
-    // phase 1 (bytes beyond the source image are zero-filled by TMA; their taps weigh 0)
+    // phase 1 (bytes beyond the source image are zero-filled by TMA; their taps weigh 0).  The first ten rows are always
+    // needed at scale 1.2 and computed without a test (a row too many only fills a strip slot nobody reads; the tile is
+    // followed by the strips, so the read stays inside the CTA's shared memory); PRMT / MAD.HI are written as PTX because
+    // the intrinsics re-mask the selector per use and split the multiply-high from its addend.
+    auto hrow = [&](int i) {
+        const unsigned* wp = reinterpret_cast<const unsigned*>(rp + i * BOXW);
+        const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+        uint4 h;
+        unsigned t;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[0])); h.x = __dp2a_lo(ab[0], t, 0u) >> 4;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[1])); h.y = __dp2a_lo(ab[1], t, 0u) >> 4;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[2])); h.z = __dp2a_lo(ab[2], t, 0u) >> 4;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[3])); h.w = __dp2a_lo(ab[3], t, 0u) >> 4;
+        sH[i * 32] = h;
+    };
+    constexpr int kAlways = 10;
 #pragma unroll
-    for (int i = 0; i < kResizeSrcRows; ++i) {
-        if (i < nsrc) {                                    // warp-uniform
-            const unsigned* wp = reinterpret_cast<const unsigned*>(rp + i * BOXW);
-            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
-            const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
-            uint4 h;
-            h.x = __dp2a_lo(ab[0], __byte_perm(lo, hi, sel[0]), 0u) >> 4;
-            h.y = __dp2a_lo(ab[1], __byte_perm(lo, hi, sel[1]), 0u) >> 4;
-            h.z = __dp2a_lo(ab[2], __byte_perm(lo, hi, sel[2]), 0u) >> 4;
-            h.w = __dp2a_lo(ab[3], __byte_perm(lo, hi, sel[3]), 0u) >> 4;
-            sH[i * 32] = h;
-        }
-    }
+    for (int i = 0; i < kAlways; ++i) hrow(i);
+#pragma unroll
+    for (int i = kAlways; i < kResizeSrcRows; ++i)
+        if (i < nsrc) hrow(i);                             // warp-uniform
     __syncwarp();
     // phase 2
     uint8_t* dp = dst + (long long)blockIdx.z * dFrame + (long long)y0 * dPitch + x4;
+    auto vrow = [&](int j) {
+        const int i0 = yo[j] - syBase;
+        const uint4 top = sH[i0 * 32], bot = sH[i0 * 32 + 32];
+        const unsigned c0 = yc[j] << 16, c1 = yc[j] & 0xffff0000u;
+        // ((b0*top + 0x20000) >> 16) + ((b1*bot) >> 16)  ==  umulhi(top, b0 << 16) + 2 + umulhi(bot, b1 << 16)
+        unsigned v0, v1, v2, v3;
+        const unsigned two = 2u;
+        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v0) : "r"(top.x), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v0) : "r"(bot.x), "r"(c1));
+        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v1) : "r"(top.y), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v1) : "r"(bot.y), "r"(c1));
+        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v2) : "r"(top.z), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v2) : "r"(bot.z), "r"(c1));
+        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v3) : "r"(top.w), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v3) : "r"(bot.w), "r"(c1));
+        const unsigned out = __byte_perm(__byte_perm(v0 >> 2, v1 >> 2, 0x0040), __byte_perm(v2 >> 2, v3 >> 2, 0x0040), 0x5410);
+        if (active) *reinterpret_cast<unsigned*>(dp) = out;
+        dp += dPitch;
+    };
+    if (nrows == kResizeDstRows) {                         // warp-uniform: every tile but the bottom one
 #pragma unroll
-    for (int j = 0; j < kResizeDstRows; ++j) {
-        if (j < nrows) {                                   // warp-uniform
-            const int i0 = yo[j] - syBase;
-            const uint4 top = sH[i0 * 32], bot = sH[i0 * 32 + 32];
-            const unsigned c0 = yc[j] << 16, c1 = yc[j] & 0xffff0000u;
-            // ((b0*top + 0x20000) >> 16) + ((b1*bot) >> 16)  ==  umulhi(top, b0 << 16) + 2 + umulhi(bot, b1 << 16)
-            const unsigned v0 = (__umulhi(top.x, c0) + 2u + __umulhi(bot.x, c1)) >> 2;
-            const unsigned v1 = (__umulhi(top.y, c0) + 2u + __umulhi(bot.y, c1)) >> 2;
-            const unsigned v2 = (__umulhi(top.z, c0) + 2u + __umulhi(bot.z, c1)) >> 2;
-            const unsigned v3 = (__umulhi(top.w, c0) + 2u + __umulhi(bot.w, c1)) >> 2;
-            const unsigned out = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
-            if (active) *reinterpret_cast<unsigned*>(dp) = out;
-            dp += dPitch;
-        }
+        for (int j = 0; j < kResizeDstRows; ++j) vrow(j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kResizeDstRows; ++j)
+            if (j < nrows) vrow(j);
     }
 }
 
