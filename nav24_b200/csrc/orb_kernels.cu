@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     const int ngx = sg.ngx, rc = sg.rc;             // stage A work items: (word column, chunk of rc rows), one round
     const int nItems = ngx * sg.nChunks;
     unsigned emptyCells = 0;                         // pass 1: cells without a keypoint at iniTh
+    const unsigned sqAddr = smem_u32(&s_q), qAddr = smem_u32(queue);
     RawRec* outL = p.raw + (long long)f * g.rawPerFrame + L.rawOff;
     const int xBase = 3 + sg.cj0 * wCell, yBase = 3 + sg.ci * L.hCell;      // :811-812, relative to (minBorderX, minBorderY)
 
@@ -390,14 +391,16 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                              gt_any2(__vabsdiffu4(__byte_perm(Lw, C, 0x4321), C),                                    \
                                      __vabsdiffu4(__byte_perm(C, Rw, 0x6543), C), kk);                               \
                 }                                                                                                    \
-                if (alive) {                                                                                         \
-                    int pos = atomicAdd(&s_q, __popc(alive));                                                        \
+                if (alive) {      /* (PTX: the C++ atomicAdd drags in the compiler's warp-aggregation path and */    \
+                    unsigned pos;     /* generic-address set-up, 40 instructions per row instead of 16) */              \
+                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos) : "r"(sqAddr), "r"(__popc(alive)) : "memory"); \
                     const unsigned e = (unsigned)(tp - tile);                                                        \
                     if (pos + 4 <= kFastQueueCap) {      /* else: s_q > cap -> the dense path below */                \
-                        if (alive & 0x80u) queue[pos++] = (unsigned short)e;                                         \
-                        if (alive & 0x8000u) queue[pos++] = (unsigned short)(e + 1);                                 \
-                        if (alive & 0x800000u) queue[pos++] = (unsigned short)(e + 2);                               \
-                        if (alive & 0x80000000u) queue[pos] = (unsigned short)(e + 3);                               \
+                        unsigned qa = qAddr + 2u * pos;                                                              \
+                        if (alive & 0x80u) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "r"(e) : "memory"); qa += 2u; }        \
+                        if (alive & 0x8000u) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "r"(e + 1u) : "memory"); qa += 2u; } \
+                        if (alive & 0x800000u) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "r"(e + 2u) : "memory"); qa += 2u; } \
+                        if (alive & 0x80000000u) asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "r"(e + 3u) : "memory");           \
                     } else {                                                                                         \
                         s_ovf = 1;                                                                                   \
                     }                                                                                                \
