@@ -967,32 +967,41 @@ __global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ Frame
     // word 0 of the lane's window (pixels x4-4 .. x4-1) in the row that enters the ring first (image row y0 - 3)
     const uint8_t* rp = tile + (y0 - rowBase) * P + 12 + lane * 4;
     unsigned hr[7][4];
-    for (int yy = y0 - 6; yy < yEnd; yy += 7) {
+    // one row enters the 7-row window: horizontal sums of tile row *rp into ring slot (s + 6) % 7
+    auto hstep = [&](int s) {
+        const unsigned w0 = *reinterpret_cast<const unsigned*>(rp), w1 = *reinterpret_cast<const unsigned*>(rp + 4),
+                       w2 = *reinterpret_cast<const unsigned*>(rp + 8);
+        rp += P;
+        unsigned* o = hr[(s + 6) % 7];
+        const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
+        o[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
+        o[1] = __dp4a(__byte_perm(w0, w1, 0x5432), K1, __dp4a(__byte_perm(w1, w2, 0x5432), K2, 0u));
+        o[2] = __dp4a(__byte_perm(w0, w1, 0x6543), K1, __dp4a(__byte_perm(w1, w2, 0x6543), K2, 0u));
+        o[3] = __dp4a(w1, K1, __dp4a(w2, K2, 0u));
+    };
+    // the output row whose window ends with the row that just entered slot (s + 6) % 7
+    auto vstep = [&](int s) {
+        unsigned v[4];
 #pragma unroll
-        for (int s = 0; s < 7; ++s) {
-            const int y = yy + s;                   // output row; the row entering the window is y + 3
-            if (y >= yEnd) break;                   // uniform
-            const unsigned w0 = *reinterpret_cast<const unsigned*>(rp), w1 = *reinterpret_cast<const unsigned*>(rp + 4),
-                           w2 = *reinterpret_cast<const unsigned*>(rp + 8);
-            rp += P;
-            unsigned* o = hr[(s + 6) % 7];
-            const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
-            o[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
-            o[1] = __dp4a(__byte_perm(w0, w1, 0x5432), K1, __dp4a(__byte_perm(w1, w2, 0x5432), K2, 0u));
-            o[2] = __dp4a(__byte_perm(w0, w1, 0x6543), K1, __dp4a(__byte_perm(w1, w2, 0x6543), K2, 0u));
-            o[3] = __dp4a(w1, K1, __dp4a(w2, K2, 0u));
-            if (y >= y0) {                          // uniform: the first six rows only fill the window
-                unsigned v[4];
+        for (int i = 0; i < 4; ++i)
+            v[i] = 18u * (hr[s % 7][i] + hr[(s + 6) % 7][i]) + (34u * (hr[(s + 1) % 7][i] + hr[(s + 5) % 7][i]) +
+                   (48u * (hr[(s + 2) % 7][i] + hr[(s + 4) % 7][i]) + (56u * hr[(s + 3) % 7][i] + half)));
+        const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+        if (active) *reinterpret_cast<unsigned*>(dp) = word;
+        dp += dPitch;
+    };
+    // six rows fill the window, then every row emits; full groups of seven rows run without any per-row test
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    v[i] = 18u * (hr[s % 7][i] + hr[(s + 6) % 7][i]) + (34u * (hr[(s + 1) % 7][i] + hr[(s + 5) % 7][i]) +
-                           (48u * (hr[(s + 2) % 7][i] + hr[(s + 4) % 7][i]) + (56u * hr[(s + 3) % 7][i] + half)));
-                const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
-                if (active) *reinterpret_cast<unsigned*>(dp) = word;
-                dp += dPitch;
-            }
-        }
+    for (int s = 0; s < 6; ++s) hstep(s);
+    const int nrows = yEnd - y0;
+    int done = 0;
+    for (; done + 7 <= nrows; done += 7) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { hstep((k + 6) % 7); vstep((k + 6) % 7); }
     }
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if (done + k < nrows) { hstep((k + 6) % 7); vstep((k + 6) % 7); }      // uniform: the bottom tile of a level
 }
 
 // ------------------------------------------------------------------------------------------
