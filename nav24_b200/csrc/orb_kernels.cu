@@ -1116,6 +1116,14 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
     // (keeping the lane's eight test pairs in registers across keypoints was measured slower: 96 registers per thread
     // cost more in occupancy than the 32 L1 wavefronts per keypoint cost in the load pipe)
     const float4* pat = reinterpret_cast<const float4*>(kPatternT.v) + lane;
+    int wpos[9], wrow[9];                       // orientation: word k*32+lane of the 31 x 9-word patch -> (tile word, v)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int idx = min(k * 32 + lane, 278);
+        const int r = (idx * 57) >> 9, c = idx - r * 9;             // idx / 9 for idx < 288
+        wpos[k] = r * (kOriBoxW / 4) + c;
+        wrow[k] = r - 15;
+    }
 
     int lCur = 0, lNext = 0, lNext2 = 0;
     int sCur = next_live(slot0, lCur);
@@ -1137,16 +1145,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         const uint8_t* s_ori = s_blur + kDescOriOff;
         // this lane's orientation weights while the boxes land
         const int off = (cx - 15) & 15;                                            // 0..15
-        const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279;
+        const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279 + lane;
+        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori) + (off >> 2);
         uint2 wt[9];
-        int widx[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int idx = min(k * 32 + lane, 278);
-            const int r = (idx * 57) >> 9, c = idx - r * 9;             // idx / 9 for idx < 288
-            wt[k] = __ldg(tab + idx);
-            widx[k] = r * (kOriBoxW / 4) + (off >> 2) + c;
-        }
+        for (int k = 0; k < 9; ++k) wt[k] = __ldg(tab + min(k * 32, 278 - lane));
         {
             unsigned done = 0;
             const unsigned bar = bar0 + 8 * st, par = (phase >> st) & 1u;
@@ -1159,17 +1162,15 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             }
             phase ^= 1u << st;
         }
-        // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane)
-        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori);
+        // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane;
+        // the lane's word positions and row numbers do not depend on the keypoint: wpos / wrow, set up once per warp)
         int m10 = 0, m01 = 0;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const int idx = k * 32 + lane;
-            if (idx < 279) {
-                const int r = (idx * 57) >> 9;
-                const unsigned w = ow[widx[k]];
+            if (k * 32 + lane < 279) {
+                const unsigned w = ow[wpos[k]];
                 asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[k].x));      // u8 pixels x s8 offsets
-                m01 += (r - 15) * (int)__dp4a(w, wt[k].y, 0u);
+                m01 += wrow[k] * (int)__dp4a(w, wt[k].y, 0u);
             }
         }
 #pragma unroll
