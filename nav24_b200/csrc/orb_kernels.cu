@@ -801,8 +801,8 @@ __global__ void __launch_bounds__(256) quadtree_kernel(const __grid_constant__ F
             const int a = aux[nd];
             if (a >= 0) {
                 const int k = quadrant_of(cur[nd], keys[i].x, keys[i].y);
-                int cidx = a;
-                for (int kk = 0; kk < k; ++kk) cidx += childCnt[nd * 4 + kk] > 0;
+                const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);      // one load instead of k dependent ones
+                const int cidx = a + (k > 0 && cc.x > 0) + (k > 1 && cc.y > 0) + (k > 2 && cc.z > 0);
                 nodeOfKey[i] = C - 1 - cidx;
             } else {
                 nodeOfKey[i] = C + (-a - 1);
