@@ -10,9 +10,9 @@ def find(s):
     return None
 marks = [('fast_score', 'int fast_score('), ('gt_any2', 'unsigned gt_any2('), ('mask_range_count', 'int mask_range_count('),
          ('setup', 'void __launch_bounds__(kFastThreads) fast_band_kernel'), ('stageA', 'for (int pass = 0; pass < 2; ++pass)'),
-         ('flush', 'if (acc) {'), ('nms', 'auto nms = [&]'), ('stageB', 'if (!s_ovf) {'), ('stageC', 'the score map is complete'),
-         ('dense', '// dense path (rare'), ('count', '// keypoints per cell and above each row'), ('emit', 'RawRec* outL = p.raw'),
-         ('end', '// K3  quadtree distribution')]
+         ('nms+emit bodies', 'auto nms = [&]'), ('stageB', 'if (!dense) {'), ('stageC', 'stage C over the warp'),
+         ('dense', '// dense path (rare'), ('count', '// keypoints per cell and above each row'),
+         ('emit', '// every keypoint of this pass lies in a cell'), ('end', '// K3  quadtree distribution')]
 marks = [(n, find(s)) for n, s in marks if find(s)]
 tot = {}
 for line in txt.split('\n'):
