@@ -217,9 +217,13 @@ __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUt
 //   tile   : one TMA box (segment interior + rim), shared by the cells of the segment
 //   stage A: antipodal-pair rejection, 4 pixels per 32-bit op; a thread owns one word column and walks down
 //            its rows with the column's last seven words in registers (the +-3 row taps)
-//   stage B: exact score of the survivors, balanced over the CTA through a queue
-//   stage C: 3x3 NMS (cell-aware) -> bit mask in raster order; per-cell counts by one warp per cell
-//   emit   : one warp per cell, one lane per row; cells of the segment append with ONE global atomic
+//   stage B: exact score of the survivors through a queue (balanced: every warp owns a slice of it and compacts the
+//            pixels that reach the threshold to the front of its slice)
+//   stage C: 3x3 NMS (cell-aware) -> bit mask in raster order, keypoints compacted in the slice again
+//   count  : one warp per cell, one lane per row: keypoints of the cell and above each of its rows; a cell whose
+//            count is final appends to the level's raw list with one global atomic; empty cells are redone at minTh
+//   emit   : every keypoint writes itself at (cell offset + row prefix + keypoints to its left in the row)
+//   A segment whose survivors overflow the queue (pure noise) takes a dense path: score every pixel, NMS over the map.
 // ------------------------------------------------------------------------------------------
 // Score of one pixel.  Ring differences are packed as biased u16x2 lanes (d+256, 256-d) by one IMAD;
 // min over an arc of 9 = min3 of three min3's (VIMNMX3.U16x2); max over the 16 arcs by max3.
