@@ -131,6 +131,28 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's host threads to the cores of the NUMA node its GPU hangs off, BEFORE any pinned buffer is
+    allocated (first touch places the pages there): with 8 ranks per box the host->device copies otherwise cross the
+    socket interconnect.  Returns the node (or None when the topology files are not there)."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU front end on the host cores.  The reference itself cannot be
     built here (needs OpenCV C++, Eigen, glog, g2o — see DESIGN.md), so this is the oracle port."""
@@ -186,6 +208,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the ORB path has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -220,14 +244,14 @@ def main():
         ctx.detect_device(dsets[i % 2], F, W, H, PITCH, PITCH * H)
         ctx.match_window_frames_async(pairs, grid)
 
+    sampler = ClockSampler(local)
+    sampler.start()             # runs through warm-up and the timed region (nvidia-smi needs ~0.1 s to deliver its first line)
     for i in range(args.warmup):
         step_resident(i)
     ctx.sync()
     cap = ctx.max_keypoints()
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     ctx.timer_start()
     for i in range(args.steps):
         step_resident(i)
@@ -340,7 +364,7 @@ def main():
         "config": {"workload": f"KITTI-shaped stereo {W}x{H} pair, {NLEVELS} levels x1.2, {NFEAT} keypoints/image, "
                                "left-right windowed Hamming matching (BASELINE.json configs[1])",
                    "pairs_per_step_per_gpu": P, "frames_per_step_per_gpu": F, "parallelism": f"sequences sharded x{world}, no collective",
-                   "pipeline": "fused detect+match; resident: one launch set per step; host buffers: chunks of <= 64 frames (short first and last chunks), H2D / three compute streams / D2H overlapped, one host synchronisation per call", "e2e_contexts": max(1, args.e2e_contexts),
+                   "pipeline": "fused detect+match; resident: one launch set per step; host buffers: chunks of <= 64 frames (short first and last chunks), H2D / three compute streams / D2H overlapped, one host synchronisation per call", "e2e_contexts": max(1, args.e2e_contexts), "host_numa_node": numa,
                    "l2": f"two input sets alternate; per-step working set {(F * (pix * 2 + H * PITCH)) / 1e6:.0f} MB > 126 MB L2"},
         "stage_ms_per_step": {"pyramid": float(stage[0]) / max(calls, 1), "fast": float(stage[1]) / max(calls, 1),
                               "quadtree_order": float(stage[2]) / max(calls, 1),
@@ -352,6 +376,7 @@ def main():
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)      # the CPU baseline uses every host core, not only the GPU's NUMA node
         cores = host_cores()
         f1, k1, dt1 = cpu_frontend_threads(sets_host[0], 1, 4)
         per_thread = max(1, int(round(12.0 / (dt1 / 4))))
