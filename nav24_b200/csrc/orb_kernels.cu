@@ -577,7 +577,8 @@ __device__ __forceinline__ int quadrant_of(const QNode& n, int x, int y) {
     return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
 }
 
-__global__ void __launch_bounds__(256) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency)
+__global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                        int sortSmemCap) {
     extern __shared__ unsigned long long s_sort[];
     __shared__ int s_scan[33];
@@ -1301,9 +1302,13 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     for (int l = 0; l < g.nlevels; ++l) maxNode = max(maxNode, g.lv[l].nodeCap);
     int cap = (min(maxNode, 12000) + 3) & ~3;      // records sorted in shared memory; larger levels sort in global memory
     size_t smem = quadtree_smem_bytes(cap);
-    cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(quadtree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(quadtree_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid(g.nlevels, B);
-    quadtree_kernel<<<grid, 256, smem, s>>>(g, p, cap);      // (128 threads: 5 % faster alone, slower in the chunked host pipeline)
+    // 256 threads per (level, frame) when the batch fills the GPU (128: 5 % faster alone, slower in the chunked host
+    // pipeline); a small batch (single-camera latency) has few CTAs, so each gets 1024 threads for its parallel passes
+    if (g.nlevels * B < 2 * 148) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, cap);
+    else quadtree_kernel<256><<<grid, 256, smem, s>>>(g, p, cap);
     order_kernel<<<B, 256, 0, s>>>(g, p);
     return 2;
 }
