@@ -88,6 +88,18 @@ def test_blur_right_edge_geometries(ctxs, W):
         assert np.array_equal(ctx.level(0, l), o.level(l)), f"pyramid level {l} of width {W}"
 
 
+GEOMS = [(280, 384), (281, 385), (283, 511), (420, 512), (421, 513), (419, 640), (560, 641), (561, 767), (559, 768),
+         (300, 1024), (287, 1025), (480, 320), (423, 387), (562, 899)]
+
+
+@pytest.mark.parametrize("H,W", GEOMS)
+def test_tile_edge_geometries(ctxs, H, W):
+    """Heights around multiples of the 140-row blur CTA tile / 32-row resize tile and widths around multiples of 128:
+    every stage output of every level against the oracle (the TMA boxes of resize, blur, FAST and describe reach over
+    the image edges there; zero fill, REFLECT_101 patches and the host-computed box sizes must all agree)."""
+    _compare_detect(_ctx(ctxs, 400), synth(H, W, 5000 + H + W, lowtex=(H + W) % 3 == 0), 400)
+
+
 def test_detect_strided_input_and_reuse(ctxs):
     ctx = _ctx(ctxs, 1000)
     big = synth(500, 800, 3)
