@@ -31,7 +31,9 @@ extern "C" {
 #define NAV24_E_BADARG (-1)    /* null pointer / empty image; detect() of the reference returns -1 here too
                                   (OP_FtDtOrbSlam.cpp:851-852) */
 #define NAV24_E_GEOMETRY (-2)  /* image too small: some level has no 35-px FAST cell, or the quadtree has no
-                                  root node (the reference divides by zero there, OP_FtDtOrbSlam.cpp:743-749,505) */
+                                  root node (the reference divides by zero there, OP_FtDtOrbSlam.cpp:743-749,505);
+                                  also a scale factor above ~1.85 (the source tile of 128 destination pixels must
+                                  fit one 256-byte TMA box) or an image side of 8192 px or more */
 #define NAV24_E_CAPACITY (-3)  /* caller's output capacity too small; n_out holds the required size */
 #define NAV24_E_OVERFLOW (-4)  /* an internal device buffer overflowed (raw FAST corners); raise
                                   nav24_orb_params.raw_keys_per_kpx and retry.  Never silently truncates. */

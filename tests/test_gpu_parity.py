@@ -100,6 +100,25 @@ def test_tile_edge_geometries(ctxs, H, W):
     _compare_detect(_ctx(ctxs, 400), synth(H, W, 5000 + H + W, lowtex=(H + W) % 3 == 0), 400)
 
 
+@pytest.mark.parametrize("scale,nlevels,ini,mn", [(1.1, 6, 20, 7), (1.5, 5, 30, 10), (1.33, 4, 12, 5), (1.8, 3, 20, 7)])
+def test_other_pyramid_parameters(scale, nlevels, ini, mn, cuda_required):
+    """Scale factor, level count and FAST thresholds other than the defaults (OP_FtDt.cpp:31-48 reads them from YAML):
+    the resize tile geometry (rows per warp, TMA box sizes) is derived from the scale factor."""
+    img = synth(480, 752, 77)
+    ctx = capi.OrbContext(800, scale_factor=scale, n_levels=nlevels, ini_th_fast=ini, min_th_fast=mn)
+    try:
+        o = oo.OrbOracle(800, scale, nlevels, ini, mn)
+        mono_o, k_o, d_o = o.detect(img)
+        mono_g, k_g, d_g = ctx.detect(img)
+        for l in range(nlevels):
+            assert np.array_equal(ctx.level(0, l), o.level(l)), f"pyramid level {l}"
+            assert np.array_equal(ctx.raw_keys(0, l), o.raw(l)), f"raw FAST keys level {l}"
+        assert mono_g == mono_o and k_g.tobytes() == k_o.tobytes()
+        assert int((d_g != d_o).any(axis=1).sum()) <= DESC_TOL * max(1, len(k_o))
+    finally:
+        ctx.close()
+
+
 def test_detect_strided_input_and_reuse(ctxs):
     ctx = _ctx(ctxs, 1000)
     big = synth(500, 800, 3)
