@@ -354,6 +354,40 @@ def test_batch_schedule_invariance_at_bench_scale(ctxs, monkeypatch):
             assert ki[f, :ni[f]].tobytes() == kps[f, :n[f]].tobytes() and np.array_equal(di[f, :ni[f]], desc[f, :n[f]])
 
 
+def test_two_devices_in_one_process(cuda_required):
+    """One context per GPU inside ONE process (SURVEY 8(b) threading row): both devices give the oracle's answer, also when
+    driven from two host threads at once.  Skipped on a one-GPU box."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    H, W, nf = 376, 1241, 2000
+    fr = sequence(H, W, 11, 6, step=(7, 0))
+    pairs = [(0, 1), (2, 3), (4, 5)]
+    o = oo.OrbOracle(nf)
+    ref = [o.detect(f) for f in fr]
+    out = [None, None]
+
+    def work(dev):
+        c = capi.OrbContext(nf, device=dev)
+        try:
+            for _ in range(3):
+                out[dev] = c.detect_match_batch(fr, pairs, capi.grid_for(W, H))
+        finally:
+            c.close()
+    ths = [threading.Thread(target=work, args=(d,)) for d in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for dev in range(2):
+        n, mono, kps, desc, m, nm = out[dev]
+        for f in range(len(fr)):
+            mo, ko, do = ref[f]
+            assert mono[f] == mo and kps[f, :n[f]].tobytes() == ko.tobytes()
+        assert np.array_equal(out[dev][4], out[0][4]) and np.array_equal(out[dev][5], out[0][5])
+
+
 def test_warp_sort_equals_std_sort(ctxs):
     """The warp-parallel introsort must leave the exact permutation libstdc++'s std::sort leaves (ties included)."""
     ctx = _ctx(ctxs, 1000)
