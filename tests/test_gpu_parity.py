@@ -354,6 +354,32 @@ def test_batch_schedule_invariance_at_bench_scale(ctxs, monkeypatch):
             assert ki[f, :ni[f]].tobytes() == kps[f, :n[f]].tobytes() and np.array_equal(di[f, :ni[f]], desc[f, :n[f]])
 
 
+def test_4k_pair_detect_and_match(cuda_required):
+    """BASELINE.json configs[3] shape: 3840x2160, 8000 keypoints per image, windowed matching of two shifted frames
+    (8008 keypoints per frame, 384 x 216 grid cells)."""
+    H, W, nf = 2160, 3840, 8000
+    fr = sequence(H, W, 24, 2, step=(9, 2))
+    ctx = capi.OrbContext(nf)
+    try:
+        n, mono, kps, desc, m, nm = ctx.detect_match_batch(fr, [(0, 1)], capi.grid_for(W, H))
+        o = oo.OrbOracle(nf)
+        ref = [o.detect(f) for f in fr]
+        exact = True
+        for f in range(2):
+            mo, ko, do = ref[f]
+            assert mono[f] == mo and n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes()
+            bad = int((desc[f, :n[f]] != do).any(axis=1).sum())
+            assert bad <= DESC_TOL * n[f]
+            exact &= bad == 0
+        (_, k1, d1), (_, k2, d2) = ref
+        mref = oo.match_window(k1, np.stack([k1["x"], k1["y"]], 1), d1, k2, np.stack([k2["x"], k2["y"]], 1), d2, oo.grid_for(W, H))
+        assert (mref >= 0).sum() > 200
+        if exact:
+            assert np.array_equal(m[0, :n[0]], mref)
+    finally:
+        ctx.close()
+
+
 def test_two_devices_in_one_process(cuda_required):
     """One context per GPU inside ONE process (SURVEY 8(b) threading row): both devices give the oracle's answer, also when
     driven from two host threads at once.  Skipped on a one-GPU box."""
