@@ -78,6 +78,12 @@ struct nav24_orb {
     FrameGeom g{};
     DevPtrs p{};
     std::vector<ResizeTab> tabs;
+    // single-frame host calls are launch-bound (13 kernels of a few CTAs each): their kernel chain is captured once per
+    // (shape, features, camera, workspace) as a CUDA graph and replayed (NAV24_GRAPH=0 turns it off)
+    int useGraph = 1;
+    cudaGraphExec_t graphExec = nullptr;
+    unsigned long long graphKey = 0, wsGen = 0;
+    long long graphLaunches = 0;
     nav24_camera cam{};       // camera of the fused paths (model 0 = pinhole: identity undistortion)
     TmaMaps maps{};           // FAST segment tiles over the un-blurred levels
     TmaMaps mapsRs{};         // m[l]: resize source tiles over level l-1 (resize_kernel producing level l)
@@ -416,6 +422,7 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
             CK(cudaMemcpy(ctx->bOriTab.ptr, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
         }
         ctx->wsB = (int)b;
+        ctx->wsGen++;      // buffers moved: a captured graph holds stale pointers
         DevPtrs& p = ctx->p;
         p.pyr = (uint8_t*)ctx->bPyr.ptr; p.blur = (uint8_t*)ctx->bBlur.ptr;
         p.cellInfo = (uint2*)ctx->bCell.ptr; p.cellDst = (int*)ctx->bCellDst.ptr; p.rawCount = (int*)ctx->bRawCount.ptr;
@@ -605,7 +612,7 @@ namespace {
 struct MatchPlan;
 int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, size_t stride, size_t frame_stride,
                 const MatchPlan* mp, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
-                int32_t* matches12, int mcap, int* n_matches, int chunkOverride = 0);
+                int32_t* matches12, int mcap, int* n_matches, int chunkOverride = 0, bool timedStages = false);
 }  // namespace
 
 // ==========================================================================================
@@ -634,6 +641,7 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
     for (int i = 0; i < nl; ++i) ctx->invScale[i] = 1.0f / ctx->scale[i];
     ctx->compute_quota(params->n_features);
     if (const char* e = getenv("NAV24_TRACE")) ctx->trace = atoi(e) != 0;
+    if (const char* e = getenv("NAV24_GRAPH")) ctx->useGraph = atoi(e);
     if (ctx->trace) { cudaEventCreate(&ctx->evT0); cudaEventCreate(&ctx->evT1); }
     if (const char* e = getenv("NAV24_CHUNK_FRAMES")) { const int v = atoi(e); if (v > 0) ctx->chunkFrames = v; }
     if (const char* e = getenv("NAV24_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= nav24_orb::kMaxStreams) ctx->nStreams = v; }
@@ -677,6 +685,7 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     for (auto& e : ctx->evT) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->evIn) cudaEventDestroy(e);
     for (auto& e : ctx->evDone) cudaEventDestroy(e);
+    if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->evPrevEnd) cudaEventDestroy(ctx->evPrevEnd);
     if (ctx->evPairs) cudaEventDestroy(ctx->evPairs);
@@ -735,7 +744,7 @@ int nav24_orb_detect_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames,
         ctx->p.l0 = (const uint8_t*)ctx->bL0.ptr; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
     }
     return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
-                       0, nullptr, /*one chunk, one stream, stage events*/ n_frames);
+                       0, nullptr, /*one chunk, one stream, stage events*/ n_frames, /*timedStages*/ true);
 }
 
 int nav24_orb_fetch(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
@@ -770,7 +779,7 @@ struct MatchPlan {
 //                         returns after enqueueing.
 int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, size_t stride, size_t frame_stride,
                 const MatchPlan* mp, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
-                int32_t* matches12, int mcap, int* n_matches, int chunkOverride) {
+                int32_t* matches12, int mcap, int* n_matches, int chunkOverride, bool timedStages) {
     const FrameGeom& g = ctx->g;
     const bool fromHost = hostGray != nullptr;
     const bool tight = fromHost && (stride == (size_t)w) && (B == 1 || frame_stride == stride * (size_t)h);
@@ -857,7 +866,7 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
     }
     ctx->prevSig = sig;
     const int ccap = std::min(cap, g.outCap);
-    const bool stages = nChunks == 1;      // per-stage events only make sense un-overlapped
+    const bool stages = timedStages && nChunks == 1;      // per-stage events: nav24_orb_detect_device only, un-overlapped
     for (int k = 0; k < nChunks; ++k) {
         const int f0 = chunkStart[k], c = chunkStart[k + 1] - f0;
         cudaStream_t cs = ctx->xstream[k % nS];
@@ -872,12 +881,64 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
             }
             CK(cudaEventRecord(ctx->evIn[k], ctx->copyStream));
             CK(cudaStreamWaitEvent(cs, ctx->evIn[k], 0));
-            if (tight)
+        }
+        // one host frame, no matching: replay the captured kernel chain (re-captured when shape, feature count, camera or
+        // the workspace changed)
+        const bool graphed = ctx->useGraph && fromHost && B == 1 && P == 0 && !stages;
+        bool replayed = false;
+        if (graphed) {
+            unsigned long long key = 1469598103934665603ull;
+            for (unsigned long long v : {(unsigned long long)w, (unsigned long long)h, (unsigned long long)ctx->prm.n_features,
+                                         ctx->wsGen, (unsigned long long)ctx->cam.model, (unsigned long long)tight,
+                                         (unsigned long long)(uintptr_t)cs})
+                key = (key ^ v) * 1099511628211ull;
+            unsigned long long camBits = 0;
+            memcpy(&camBits, &ctx->cam.fx, 8); key = (key ^ camBits) * 1099511628211ull;
+            memcpy(&camBits, &ctx->cam.cx, 8); key = (key ^ camBits) * 1099511628211ull;
+            memcpy(&camBits, &ctx->cam.d[0], 8); key = (key ^ camBits) * 1099511628211ull;
+            memcpy(&camBits, &ctx->cam.d[2], 8); key = (key ^ camBits) * 1099511628211ull;
+            if (!ctx->graphExec || key != ctx->graphKey) {
+                if (ctx->graphExec) { cudaGraphExecDestroy(ctx->graphExec); ctx->graphExec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                const long long before = ctx->launches;
+                const cudaError_t eb = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+                if (eb != cudaSuccess && ctx->trace) fprintf(stderr, "[nav24 trace] begin capture failed: %s\n", cudaGetErrorString(eb));
+                if (eb == cudaSuccess) {
+                    if (tight)
+                        ctx->launches += launch_repack((const uint8_t*)ctx->bL0Tight.ptr, w, h, l0, ctx->l0Pitch, 1, cs);
+                    const int prc = run_pipeline(ctx, 0, 1, cs, false);
+                    const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
+                    if (prc == NAV24_OK && ee == cudaSuccess && graph &&
+                        cudaGraphInstantiate(&ctx->graphExec, graph, 0) == cudaSuccess) {
+                        ctx->graphKey = key;
+                        ctx->graphLaunches = ctx->launches - before;
+                    } else {
+                        ctx->graphExec = nullptr;
+                        ctx->useGraph = 0;      // this driver / configuration cannot capture the chain: plain launches from now on
+                        if (ctx->trace) fprintf(stderr, "[nav24 trace] graph capture failed: pipeline rc %d, end-capture %s\n", prc, cudaGetErrorString(ee));
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                } else {
+                    ctx->useGraph = 0;
+                    cudaGetLastError();
+                }
+                ctx->launches = before;
+            }
+            if (ctx->graphExec) {
+                if (ctx->trace) fprintf(stderr, "[nav24 trace] graph replay (%lld kernels)\n", ctx->graphLaunches);
+                CK(cudaGraphLaunch(ctx->graphExec, cs));
+                ctx->launches += ctx->graphLaunches;
+                replayed = true;
+            }
+        }
+        if (!replayed) {
+            if (fromHost && tight)
                 ctx->launches += launch_repack((const uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, w, h,
                                                l0 + (size_t)f0 * ctx->l0Pitch * h, ctx->l0Pitch, c, cs);
+            rc = run_pipeline(ctx, f0, c, cs, stages);
+            if (rc != NAV24_OK) return rc;
         }
-        rc = run_pipeline(ctx, f0, c, cs, stages);
-        if (rc != NAV24_OK) return rc;
         const int np = firstOfChunk[k + 1] - firstOfChunk[k];
         if (np > 0) {
             ma.pairBase = firstOfChunk[k];
