@@ -716,14 +716,12 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
                 sv = sortRec;
                 __syncthreads();
             }
-            if (m <= sortSmemCap) {     // one warp produces std::sort's exact permutation (stdsort_warp.cuh)
-                if (tid < 32) {
-                    unsigned short* sa = reinterpret_cast<unsigned short*>(s_sort + sortSmemCap);
-                    unsigned short* sb = sa + sortSmemCap;
-                    unsigned* bits = reinterpret_cast<unsigned*>(sb + sortSmemCap);
-                    int* stk = reinterpret_cast<int*>(bits + ((sortSmemCap + 31) >> 5));
-                    stdsort::sort_warp(sv, m, sa, sb, bits, stk);
-                }
+            if (m <= sortSmemCap) {     // the CTA produces std::sort's exact permutation (stdsort_warp.cuh)
+                unsigned short* sa = reinterpret_cast<unsigned short*>(s_sort + sortSmemCap);
+                unsigned short* sb = sa + sortSmemCap;
+                unsigned* bits = reinterpret_cast<unsigned*>(sb + sortSmemCap);
+                int* rng = reinterpret_cast<int*>(bits + ((sortSmemCap + 31) >> 5));
+                stdsort::sort_block(sv, m, sa, sb, bits, rng);
             } else if (tid == 0) {
                 stdsort::sort(sv, m);
             }
@@ -1271,20 +1269,25 @@ int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B
 }
 
 // records | two u16 position lists | leaf-start bit mask | range stack  (see stdsort_warp.cuh)
-static size_t quadtree_smem_bytes(int cap) { return (size_t)cap * 12 + (size_t)((cap + 31) / 32) * 4 + 192 * 4 + 16; }
+// records | two u16 position lists | leaf-start bit mask | two range lists of sort_block (>= the 192-int stack of sort_warp)
+static size_t quadtree_smem_bytes(int cap) {
+    return (size_t)cap * 12 + (size_t)((cap + 31) / 32) * 4 + (size_t)std::max(192, 2 * (3 * (cap / 16 + 2) + 1)) * 4 + 16;
+}
 
 // test hook: std::sort of n records (key = high 32 bits) by one warp, in shared memory
 namespace {
-__global__ void __launch_bounds__(32) debug_sort_kernel(unsigned long long* recs, int n, int cap) {
+__global__ void __launch_bounds__(256) debug_sort_kernel(unsigned long long* recs, int n, int cap) {
     extern __shared__ unsigned long long s_rec[];
-    for (int i = threadIdx.x; i < n; i += 32) s_rec[i] = recs[i];
-    __syncwarp();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_rec[i] = recs[i];
+    __syncthreads();
     unsigned short* sa = reinterpret_cast<unsigned short*>(s_rec + cap);
     unsigned short* sb = sa + cap;
     unsigned* bits = reinterpret_cast<unsigned*>(sb + cap);
-    int* stk = reinterpret_cast<int*>(bits + ((cap + 31) >> 5));
-    stdsort::sort_warp(s_rec, n, sa, sb, bits, stk);
-    for (int i = threadIdx.x; i < n; i += 32) recs[i] = s_rec[i];
+    int* scratch = reinterpret_cast<int*>(bits + ((cap + 31) >> 5));
+    if (blockDim.x == 32) stdsort::sort_warp(s_rec, n, sa, sb, bits, scratch);      // one warp, range stack
+    else stdsort::sort_block(s_rec, n, sa, sb, bits, scratch);                      // the CTA, rounds of ranges (quadtree_kernel)
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) recs[i] = s_rec[i];
 }
 }  // namespace
 
@@ -1293,7 +1296,7 @@ int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s) {
     const size_t smem = quadtree_smem_bytes(cap);
     if (smem > 200 * 1024) return -1;
     cudaFuncSetAttribute(debug_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    debug_sort_kernel<<<1, 32, smem, s>>>(d_recs, n, cap);
+    debug_sort_kernel<<<1, (n & 1) ? 32 : 256, smem, s>>>(d_recs, n, cap);      // odd n: the one-warp version, even n: the CTA version
     return 1;
 }
 

@@ -124,5 +124,86 @@ __device__ __forceinline__ void sort_warp(rec_t* v, int n, unsigned short* sa, u
     __syncwarp();
 }
 
+// std::sort(v, v+n) by a whole CTA (blockDim.x a multiple of 32), same permutation again.  The range stack of sort_warp
+// becomes a list of ranges per ROUND: every range longer than 16 is partitioned by one warp (warp_partition works inside
+// the range's own slice of sa / sb), its two halves go to the next round's list or are marked as leaves; rounds are
+// separated by block barriers.  With w warps the critical path is about n + n/2 + n/4 + ... elements instead of
+// n * log2(n / 16).  Scratch: sa, sb >= n entries each; startBits >= (n+31)/32 words; ranges >= 2 * (3 * (n / 16 + 2) + 1)
+// ints.  All threads of the block must call.
+__device__ __forceinline__ int block_sort_range_ints(int n) { return 2 * (3 * (n / 16 + 2) + 1); }
+
+__device__ __forceinline__ void sort_block(rec_t* v, int n, unsigned short* sa, unsigned short* sb, unsigned* startBits,
+                                           int* ranges) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
+    if (n <= 1) return;                                       // (uniform)
+    const int nW = (n + 31) >> 5;
+    const int listInts = 3 * (n / 16 + 2) + 1;                // [count | (first, last, depth) ...]
+    int* cur = ranges;
+    int* nxt = ranges + listInts;
+    for (int w = tid; w < nW; w += nth) startBits[w] = 0u;
+    __syncthreads();
+    if (tid == 0) {
+        nxt[0] = 0;
+        if (n > 16) { cur[0] = 1; cur[1] = 0; cur[2] = n; cur[3] = 2 * floor_log2(n); }
+        else { cur[0] = 0; startBits[0] = 1u; }
+    }
+    __syncthreads();
+    while (cur[0] > 0) {                                      // (uniform: read after a barrier)
+        const int nCur = cur[0];
+        for (int r = wid; r < nCur; r += nw) {
+            const int first = cur[1 + 3 * r], last = cur[2 + 3 * r];
+            int depth = cur[3 + 3 * r];
+            if (depth == 0) {
+                if (lane == 0) { heap_sort(v + first, last - first); atomicOr(&startBits[first >> 5], 1u << (first & 31)); }
+                __syncwarp();
+                continue;
+            }
+            --depth;
+            const int cut = warp_partition(v, first, last, sa + first, sb + first);
+            if (lane == 0) {
+                const int f2[2] = {first, cut}, l2[2] = {cut, last};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int len = l2[c] - f2[c];
+                    if (len > 16) {
+                        const int slot = atomicAdd(&nxt[0], 1);
+                        nxt[1 + 3 * slot] = f2[c]; nxt[2 + 3 * slot] = l2[c]; nxt[3 + 3 * slot] = depth;
+                    } else if (len > 0) {
+                        atomicOr(&startBits[f2[c] >> 5], 1u << (f2[c] & 31));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        { int* t = cur; cur = nxt; nxt = t; }
+        if (tid == 0) nxt[0] = 0;
+        __syncthreads();
+    }
+    // every leaf range is insertion-sorted by one thread
+    for (int w = tid; w < nW; w += nth) {
+        unsigned bits = startBits[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int s = w * 32 + b;
+            int e;
+            if (bits) e = w * 32 + __ffs(bits) - 1;
+            else {
+                int ww = w + 1;
+                while (ww < nW && startBits[ww] == 0u) ++ww;
+                e = ww < nW ? ww * 32 + __ffs(startBits[ww]) - 1 : n;
+            }
+            for (int i = s + 1; i < e; ++i) {
+                const rec_t val = v[i];
+                int j = i - 1;
+                while (j >= s && less(val, v[j])) { v[j + 1] = v[j]; --j; }
+                v[j + 1] = val;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 }  // namespace stdsort
 }  // namespace nav24

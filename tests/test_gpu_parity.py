@@ -418,7 +418,8 @@ def test_warp_sort_equals_std_sort(ctxs):
     """The warp-parallel introsort must leave the exact permutation libstdc++'s std::sort leaves (ties included)."""
     ctx = _ctx(ctxs, 1000)
     rng = np.random.default_rng(2024)
-    sizes = [1, 2, 3, 15, 16, 17, 18, 31, 32, 33, 47, 64, 100, 217, 434, 435, 1000, 1737, 4097, 8687]
+    # odd sizes run the one-warp version, even sizes the whole-CTA version (launch_debug_sort)
+    sizes = [1, 2, 3, 15, 16, 17, 18, 31, 32, 33, 34, 47, 48, 64, 100, 217, 218, 434, 435, 1000, 1737, 1738, 4096, 4097, 8687, 8688]
     for n in sizes:
         for kind in range(6):
             if kind == 0:   cnt = rng.integers(2, 6, n); ulx = rng.integers(0, 40, n) * 31       # tie-heavy, like the quadtree
