@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 H, W, NFEAT, NLEVELS = 376, 1241, 2000, 8
 PITCH = 1280                      # 16-byte aligned row pitch of the device-resident frames
 L2_BYTES = 126e6
-NCU_DRAM_BYTES_PER_FRAME = 874.2e6 / 256     # pyramid + FAST, measured (see roofline.traffic)
+NCU_DRAM_BYTES_PER_FRAME = 870.8e6 / 256     # pyramid + FAST, measured (see roofline.traffic)
 
 
 def level_pixels(h, w, nlevels=8):
@@ -348,8 +348,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "pyramid (resize_kernel x7) + FAST (fast_band_kernel)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the 7 resize launches + the FAST launch from the ncu
-                # --set full capture profiles/r01_v8_ncu_full_summary.md (874.2 MB per 256 frames), scaled to this batch
-                "traffic": NCU_DRAM_BYTES_PER_FRAME * F, "traffic_source": "profiles/r01_v8_ncu_full_summary.md",
+                # --set full capture profiles/r01_v9_ncu_full_summary.md (870.8 MB per 256 frames), scaled to this batch
+                "traffic": NCU_DRAM_BYTES_PER_FRAME * F, "traffic_source": "profiles/r01_v9_ncu_full_summary.md",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_frame * F,
                 "avg_ms_per_step": pf_ms,
                 "timing": "CUDA events on the library's stream around the pyramid and FAST launches, measured in a second pass "
