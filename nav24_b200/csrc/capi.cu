@@ -342,21 +342,17 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         for (int l = 1; l < nl; ++l) {
             ResizeTab& T = ctx->tabs[l];
             T = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l], 0, 0, 0};
-            // warp tile: `rows` destination rows whose source rows fit the strip; CTA tile: 128 x 4*rows destination
-            // pixels; the TMA box over the source level covers the CTA tile (x start rounded down to 16 bytes, and the
-            // three aligned words each thread reads)
+            // warp strip: `rows` destination rows; CTA tile: 128 x 4*rows destination pixels (the level's rows dealt evenly
+            // over the CTA rows); the TMA box over the source level covers the CTA tile (x start rounded down to 16 bytes,
+            // and the three aligned words each thread reads)
             const int* xo = allOfs.data() + oX[l]; const int* yo = allOfs.data() + oY[l];
             const int dw = g.lv[l].w, dh = g.lv[l].h;
-            const double sc = (double)g.lv[l - 1].h / dh;
-            T.rows = std::max(1, std::min(kResizeDstRows, (int)((kResizeSrcRows - 2) / sc)));
+            const int ctaRows = (dh + kResizeCtaRows - 1) / kResizeCtaRows;
+            T.rows = std::max(1, std::min(kResizeMaxRows, ((dh + ctaRows - 1) / ctaRows + 3) / 4));
             int needW = 0, needH = 0;
             for (int x0 = 0; x0 < dw; x0 += 128) {
                 const int xl = std::min(x0 + 127, dw - 1) & ~3;
                 needW = std::max(needW, (xo[xl] & ~3) + 12 - (xo[x0] & ~15));
-            }
-            for (int y0 = 0; y0 < dh; y0 += T.rows) {
-                const int span = yo[std::min(y0 + T.rows - 1, dh - 1)] + 2 - yo[y0];
-                if (span > kResizeSrcRows) return ctx->fail(NAV24_E_GEOMETRY, "scale factor too large for the resize tile");
             }
             for (int y0 = 0; y0 < dh; y0 += 4 * T.rows)
                 needH = std::max(needH, yo[std::min(y0 + 4 * T.rows - 1, dh - 1)] + 2 - yo[y0]);

@@ -128,12 +128,12 @@ struct FastSmem { int offMap, offMask, offQueue, total; };   // dynamic shared m
 
 struct ResizeTab {           // per level >= 1: source offsets and 11-bit coefficient pairs
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;
-    int rows;                // destination rows per warp tile (their source rows fit kResizeSrcRows)
+    int rows;                // destination rows per warp strip (<= kResizeMaxRows)
     int boxW, boxH;          // TMA box over the SOURCE level that covers one CTA tile (128 x 4*rows destination pixels)
 };
 
-constexpr int kResizeSrcRows = 12;     // source rows of one warp tile of resize_kernel
-constexpr int kResizeDstRows = 8;      // destination rows of one warp tile (upper bound)
+constexpr int kResizeMaxRows = 32;     // destination rows of one warp strip of resize_kernel (one lane per row's constants)
+constexpr int kResizeCtaRows = 64;     // target destination rows per CTA (4 warp strips)
 
 // launchers (orb_kernels.cu); each returns the number of kernels launched
 // tight (pitch = w) host-order frames -> 16-byte aligned pitch (TMA needs it); returns 1

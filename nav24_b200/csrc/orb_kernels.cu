@@ -81,36 +81,38 @@ __global__ void __launch_bounds__(256) repack_kernel(const uint8_t* __restrict__
 // K1  pyramid level l-1 -> l.  cv::resize(INTER_LINEAR) on CV_8UC1 = 11-bit fixed-point separable
 // bilinear; replaces ComputePyramid (OP_FtDtOrbSlam.cpp:936-960).
 // One CTA = 128 destination columns x 4*rows destination rows; its source pixels arrive as ONE TMA box (x start rounded
-// down to 16 bytes; the box sizes come from the host, ResizeTab).  One WARP owns `rows` destination rows (8 at scale
-// 1.2), a thread 4 adjacent columns.
-// Phase 1, per SOURCE row of the warp tile (<= kResizeSrcRows): the three aligned words that cover the thread's
-// <= 8-byte source window are shifted to byte 0 (2 SHF), each pixel's two taps are picked by one PRMT (selectors are
-// per-thread constants) and S[s]*a0 + S[s+1]*a1 is one DP2A; the four horizontally interpolated values go to the
-// warp's shared-memory strip as one 16-byte store.
-// Phase 2, per DESTINATION row (statically unrolled; row offset and coefficient pair are warp-uniform loads issued
-// up front): two 16-byte loads from the strip (a thread only ever reads its own columns, shared memory is used for the
-// dynamic ROW index), ((b0*top + 2^17) >> 16) + ((b1*bot) >> 16) as two multiply-highs by the coefficients
-// pre-shifted left by 16, >> 2, pack, one 32-bit store.
+// down to 16 bytes; the box sizes come from the host, ResizeTab).  One WARP walks down `rows` destination rows, a
+// thread owns 4 adjacent columns of every row.  The horizontally interpolated values of the two source rows a
+// destination row blends live in REGISTERS (top / bot): the source row index is monotone in the destination row, so
+// stepping down one destination row either re-uses `bot` as the new `top` (source step 1) or computes both rows
+// (step 2); no shared-memory strip, no dynamic row index — the only shared-memory traffic is the three aligned words
+// per thread and source row.
+//   horizontal, per source row: the three aligned words that cover the thread's <= 8-byte source window are shifted to
+//     byte 0 (2 SHF), each pixel's two taps are picked by one PRMT (selectors are per-thread constants) and
+//     S[s]*a0 + S[s+1]*a1 is one DP2A, >> 4
+//   vertical, per destination row (row offset and coefficient pair are warp-uniform: lane j holds those of row j, one
+//     SHFL each): ((b0*top + 2^17) >> 16) + ((b1*bot) >> 16) as two multiply-highs by the coefficients pre-shifted
+//     left by 16, >> 2, pack, one 32-bit store.
 // ------------------------------------------------------------------------------------------
 template <int BOXW>
 __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUtensorMap srcMap, int frameBase,
                                                      uint8_t* __restrict__ dst, int dPitch, long long dFrame, int dw, int dh,
                                                      ResizeTab t) {
-    extern __shared__ __align__(128) uint8_t s_rs[];       // [boxH][BOXW] source tile | uint4 [4][kResizeSrcRows][32] strips
+    extern __shared__ __align__(128) uint8_t s_rs[];       // [boxH][BOXW] source tile
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint2 s_yt[4][kResizeMaxRows];              // per warp strip: (source row inside the tile, b0 | b1 << 16) per destination row
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int rows = t.rows;
+    const int rows = t.rows;                               // <= kResizeMaxRows (one lane per row of the warp's strip)
     const int x0c = blockIdx.x * 128, y0c = blockIdx.y * 4 * rows;
     const int tileX0 = __ldg(t.xofs + x0c) & ~15, tileY0 = __ldg(t.yofs + y0c);
     const unsigned barAddr = smem_u32(&bar);
-    const unsigned tileBytes = (unsigned)(BOXW * t.boxH);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(tileBytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"((unsigned)(BOXW * t.boxH)) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                 smem_u32(s_rs)),
@@ -120,15 +122,13 @@ __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUt
     const int x4 = x0c + lane * 4;
     const int y0 = y0c + wid * rows;
     if (y0 >= dh) return;                                  // warp-uniform
-    uint4* sH = reinterpret_cast<uint4*>(s_rs + ((tileBytes + 127u) & ~127u)) + wid * (kResizeSrcRows * 32) + lane;
     const int nrows = min(rows, dh - y0);
-    // warp-uniform vertical constants of the tile's destination rows
-    int yo[kResizeDstRows]; unsigned yc[kResizeDstRows];
-#pragma unroll
-    for (int j = 0; j < kResizeDstRows; ++j) {
-        const int y = y0 + min(j, nrows - 1);
-        yo[j] = __ldg(t.yofs + y);
-        yc[j] = __ldg(reinterpret_cast<const unsigned*>(t.yab) + y);      // b0 | b1 << 16, both in [0, 2048]
+    // vertical constants of the strip: lane j stores source row (inside the tile) and coefficient pair of destination
+    // row y0 + j; the row loop reads them back with one broadcast 8-byte load
+    if (lane < nrows) {
+        const int yl = y0 + lane;
+        s_yt[wid][lane] = make_uint2((unsigned)(__ldg(t.yofs + yl) - tileY0),
+                                     __ldg(reinterpret_cast<const unsigned*>(t.yab) + yl));      // b0 | b1 << 16, both in [0, 2048]
     }
     // per-thread horizontal constants
     const bool active = x4 < dw;
@@ -142,9 +142,8 @@ __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUt
         sel[k] = (unsigned)d | ((unsigned)(d + 1) << 4);
         ab[k] = __ldg(reinterpret_cast<const unsigned*>(t.xab) + x);      // (a0, a1) as two u16 (both in [0, 2048])
     }
-    const int syBase = yo[0];
-    const int nsrc = min(yo[kResizeDstRows - 1] + 2 - syBase, kResizeSrcRows);      // warp-uniform (the host sized `rows` for it)
-    const uint8_t* rp = s_rs + (syBase - tileY0) * BOXW + ((s0 & ~3) - tileX0);      // the thread's window in the tile
+    const unsigned rpa = smem_u32(s_rs) + (unsigned)((s0 & ~3) - tileX0);      // the thread's window in tile row 0
+    __syncwarp();
     {
         unsigned done = 0;
         while (!done) {
@@ -155,54 +154,83 @@ __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUt
                 : "memory");
         }
     }
-    // phase 1 (bytes beyond the source image are zero-filled by TMA; their taps weigh 0).  The first ten rows are always
-    // needed at scale 1.2 and computed without a test (a row too many only fills a strip slot nobody reads; the tile is
-    // followed by the strips, so the read stays inside the CTA's shared memory); PRMT / MAD.HI are written as PTX because
-    // the intrinsics re-mask the selector per use and split the multiply-high from its addend.
-    auto hrow = [&](int i) {
-        const unsigned* wp = reinterpret_cast<const unsigned*>(rp + i * BOXW);
-        const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
-        const unsigned lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
-        uint4 h;
-        unsigned t;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[0])); h.x = __dp2a_lo(ab[0], t, 0u) >> 4;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[1])); h.y = __dp2a_lo(ab[1], t, 0u) >> 4;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[2])); h.z = __dp2a_lo(ab[2], t, 0u) >> 4;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(lo), "r"(hi), "r"(sel[3])); h.w = __dp2a_lo(ab[3], t, 0u) >> 4;
-        sH[i * 32] = h;
-    };
-    constexpr int kAlways = 10;
-#pragma unroll
-    for (int i = 0; i < kAlways; ++i) hrow(i);
-#pragma unroll
-    for (int i = kAlways; i < kResizeSrcRows; ++i)
-        if (i < nsrc) hrow(i);                             // warp-uniform
-    __syncwarp();
-    // phase 2
-    uint8_t* dp = dst + (long long)blockIdx.z * dFrame + (long long)y0 * dPitch + x4;
-    auto vrow = [&](int j) {
-        const int i0 = yo[j] - syBase;
-        const uint4 top = sH[i0 * 32], bot = sH[i0 * 32 + 32];
-        const unsigned c0 = yc[j] << 16, c1 = yc[j] & 0xffff0000u;
-        // ((b0*top + 0x20000) >> 16) + ((b1*bot) >> 16)  ==  umulhi(top, b0 << 16) + 2 + umulhi(bot, b1 << 16)
-        unsigned v0, v1, v2, v3;
-        const unsigned two = 2u;
-        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v0) : "r"(top.x), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v0) : "r"(bot.x), "r"(c1));
-        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v1) : "r"(top.y), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v1) : "r"(bot.y), "r"(c1));
-        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v2) : "r"(top.z), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v2) : "r"(bot.z), "r"(c1));
-        asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(v3) : "r"(top.w), "r"(c0), "r"(two)); asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v3) : "r"(bot.w), "r"(c1));
-        const unsigned out = __byte_perm(__byte_perm(v0 >> 2, v1 >> 2, 0x0040), __byte_perm(v2 >> 2, v3 >> 2, 0x0040), 0x5410);
-        if (active) *reinterpret_cast<unsigned*>(dp) = out;
-        dp += dPitch;
-    };
-    if (nrows == kResizeDstRows) {                         // warp-uniform: every tile but the bottom one
-#pragma unroll
-        for (int j = 0; j < kResizeDstRows; ++j) vrow(j);
-    } else {
-#pragma unroll
-        for (int j = 0; j < kResizeDstRows; ++j)
-            if (j < nrows) vrow(j);
+    // horizontal pass of tile row i (bytes beyond the source image are zero-filled by TMA; their taps weigh 0).  PRMT is
+    // written as PTX because the intrinsic re-masks the selector per use; the loads as PTX on a shared-window address so
+    // that the three taps are immediate offsets of one register.
+#define NAV24_HROW(i, h)                                                                                              \
+    {                                                                                                                 \
+        const unsigned a_ = rpa + (unsigned)(i) * (unsigned)BOXW;                                                     \
+        unsigned w0_, w1_, w2_;                                                                                       \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0_) : "r"(a_));                                                \
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1_) : "r"(a_));                                              \
+        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2_) : "r"(a_));                                              \
+        const unsigned lo_ = __funnelshift_r(w0_, w1_, shift), hi_ = __funnelshift_r(w1_, w2_, shift);                \
+        _Pragma("unroll") for (int k = 0; k < 4; ++k) {                                                               \
+            unsigned tt_;                                                                                             \
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(tt_) : "r"(lo_), "r"(hi_), "r"(sel[k]));                            \
+            h[k] = __dp2a_lo(ab[k], tt_, 0u) >> 4;                                                                    \
+        }                                                                                                             \
     }
+    // vertical pass of one destination row: ((b0*T + 0x20000) >> 16) + ((b1*B) >> 16) == umulhi(T, b0 << 16) + umulhi(B,
+    // b1 << 16) + 2 (multiply-highs without addend: the fused form wants a 64-bit addend register pair per use), >> 2
+    // on two pixels per register, bytes 0 and 2 of each picked by the final PRMT
+#define NAV24_VROW(T, B, yc)                                                                                          \
+    {                                                                                                                 \
+        const unsigned c0_ = (yc) << 16, c1_ = (yc) & 0xffff0000u;                                                    \
+        unsigned v_[4];                                                                                               \
+        _Pragma("unroll") for (int k = 0; k < 4; ++k) v_[k] = __umulhi(T[k], c0_) + __umulhi(B[k], c1_) + 2u;         \
+        const unsigned p01_ = (v_[0] | (v_[1] << 16)) >> 2, p23_ = (v_[2] | (v_[3] << 16)) >> 2;                      \
+        const unsigned out_ = __byte_perm(p01_, p23_, 0x6420);                                                        \
+        if (active) *reinterpret_cast<unsigned*>(dp) = out_;                                                          \
+        dp += dPitch;                                                                                                 \
+    }
+    uint8_t* dp = dst + (long long)blockIdx.z * dFrame + (long long)y0 * dPitch + x4;
+    const uint2* yt = s_yt[wid];
+    unsigned A[4], B[4];
+    int cur = (int)yt[0].x;
+    NAV24_HROW(cur, A)
+    NAV24_HROW(cur + 1, B)
+    // two states so that "the old bottom row is the new top row" needs no register moves: (top, bot) = (A, B) or (B, A)
+    int j = 0;
+stateAB:
+    for (; j < nrows; ++j) {
+        const uint2 y = yt[j];
+        const int sy = (int)y.x;
+        if (sy == cur + 1) {                               // warp-uniform
+            NAV24_HROW(sy + 1, A)
+            cur = sy;
+            NAV24_VROW(B, A, y.y)
+            ++j;
+            goto stateBA;
+        }
+        if (sy != cur) {
+            NAV24_HROW(sy, A)
+            NAV24_HROW(sy + 1, B)
+            cur = sy;
+        }
+        NAV24_VROW(A, B, y.y)
+    }
+    return;
+stateBA:
+    for (; j < nrows; ++j) {
+        const uint2 y = yt[j];
+        const int sy = (int)y.x;
+        if (sy == cur + 1) {
+            NAV24_HROW(sy + 1, B)
+            cur = sy;
+            NAV24_VROW(A, B, y.y)
+            ++j;
+            goto stateAB;
+        }
+        if (sy != cur) {
+            NAV24_HROW(sy, B)
+            NAV24_HROW(sy + 1, A)
+            cur = sy;
+        }
+        NAV24_VROW(B, A, y.y)
+    }
+#undef NAV24_HROW
+#undef NAV24_VROW
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1186,17 +1214,24 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         float b, a;
         sincosf(__fmul_rn(angle, factorPI), &b, &a);
 
-        // computeOrbDescriptor: the 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38)
-        const uint8_t* pc = s_blur + 18 * kDescBoxW + 18 + ((cx - 18) & 15);      // the keypoint
+        // computeOrbDescriptor: the 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38).
+        // cvRound = round-half-even of an f32 in (-2^22, 2^22): adding 1.5 * 2^23 leaves the integer in the low mantissa
+        // bits (float bits = 0x4B400000 + n), one full-rate FADD instead of a quarter-rate F2I per coordinate (1024 per
+        // keypoint); the bias of row and column is folded into the base address.
+        const float kMagic = 12582912.f;
+        const unsigned pcA = smem_u32(s_blur) + (unsigned)(18 * kDescBoxW + 18 + ((cx - 18) & 15)) -
+                             (unsigned)(kDescBoxW + 1) * 0x4B400000u;               // the keypoint, minus the biases
         unsigned val = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 q4 = __ldg(pat + j * 32);
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(q4.x, b), __fmul_rn(q4.y, a)));
-            const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(q4.x, a), __fmul_rn(q4.y, b)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(q4.z, b), __fmul_rn(q4.w, a)));
-            const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(q4.z, a), __fmul_rn(q4.w, b)));
-            const int t0 = pc[r0 * kDescBoxW + q0], t1 = pc[r1 * kDescBoxW + q1];
+            const unsigned r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q4.x, b), __fmul_rn(q4.y, a)), kMagic));
+            const unsigned q0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q4.x, a), __fmul_rn(q4.y, b)), kMagic));
+            const unsigned r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q4.z, b), __fmul_rn(q4.w, a)), kMagic));
+            const unsigned q1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q4.z, a), __fmul_rn(q4.w, b)), kMagic));
+            unsigned t0, t1;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(pcA + r0 * (unsigned)kDescBoxW + q0));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(pcA + r1 * (unsigned)kDescBoxW + q1));
             val |= (unsigned)(t0 < t1) << j;
         }
         LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + sCur;
@@ -1236,7 +1271,7 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
         const LevelGeom& D = g.lv[l];
         const ResizeTab& T = tabs[l];
         dim3 grid((D.w + 127) / 128, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
-        const size_t smem = (size_t)((T.boxW * T.boxH + 127) / 128 * 128) + 4 * kResizeSrcRows * 32 * sizeof(uint4);
+        const size_t smem = (size_t)((T.boxW * T.boxH + 127) / 128 * 128);
         if (T.boxW == 192)
             resize_kernel<192><<<grid, 128, smem, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
         else
