@@ -137,6 +137,12 @@ int nav24_orb_detect_match_device(nav24_orb* ctx, const uint8_t* d_gray, int n_f
 int nav24_match_fetch(nav24_orb* ctx, int32_t* matches12, int mcap, int* n_matches);
 /* Waits for the last nav24_orb_detect_device and copies its results out. kps/desc may be NULL (counts only). */
 int nav24_orb_fetch(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out);
+/* The same for frames [first_frame, first_frame + n_frames) / pairs [first_pair, first_pair + n_pairs) of the last call:
+ * a caller that keeps many sequences resident (BASELINE.json configs[4]: 64 sequences x 100 frames) reads the results
+ * back one sequence at a time instead of holding the whole batch in host memory. */
+int nav24_orb_fetch_range(nav24_orb* ctx, int first_frame, int n_frames, nav24_kp* kps, uint8_t* desc, int cap,
+                          int* n_out, int* mono_out);
+int nav24_match_fetch_range(nav24_orb* ctx, int first_pair, int n_pairs, int32_t* matches12, int mcap, int* n_matches);
 int nav24_orb_sync(nav24_orb* ctx);
 /* Upper bound of keypoints per frame for the current n_features (quota + 3 per level). */
 int nav24_orb_max_keypoints(const nav24_orb* ctx);
@@ -151,8 +157,9 @@ int nav24_orb_get_level(nav24_orb* ctx, int frame, int level, int which, uint8_t
 int nav24_orb_get_raw_keys(nav24_orb* ctx, int frame, int level, float* xyr, int cap);
 /* Keypoints of one level after DistributeOctTree + orientation, level coordinates, quadtree order. */
 int nav24_orb_get_level_keypoints(nav24_orb* ctx, int frame, int level, nav24_kp* kps, int cap);
-/* Device time (ms, CUDA events on the context's stream) of the stages of the last detect call:
- * [0] pyramid, [1] FAST, [2] quadtree, [3] order+orientation+blur+descriptors, [4] total kernels. */
+/* Device time (ms, CUDA events on the context's stream) of the stages of the last nav24_orb_detect_device call (the
+ * only entry point that records them: one chunk on one stream, nothing overlapped); NAV24_E_BADARG when the last
+ * detect call was another one:  [0] pyramid, [1] FAST, [2] quadtree, [3] order+orientation+blur+descriptors, [4] total. */
 int nav24_orb_stage_ms(nav24_orb* ctx, float* ms5);
 /* Same stages summed over the detect calls since the last reset (at most the last 64); *calls = how many. */
 int nav24_orb_stage_ms_sum(nav24_orb* ctx, float* ms5, int* calls, int reset);

@@ -7,6 +7,7 @@ nav24_orb_create fails with NAV24_E_CUDA.
 import ctypes as C
 import os
 import re
+import weakref
 
 import numpy as np
 
@@ -84,6 +85,8 @@ def lib():
     L.nav24_orb_detect_match_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, vp,
                                                 C.POINTER(GridCfg), C.c_float, C.c_float, C.c_int, C.c_int]
     L.nav24_match_fetch.argtypes = [vp, vp, C.c_int, vp]
+    L.nav24_orb_fetch_range.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    L.nav24_match_fetch_range.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
     L.nav24_orb_sync.argtypes = [vp]
     L.nav24_orb_max_keypoints.argtypes = [vp]
     L.nav24_orb_get_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, ip, ip]
@@ -142,6 +145,7 @@ def pinned_empty(shape, dtype=np.uint8):
     if rc != OK:
         raise Nav24Error(rc, "cudaHostAlloc failed")
     buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+    weakref.finalize(buf, lib().nav24_host_free, C.c_void_p(ptr.value))      # released when the last view of it is gone
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr
 
@@ -262,6 +266,20 @@ class OrbContext:
         desc = np.zeros((B, cap, 32), np.uint8) if want_data else None
         self._check(self.L.nav24_orb_fetch(self.h, _p(kps), _p(desc), cap, _p(n), _p(mono)))
         return n, mono, kps, desc
+
+    def fetch_range(self, f0, nf, cap=None):
+        """Results of frames [f0, f0+nf) of the last (device-resident) detect call."""
+        cap = cap or self.max_keypoints()
+        n = np.zeros(nf, np.int32); mono = np.zeros(nf, np.int32)
+        kps = np.zeros((nf, cap), KP_DTYPE); desc = np.zeros((nf, cap, 32), np.uint8)
+        self._check(self.L.nav24_orb_fetch_range(self.h, f0, nf, _p(kps), _p(desc), cap, _p(n), _p(mono)))
+        return n, mono, kps, desc
+
+    def match_fetch_range(self, p0, npairs):
+        cap = self.max_keypoints()
+        m = np.full((npairs, cap), -1, np.int32); nm = np.zeros(npairs, np.int32)
+        self._check(self.L.nav24_match_fetch_range(self.h, p0, npairs, _p(m), cap, _p(nm)))
+        return m, nm
 
     def sync(self):
         self._check(self.L.nav24_orb_sync(self.h))

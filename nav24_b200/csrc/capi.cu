@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,9 @@ struct nav24_orb {
     int taper = 1;                             // host pipeline: short first and last chunks (NAV24_TAPER=0: uniform)
     std::vector<cudaEvent_t> evIn, evDone;      // per chunk of the host-buffer pipeline (no timing)
     cudaEvent_t evJoin = nullptr, evPrevEnd = nullptr, evPairs = nullptr;
+    cudaEvent_t evSlotDone[2] = {nullptr, nullptr};      // end of the last call that used pair-table slot 0 / 1
+    bool slotUsed[2] = {false, false};
+    bool stagesValid = false;                  // the stage events belong to the last detect call (nav24_orb_detect_device only)
     bool trace = false;                      // NAV24_TRACE=1: per-chunk timeline of the host pipeline on stderr
     cudaEvent_t evT0 = nullptr, evT1 = nullptr;
     bool prevEndValid = false;
@@ -147,6 +151,20 @@ struct nav24_orb {
 };
 
 namespace {
+
+// Nothing throws across the C boundary: every entry point that can allocate host memory runs inside this guard
+// (std::bad_alloc -> NAV24_E_NOMEM, anything else -> NAV24_E_CUDA; the context keeps a short message when it can).
+template <class F> int guarded(nav24_orb* ctx, F&& body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        if (ctx) { try { ctx->err = "out of host memory"; } catch (...) {} }
+        return NAV24_E_NOMEM;
+    } catch (...) {
+        if (ctx) { try { ctx->err = "unexpected C++ exception"; } catch (...) {} }
+        return NAV24_E_CUDA;
+    }
+}
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -538,19 +556,23 @@ int check_device_error(nav24_orb* ctx) {
     return decode_device_error(ctx, e);
 }
 
-int fetch_results(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
+// results of frames [f0, f0 + nf) of the last detect batch
+int fetch_results(nav24_orb* ctx, int f0, int nf, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
     if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results to fetch");
-    const int B = ctx->lastB;
+    if (f0 < 0 || nf < 0 || f0 + nf > ctx->lastB) return ctx->fail(NAV24_E_BADARG, "frame range outside the last batch");
+    const int B = nf;
     const FrameGeom& g = ctx->g;
     std::vector<int> n(B), m(B);
-    CK(cudaMemcpyAsync(n.data(), ctx->p.nOut, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(m.data(), ctx->p.monoOut, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (B > 0) {
+        CK(cudaMemcpyAsync(n.data(), ctx->p.nOut + f0, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(m.data(), ctx->p.monoOut + f0, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     const int ccap = std::min(cap, g.outCap);
-    if (kps && ccap > 0)
-        CK(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(nav24_kp), ctx->p.outKp, (size_t)g.outCap * sizeof(nav24_kp),
+    if (kps && ccap > 0 && B > 0)
+        CK(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(nav24_kp), ctx->p.outKp + (size_t)f0 * g.outCap, (size_t)g.outCap * sizeof(nav24_kp),
                              (size_t)ccap * sizeof(nav24_kp), B, cudaMemcpyDeviceToHost, ctx->stream));
-    if (desc && ccap > 0)
-        CK(cudaMemcpy2DAsync(desc, (size_t)cap * 32, ctx->p.outDesc, (size_t)g.outCap * 32, (size_t)ccap * 32, B,
+    if (desc && ccap > 0 && B > 0)
+        CK(cudaMemcpy2DAsync(desc, (size_t)cap * 32, ctx->p.outDesc + (size_t)f0 * g.outCap * 32, (size_t)g.outCap * 32, (size_t)ccap * 32, B,
                              cudaMemcpyDeviceToHost, ctx->stream));
     int rc = check_device_error(ctx);   // synchronises the stream
     if (rc != NAV24_OK) return rc;
@@ -614,6 +636,8 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
 // ==========================================================================================
 extern "C" {
 
+void nav24_orb_destroy(nav24_orb* ctx);
+
 int nav24_abi_version(void) { return NAV24_ABI_VERSION; }
 
 int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out) {
@@ -625,7 +649,9 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return NAV24_E_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return NAV24_E_CUDA;
-    nav24_orb* ctx = new nav24_orb();
+    nav24_orb* ctx = nullptr;
+    const int rcCreate = guarded(nullptr, [&]() -> int {
+    ctx = new nav24_orb();
     ctx->device = device;
     ctx->prm = *params;
     ctx->nIniFeatures = params->n_features;
@@ -654,13 +680,19 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
         cudaStreamCreateWithFlags(&ctx->outStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evPrevEnd, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->evPairs, cudaEventDisableTiming) != cudaSuccess) {
-        delete ctx;
+        cudaEventCreateWithFlags(&ctx->evPairs, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evSlotDone[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evSlotDone[1], cudaEventDisableTiming) != cudaSuccess)
         return NAV24_E_CUDA;
-    }
     ctx->xstream[0] = ctx->stream;
     for (auto& r : ctx->evRing) for (auto& e : r) cudaEventCreate(&e);
     for (auto& e : ctx->evT) cudaEventCreate(&e);
+    return NAV24_OK;
+    });
+    if (rcCreate != NAV24_OK) {      // whatever was created so far goes through the one teardown path
+        nav24_orb_destroy(ctx);
+        return rcCreate;
+    }
     *out = ctx;
     return NAV24_OK;
 }
@@ -685,6 +717,9 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->evPrevEnd) cudaEventDestroy(ctx->evPrevEnd);
     if (ctx->evPairs) cudaEventDestroy(ctx->evPairs);
+    for (auto& e : ctx->evSlotDone) if (e) cudaEventDestroy(e);
+    if (ctx->evT0) cudaEventDestroy(ctx->evT0);
+    if (ctx->evT1) cudaEventDestroy(ctx->evT1);
     if (ctx->hN) cudaFreeHost(ctx->hN);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     for (int i = 1; i < nav24_orb::kMaxStreams; ++i) {
@@ -726,27 +761,40 @@ int nav24_orb_max_keypoints(const nav24_orb* ctx) {
 
 int nav24_orb_detect_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames, int w, int h, size_t stride,
                             size_t frame_stride) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!d_gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
-    int rc = ensure_workspace(ctx, w, h, n_frames);
-    if (rc != NAV24_OK) return rc;
-    const bool aligned = (((uintptr_t)d_gray | stride | frame_stride) & 15) == 0;
-    if (aligned) {
-        ctx->p.l0 = d_gray; ctx->p.l0Pitch = (long long)stride; ctx->p.l0Frame = (long long)frame_stride;
-    } else {
-        for (int f = 0; f < n_frames; ++f)
-            CK(cudaMemcpy2DAsync((uint8_t*)ctx->bL0.ptr + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch,
-                                 d_gray + (size_t)f * frame_stride, stride, w, h, cudaMemcpyDeviceToDevice, ctx->stream));
-        ctx->p.l0 = (const uint8_t*)ctx->bL0.ptr; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
-    }
-    return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
-                       0, nullptr, /*one chunk, one stream, stage events*/ n_frames, /*timedStages*/ true);
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!d_gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+        int rc = ensure_workspace(ctx, w, h, n_frames);
+        if (rc != NAV24_OK) return rc;
+        const bool aligned = (((uintptr_t)d_gray | stride | frame_stride) & 15) == 0;
+        if (aligned) {
+            ctx->p.l0 = d_gray; ctx->p.l0Pitch = (long long)stride; ctx->p.l0Frame = (long long)frame_stride;
+        } else {
+            for (int f = 0; f < n_frames; ++f)
+                CK(cudaMemcpy2DAsync((uint8_t*)ctx->bL0.ptr + (size_t)f * ctx->l0Pitch * h, ctx->l0Pitch,
+                                     d_gray + (size_t)f * frame_stride, stride, w, h, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->p.l0 = (const uint8_t*)ctx->bL0.ptr; ctx->p.l0Pitch = ctx->l0Pitch; ctx->p.l0Frame = (long long)ctx->l0Pitch * h;
+        }
+        return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                           0, nullptr, /*one chunk, one stream, stage events*/ n_frames, /*timedStages*/ true);
+    });
 }
 
 int nav24_orb_fetch(nav24_orb* ctx, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
-    if (!ctx) return NAV24_E_BADARG;
-    cudaSetDevice(ctx->device);
-    return fetch_results(ctx, kps, desc, cap, n_out, mono_out);
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        cudaSetDevice(ctx->device);
+        return fetch_results(ctx, 0, ctx->lastB, kps, desc, cap, n_out, mono_out);
+    });
+}
+
+int nav24_orb_fetch_range(nav24_orb* ctx, int first_frame, int n_frames, nav24_kp* kps, uint8_t* desc, int cap, int* n_out,
+                          int* mono_out) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        cudaSetDevice(ctx->device);
+        return fetch_results(ctx, first_frame, n_frames, kps, desc, cap, n_out, mono_out);
+    });
 }
 
 int nav24_orb_sync(nav24_orb* ctx) {
@@ -814,6 +862,10 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
     auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
     mix((unsigned long long)B); mix((unsigned long long)C); mix((unsigned long long)w); mix((unsigned long long)h);
     mix((unsigned long long)nChunks); mix((unsigned long long)nS);
+    // everything that shapes the slabs or what the kernels read: workspace generation, feature count, camera, frames
+    mix(ctx->wsGen); mix((unsigned long long)ctx->prm.n_features); mix((unsigned long long)(uintptr_t)ctx->p.l0);
+    mix((unsigned long long)ctx->p.l0Pitch); mix((unsigned long long)ctx->p.l0Frame);
+    { unsigned long long cb[5] = {0, 0, 0, 0, 0}; static_assert(sizeof(nav24_camera) <= sizeof(cb), "camera bytes"); memcpy(cb, &ctx->cam, sizeof(nav24_camera)); for (unsigned long long v : cb) mix(v); }
 
     // pairs grouped by chunk (pairs spanning chunks go last)
     MatchArgs ma{};
@@ -822,10 +874,17 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
     if (P > 0) {
         rc = ensure_match_scratch(ctx, P, g.outCap, mp->grid);
         if (rc != NAV24_OK) return rc;
-        CK(ctx->mPairs.ensure((size_t)P * 16)); CK(ctx->mPairOrder.ensure((size_t)P * 8));      // two copies: ping-pong
+        // two slots (ping-pong) of FIXED size — half of the buffer, which only changes when it is re-allocated (cudaFree
+        // synchronises the device) — so back-to-back asynchronous calls with different pair counts never overlap, and the
+        // upload into a slot waits for the end of the call that used it last (two calls ago): a still-queued
+        // match_window_kernel never sees its pair table overwritten.
+        if ((size_t)P * 16 > ctx->mPairs.bytes || (size_t)P * 8 > ctx->mPairOrder.bytes) ctx->slotUsed[0] = ctx->slotUsed[1] = false;
+        CK(ctx->mPairs.ensure((size_t)P * 16)); CK(ctx->mPairOrder.ensure((size_t)P * 8));
         ctx->callParity ^= 1;
-        int* dPairs = (int*)ctx->mPairs.ptr + (size_t)ctx->callParity * 2 * P;
-        int* dOrder = (int*)ctx->mPairOrder.ptr + (size_t)ctx->callParity * P;
+        const int slot = ctx->callParity;
+        int* dPairs = (int*)ctx->mPairs.ptr + (size_t)slot * (ctx->mPairs.bytes / 16) * 2;
+        int* dOrder = (int*)ctx->mPairOrder.ptr + (size_t)slot * (ctx->mPairOrder.bytes / 8);
+        if (ctx->slotUsed[slot]) CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evSlotDone[slot], 0));
         std::vector<int> chunkOf(P), order(P);
         for (int q = 0; q < 2 * P; ++q) mix((unsigned long long)(unsigned)mp->pairs[q]);
         for (int q = 0; q < P; ++q) {
@@ -965,6 +1024,8 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evPrevEnd, ctx->stream));
     ctx->prevEndValid = true;
+    if (P > 0) { CK(cudaEventRecord(ctx->evSlotDone[ctx->callParity], ctx->stream)); ctx->slotUsed[ctx->callParity] = true; }
+    ctx->stagesValid = stages;
     ctx->lastB = B;
     ctx->lastValid = true;
     ctx->lastP = P; ctx->lastMatchCap = g.outCap;
@@ -1021,156 +1082,184 @@ extern "C" {
 
 int nav24_orb_detect_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int w, int h, size_t stride,
                            size_t frame_stride, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
-    int rc = ensure_workspace(ctx, w, h, n_frames);
-    if (rc != NAV24_OK) return rc;
-    return run_chunked(ctx, n_frames, w, h, gray, stride, frame_stride, nullptr, kps, desc, cap, n_out, mono_out, nullptr, 0,
-                       nullptr);
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+        int rc = ensure_workspace(ctx, w, h, n_frames);
+        if (rc != NAV24_OK) return rc;
+        return run_chunked(ctx, n_frames, w, h, gray, stride, frame_stride, nullptr, kps, desc, cap, n_out, mono_out, nullptr, 0,
+                           nullptr);
+    });
 }
 
 int nav24_orb_detect_match_batch(nav24_orb* ctx, const uint8_t* gray, int n_frames, int w, int h, size_t stride,
                                  size_t frame_stride, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
                                  int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid, float window, float nnratio,
                                  int th_low, int check_ori, int32_t* matches12, int mcap, int* n_matches) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
-    int rc = check_pairs(ctx, n_pairs, pairs_ab, n_frames, grid);
-    if (rc != NAV24_OK) return rc;
-    rc = ensure_workspace(ctx, w, h, n_frames);
-    if (rc != NAV24_OK) return rc;
-    if (matches12 && mcap < ctx->g.outCap) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
-    MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
-    return run_chunked(ctx, n_frames, w, h, gray, stride, frame_stride, n_pairs > 0 ? &mp : nullptr, kps, desc, cap, n_out,
-                       mono_out, matches12, mcap, n_matches);
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+        int rc = check_pairs(ctx, n_pairs, pairs_ab, n_frames, grid);
+        if (rc != NAV24_OK) return rc;
+        rc = ensure_workspace(ctx, w, h, n_frames);
+        if (rc != NAV24_OK) return rc;
+        if (matches12 && mcap < ctx->g.outCap) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
+        MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
+        return run_chunked(ctx, n_frames, w, h, gray, stride, frame_stride, n_pairs > 0 ? &mp : nullptr, kps, desc, cap, n_out,
+                           mono_out, matches12, mcap, n_matches);
+    });
 }
 
 int nav24_orb_detect_match_device(nav24_orb* ctx, const uint8_t* d_gray, int n_frames, int w, int h, size_t stride,
                                   size_t frame_stride, int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid,
                                   float window, float nnratio, int th_low, int check_ori) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!d_gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
-    if ((((uintptr_t)d_gray | stride | frame_stride) & 15) != 0)
-        return ctx->fail(NAV24_E_BADARG, "device frames need a 16-byte aligned base, row stride and frame stride");
-    int rc = check_pairs(ctx, n_pairs, pairs_ab, n_frames, grid);
-    if (rc != NAV24_OK) return rc;
-    rc = ensure_workspace(ctx, w, h, n_frames);
-    if (rc != NAV24_OK) return rc;
-    ctx->p.l0 = d_gray; ctx->p.l0Pitch = (long long)stride; ctx->p.l0Frame = (long long)frame_stride;
-    MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
-    // Device-resident frames need no copy overlap, and cutting the batch only shortens the latency-bound launches
-    // (quadtree, matcher) without making them cheaper: measured 3.24 ms/step as one chunk vs 3.47 ms in chunks of 64.
-    return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, n_pairs > 0 ? &mp : nullptr, nullptr, nullptr, 0,
-                       nullptr, nullptr, nullptr, 0, nullptr, ctx->residentChunk > 0 ? ctx->residentChunk : n_frames);
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!d_gray || n_frames <= 0 || w <= 0 || h <= 0 || stride < (size_t)w) return ctx->fail(NAV24_E_BADARG, "empty image");
+        if ((((uintptr_t)d_gray | stride | frame_stride) & 15) != 0)
+            return ctx->fail(NAV24_E_BADARG, "device frames need a 16-byte aligned base, row stride and frame stride");
+        int rc = check_pairs(ctx, n_pairs, pairs_ab, n_frames, grid);
+        if (rc != NAV24_OK) return rc;
+        rc = ensure_workspace(ctx, w, h, n_frames);
+        if (rc != NAV24_OK) return rc;
+        ctx->p.l0 = d_gray; ctx->p.l0Pitch = (long long)stride; ctx->p.l0Frame = (long long)frame_stride;
+        MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
+        // Device-resident frames need no copy overlap, and cutting the batch only shortens the latency-bound launches
+        // (quadtree, matcher) without making them cheaper: measured 3.24 ms/step as one chunk vs 3.47 ms in chunks of 64.
+        return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, n_pairs > 0 ? &mp : nullptr, nullptr, nullptr, 0,
+                           nullptr, nullptr, nullptr, 0, nullptr, ctx->residentChunk > 0 ? ctx->residentChunk : n_frames);
+    });
+}
+
+int nav24_match_fetch_range(nav24_orb* ctx, int first_pair, int n_pairs, int32_t* matches12, int mcap, int* n_matches) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!ctx->lastValid || ctx->lastP <= 0) return ctx->fail(NAV24_E_BADARG, "no match results on the device");
+        if (first_pair < 0 || n_pairs < 0 || first_pair + n_pairs > ctx->lastP) return ctx->fail(NAV24_E_BADARG, "pair range outside the last call");
+        cudaSetDevice(ctx->device);
+        const int P = n_pairs, oc = ctx->lastMatchCap;
+        if (matches12 && mcap < oc) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
+        cudaStream_t s = ctx->stream;
+        if (matches12 && P > 0)
+            CK(cudaMemcpy2DAsync(matches12, (size_t)mcap * 4, (const int*)ctx->mMatches.ptr + (size_t)first_pair * oc, (size_t)oc * 4,
+                                 (size_t)oc * 4, P, cudaMemcpyDeviceToHost, s));
+        std::vector<int> nm(P);
+        if (P > 0) CK(cudaMemcpyAsync(nm.data(), (const int*)ctx->mNMatches.ptr + first_pair, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+        int rc = check_device_error(ctx);      // synchronises ctx->stream (which joined the other compute streams)
+        if (rc != NAV24_OK) return rc;
+        int total = 0;
+        for (int q = 0; q < P; ++q) { if (n_matches) n_matches[q] = nm[q]; total += nm[q]; }
+        return total;
+    });
 }
 
 int nav24_match_fetch(nav24_orb* ctx, int32_t* matches12, int mcap, int* n_matches) {
     if (!ctx) return NAV24_E_BADARG;
-    if (!ctx->lastValid || ctx->lastP <= 0) return ctx->fail(NAV24_E_BADARG, "no match results on the device");
-    cudaSetDevice(ctx->device);
-    const int P = ctx->lastP, oc = ctx->lastMatchCap;
-    if (matches12 && mcap < oc) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
-    cudaStream_t s = ctx->stream;
-    if (matches12)
-        CK(cudaMemcpy2DAsync(matches12, (size_t)mcap * 4, ctx->mMatches.ptr, (size_t)oc * 4, (size_t)oc * 4, P, cudaMemcpyDeviceToHost, s));
-    std::vector<int> nm(P);
-    CK(cudaMemcpyAsync(nm.data(), ctx->mNMatches.ptr, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
-    int rc = check_device_error(ctx);      // synchronises ctx->stream (which joined stream2)
-    if (rc != NAV24_OK) return rc;
-    int total = 0;
-    for (int q = 0; q < P; ++q) { if (n_matches) n_matches[q] = nm[q]; total += nm[q]; }
-    return total;
+    return nav24_match_fetch_range(ctx, 0, ctx->lastP, matches12, mcap, n_matches);
 }
 
 int nav24_orb_detect(nav24_orb* ctx, const uint8_t* gray, int w, int h, size_t stride, nav24_kp* kps, uint8_t* desc,
                      int cap, int* n_out) {
-    int mono = 0, n = 0;
-    int rc = nav24_orb_detect_batch(ctx, gray, 1, w, h, stride, stride * (size_t)(h > 0 ? h : 0), kps, desc, cap, &n, &mono);
-    if (n_out) *n_out = n;
-    return rc < 0 ? rc : mono;
+    return guarded(ctx, [&]() -> int {
+        int mono = 0, n = 0;
+        int rc = nav24_orb_detect_batch(ctx, gray, 1, w, h, stride, stride * (size_t)(h > 0 ? h : 0), kps, desc, cap, &n, &mono);
+        if (n_out) *n_out = n;
+        return rc < 0 ? rc : mono;
+    });
 }
 
 int nav24_orb_get_level(nav24_orb* ctx, int frame, int level, int which, uint8_t* dst, size_t dst_stride, int* w, int* h) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
-        return ctx->fail(NAV24_E_BADARG, "bad frame/level");
-    cudaSetDevice(ctx->device);
-    const LevelGeom& L = ctx->g.lv[level];
-    if (w) *w = L.w;
-    if (h) *h = L.h;
-    if (!dst) return NAV24_OK;
-    const uint8_t* src; size_t pitch;
-    if (which == 1) { src = ctx->p.blur + (size_t)frame * ctx->g.blurFrameBytes + L.boff; pitch = L.pitch; }
-    else if (level == 0) { src = ctx->p.l0 + (size_t)frame * ctx->p.l0Frame; pitch = (size_t)ctx->p.l0Pitch; }
-    else { src = ctx->p.pyr + (size_t)frame * ctx->g.pyrFrameBytes + L.off; pitch = L.pitch; }
-    CK(cudaMemcpy2DAsync(dst, dst_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return NAV24_OK;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
+            return ctx->fail(NAV24_E_BADARG, "bad frame/level");
+        cudaSetDevice(ctx->device);
+        const LevelGeom& L = ctx->g.lv[level];
+        if (w) *w = L.w;
+        if (h) *h = L.h;
+        if (!dst) return NAV24_OK;
+        const uint8_t* src; size_t pitch;
+        if (which == 1) { src = ctx->p.blur + (size_t)frame * ctx->g.blurFrameBytes + L.boff; pitch = L.pitch; }
+        else if (level == 0) { src = ctx->p.l0 + (size_t)frame * ctx->p.l0Frame; pitch = (size_t)ctx->p.l0Pitch; }
+        else { src = ctx->p.pyr + (size_t)frame * ctx->g.pyrFrameBytes + L.off; pitch = L.pitch; }
+        CK(cudaMemcpy2DAsync(dst, dst_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return NAV24_OK;
+    });
 }
 
 int nav24_orb_get_raw_keys(nav24_orb* ctx, int frame, int level, float* xyr, int cap) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
-        return ctx->fail(NAV24_E_BADARG, "bad frame/level");
-    cudaSetDevice(ctx->device);
-    int n = 0;
-    CK(cudaMemcpyAsync(&n, ctx->p.rawTotal + frame * ctx->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (!xyr || n == 0) return n;
-    std::vector<RawRec> r(n);
-    CK(cudaMemcpyAsync(r.data(), ctx->p.keys + (size_t)frame * ctx->g.rawPerFrame + ctx->g.lv[level].rawOff, n * sizeof(RawRec),
-                       cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n && i < cap; ++i) { xyr[3 * i] = r[i].x; xyr[3 * i + 1] = r[i].y; xyr[3 * i + 2] = r[i].score; }
-    return n;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
+            return ctx->fail(NAV24_E_BADARG, "bad frame/level");
+        cudaSetDevice(ctx->device);
+        int n = 0;
+        CK(cudaMemcpyAsync(&n, ctx->p.rawTotal + frame * ctx->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!xyr || n == 0) return n;
+        std::vector<RawRec> r(n);
+        CK(cudaMemcpyAsync(r.data(), ctx->p.keys + (size_t)frame * ctx->g.rawPerFrame + ctx->g.lv[level].rawOff, n * sizeof(RawRec),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n && i < cap; ++i) { xyr[3 * i] = r[i].x; xyr[3 * i + 1] = r[i].y; xyr[3 * i + 2] = r[i].score; }
+        return n;
+    });
 }
 
 int nav24_orb_get_level_keypoints(nav24_orb* ctx, int frame, int level, nav24_kp* kps, int cap) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
-        return ctx->fail(NAV24_E_BADARG, "bad frame/level");
-    cudaSetDevice(ctx->device);
-    int n = 0;
-    CK(cudaMemcpyAsync(&n, ctx->p.levelCount + frame * ctx->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (!kps || n == 0) return n;
-    std::vector<LevelKp> r(n);
-    const LevelGeom& L = ctx->g.lv[level];
-    CK(cudaMemcpyAsync(r.data(), ctx->p.lkp + (size_t)frame * ctx->g.kpPerFrame + L.kpOff, n * sizeof(LevelKp),
-                       cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n && i < cap; ++i) {
-        kps[i].x = r[i].x; kps[i].y = r[i].y; kps[i].size = L.patch; kps[i].angle = r[i].angle;
-        kps[i].response = r[i].score; kps[i].octave = level; kps[i].class_id = -1;
-    }
-    return n;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!ctx->lastValid || frame < 0 || frame >= ctx->lastB || level < 0 || level >= ctx->g.nlevels)
+            return ctx->fail(NAV24_E_BADARG, "bad frame/level");
+        cudaSetDevice(ctx->device);
+        int n = 0;
+        CK(cudaMemcpyAsync(&n, ctx->p.levelCount + frame * ctx->g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!kps || n == 0) return n;
+        std::vector<LevelKp> r(n);
+        const LevelGeom& L = ctx->g.lv[level];
+        CK(cudaMemcpyAsync(r.data(), ctx->p.lkp + (size_t)frame * ctx->g.kpPerFrame + L.kpOff, n * sizeof(LevelKp),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n && i < cap; ++i) {
+            kps[i].x = r[i].x; kps[i].y = r[i].y; kps[i].size = L.patch; kps[i].angle = r[i].angle;
+            kps[i].response = r[i].score; kps[i].octave = level; kps[i].class_id = -1;
+        }
+        return n;
+    });
 }
 
 int nav24_orb_stage_ms(nav24_orb* ctx, float* ms5) {
-    if (!ctx || !ms5) return NAV24_E_BADARG;
-    if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect call yet");
-    cudaSetDevice(ctx->device);
-    CK(cudaEventSynchronize(ctx->ev[4]));
-    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms5[i], ctx->ev[i], ctx->ev[i + 1]));
-    CK(cudaEventElapsedTime(&ms5[4], ctx->ev[0], ctx->ev[4]));
-    return NAV24_OK;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx || !ms5) return NAV24_E_BADARG;
+        if (!ctx->lastValid || !ctx->stagesValid)
+            return ctx->fail(NAV24_E_BADARG, "stage timers cover nav24_orb_detect_device only: the last call recorded none");
+        cudaSetDevice(ctx->device);
+        CK(cudaEventSynchronize(ctx->ev[4]));
+        for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms5[i], ctx->ev[i], ctx->ev[i + 1]));
+        CK(cudaEventElapsedTime(&ms5[4], ctx->ev[0], ctx->ev[4]));
+        return NAV24_OK;
+    });
 }
 
 int nav24_orb_stage_ms_sum(nav24_orb* ctx, float* ms5, int* calls, int reset) {
-    if (!ctx || !ms5) return NAV24_E_BADARG;
-    cudaSetDevice(ctx->device);
-    const int n = (int)std::min<long long>(ctx->evCalls, nav24_orb::kEvRing);
-    for (int i = 0; i < 5; ++i) ms5[i] = 0.f;
-    for (int c = 0; c < n; ++c) {
-        cudaEvent_t* e = ctx->evRing[(ctx->evCalls - 1 - c) % nav24_orb::kEvRing];
-        CK(cudaEventSynchronize(e[4]));
-        float t;
-        for (int i = 0; i < 4; ++i) { CK(cudaEventElapsedTime(&t, e[i], e[i + 1])); ms5[i] += t; }
-        CK(cudaEventElapsedTime(&t, e[0], e[4])); ms5[4] += t;
-    }
-    if (calls) *calls = n;
-    if (reset) ctx->evCalls = 0;
-    return NAV24_OK;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx || !ms5) return NAV24_E_BADARG;
+        cudaSetDevice(ctx->device);
+        const int n = (int)std::min<long long>(ctx->evCalls, nav24_orb::kEvRing);
+        for (int i = 0; i < 5; ++i) ms5[i] = 0.f;
+        for (int c = 0; c < n; ++c) {
+            cudaEvent_t* e = ctx->evRing[(ctx->evCalls - 1 - c) % nav24_orb::kEvRing];
+            CK(cudaEventSynchronize(e[4]));
+            float t;
+            for (int i = 0; i < 4; ++i) { CK(cudaEventElapsedTime(&t, e[i], e[i + 1])); ms5[i] += t; }
+            CK(cudaEventElapsedTime(&t, e[0], e[4])); ms5[4] += t;
+        }
+        if (calls) *calls = n;
+        if (reset) ctx->evCalls = 0;
+        return NAV24_OK;
+    });
 }
 
 long long nav24_orb_launch_count(const nav24_orb* ctx) { return ctx ? ctx->launches : 0; }
@@ -1199,100 +1288,106 @@ int nav24_match_window_batch(nav24_orb* ctx, int P, int cap, const nav24_kp* k1,
                              const int* n1, const nav24_kp* k2, const float* ud2, const uint8_t* d2, const int* n2,
                              const nav24_grid_cfg* grid, float window, float nnratio, int th_low, int check_ori,
                              int32_t* matches12, int* n_matches) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (P <= 0 || cap <= 0 || !k1 || !k2 || !ud1 || !ud2 || !d1 || !d2 || !n1 || !n2 || !matches12 || !grid_ok(grid))
-        return ctx->fail(NAV24_E_BADARG, "bad matcher argument");
-    for (int p = 0; p < P; ++p)
-        if (n1[p] < 0 || n1[p] > cap || n2[p] < 0 || n2[p] > cap) return ctx->fail(NAV24_E_BADARG, "n1/n2 exceed cap");
-    cudaSetDevice(ctx->device);
-    int rc = ensure_match_scratch(ctx, P, cap, grid);
-    if (rc != NAV24_OK) return rc;
-    const size_t pc = (size_t)P * cap;
-    CK(ctx->mK1.ensure(pc * sizeof(nav24_kp))); CK(ctx->mK2.ensure(pc * sizeof(nav24_kp)));
-    CK(ctx->mU1.ensure(pc * 8)); CK(ctx->mU2.ensure(pc * 8));
-    CK(ctx->mD1.ensure(pc * 32)); CK(ctx->mD2.ensure(pc * 32));
-    CK(ctx->mN1.ensure((size_t)P * 4)); CK(ctx->mN2.ensure((size_t)P * 4));
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->mK1.ptr, k1, pc * sizeof(nav24_kp), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->mK2.ptr, k2, pc * sizeof(nav24_kp), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->mU1.ptr, ud1, pc * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->mU2.ptr, ud2, pc * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->mD1.ptr, d1, pc * 32, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->mD2.ptr, d2, pc * 32, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->mN1.ptr, n1, (size_t)P * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->mN2.ptr, n2, (size_t)P * 4, cudaMemcpyHostToDevice, s));
-    MatchArgs a{};
-    fill_match_args(ctx, a, grid, window, nnratio, th_low, check_ori, cap);
-    a.k1 = (const nav24_kp*)ctx->mK1.ptr; a.k2 = (const nav24_kp*)ctx->mK2.ptr;
-    a.ud1 = (const float*)ctx->mU1.ptr; a.ud2 = (const float*)ctx->mU2.ptr;
-    a.d1 = (const uint8_t*)ctx->mD1.ptr; a.d2 = (const uint8_t*)ctx->mD2.ptr;
-    a.n1 = (const int*)ctx->mN1.ptr; a.n2 = (const int*)ctx->mN2.ptr;
-    a.stride1 = cap; a.stride2 = cap; a.pairs = nullptr;
-    ctx->launches += launch_match_window(a, P, s);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(matches12, a.matches12, pc * 4, cudaMemcpyDeviceToHost, s));
-    std::vector<int> nm(P);
-    CK(cudaMemcpyAsync(nm.data(), a.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    int total = 0;
-    for (int p = 0; p < P; ++p) { if (n_matches) n_matches[p] = nm[p]; total += nm[p]; }
-    return total;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (P <= 0 || cap <= 0 || !k1 || !k2 || !ud1 || !ud2 || !d1 || !d2 || !n1 || !n2 || !matches12 || !grid_ok(grid))
+            return ctx->fail(NAV24_E_BADARG, "bad matcher argument");
+        for (int p = 0; p < P; ++p)
+            if (n1[p] < 0 || n1[p] > cap || n2[p] < 0 || n2[p] > cap) return ctx->fail(NAV24_E_BADARG, "n1/n2 exceed cap");
+        cudaSetDevice(ctx->device);
+        int rc = ensure_match_scratch(ctx, P, cap, grid);
+        if (rc != NAV24_OK) return rc;
+        const size_t pc = (size_t)P * cap;
+        CK(ctx->mK1.ensure(pc * sizeof(nav24_kp))); CK(ctx->mK2.ensure(pc * sizeof(nav24_kp)));
+        CK(ctx->mU1.ensure(pc * 8)); CK(ctx->mU2.ensure(pc * 8));
+        CK(ctx->mD1.ensure(pc * 32)); CK(ctx->mD2.ensure(pc * 32));
+        CK(ctx->mN1.ensure((size_t)P * 4)); CK(ctx->mN2.ensure((size_t)P * 4));
+        cudaStream_t s = ctx->stream;
+        CK(cudaMemcpyAsync(ctx->mK1.ptr, k1, pc * sizeof(nav24_kp), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->mK2.ptr, k2, pc * sizeof(nav24_kp), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->mU1.ptr, ud1, pc * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->mU2.ptr, ud2, pc * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->mD1.ptr, d1, pc * 32, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->mD2.ptr, d2, pc * 32, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->mN1.ptr, n1, (size_t)P * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->mN2.ptr, n2, (size_t)P * 4, cudaMemcpyHostToDevice, s));
+        MatchArgs a{};
+        fill_match_args(ctx, a, grid, window, nnratio, th_low, check_ori, cap);
+        a.k1 = (const nav24_kp*)ctx->mK1.ptr; a.k2 = (const nav24_kp*)ctx->mK2.ptr;
+        a.ud1 = (const float*)ctx->mU1.ptr; a.ud2 = (const float*)ctx->mU2.ptr;
+        a.d1 = (const uint8_t*)ctx->mD1.ptr; a.d2 = (const uint8_t*)ctx->mD2.ptr;
+        a.n1 = (const int*)ctx->mN1.ptr; a.n2 = (const int*)ctx->mN2.ptr;
+        a.stride1 = cap; a.stride2 = cap; a.pairs = nullptr;
+        ctx->launches += launch_match_window(a, P, s);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(matches12, a.matches12, pc * 4, cudaMemcpyDeviceToHost, s));
+        std::vector<int> nm(P);
+        CK(cudaMemcpyAsync(nm.data(), a.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        int total = 0;
+        for (int p = 0; p < P; ++p) { if (n_matches) n_matches[p] = nm[p]; total += nm[p]; }
+        return total;
+    });
 }
 
 int nav24_match_window(nav24_orb* ctx, const nav24_kp* k1, const float* ud1, const uint8_t* d1, int n1, const nav24_kp* k2,
                        const float* ud2, const uint8_t* d2, int n2, const nav24_grid_cfg* grid, float window, float nnratio,
                        int th_low, int check_ori, int32_t* matches12) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (n1 < 0 || n2 < 0) return ctx->fail(NAV24_E_BADARG, "negative count");
-    if (n1 == 0) return 0;
-    const int cap = std::max(std::max(n1, n2), 1);
-    // pad both sides to a common capacity so that the batched entry point can be reused
-    std::vector<nav24_kp> K1(cap), K2(cap);
-    std::vector<float> U1(2 * (size_t)cap), U2(2 * (size_t)cap);
-    std::vector<uint8_t> D1(32 * (size_t)cap), D2(32 * (size_t)cap);
-    std::vector<int32_t> M(cap, -1);
-    if (!k1 || !ud1 || !d1 || !matches12 || (n2 > 0 && (!k2 || !ud2 || !d2))) return ctx->fail(NAV24_E_BADARG, "null pointer");
-    memcpy(K1.data(), k1, (size_t)n1 * sizeof(nav24_kp)); memcpy(U1.data(), ud1, (size_t)n1 * 8); memcpy(D1.data(), d1, (size_t)n1 * 32);
-    if (n2) { memcpy(K2.data(), k2, (size_t)n2 * sizeof(nav24_kp)); memcpy(U2.data(), ud2, (size_t)n2 * 8); memcpy(D2.data(), d2, (size_t)n2 * 32); }
-    int nm = 0;
-    int rc = nav24_match_window_batch(ctx, 1, cap, K1.data(), U1.data(), D1.data(), &n1, K2.data(), U2.data(), D2.data(), &n2,
-                                      grid, window, nnratio, th_low, check_ori, M.data(), &nm);
-    if (rc < 0) return rc;
-    memcpy(matches12, M.data(), (size_t)n1 * 4);
-    return nm;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (n1 < 0 || n2 < 0) return ctx->fail(NAV24_E_BADARG, "negative count");
+        if (n1 == 0) return 0;
+        const int cap = std::max(std::max(n1, n2), 1);
+        // pad both sides to a common capacity so that the batched entry point can be reused
+        std::vector<nav24_kp> K1(cap), K2(cap);
+        std::vector<float> U1(2 * (size_t)cap), U2(2 * (size_t)cap);
+        std::vector<uint8_t> D1(32 * (size_t)cap), D2(32 * (size_t)cap);
+        std::vector<int32_t> M(cap, -1);
+        if (!k1 || !ud1 || !d1 || !matches12 || (n2 > 0 && (!k2 || !ud2 || !d2))) return ctx->fail(NAV24_E_BADARG, "null pointer");
+        memcpy(K1.data(), k1, (size_t)n1 * sizeof(nav24_kp)); memcpy(U1.data(), ud1, (size_t)n1 * 8); memcpy(D1.data(), d1, (size_t)n1 * 32);
+        if (n2) { memcpy(K2.data(), k2, (size_t)n2 * sizeof(nav24_kp)); memcpy(U2.data(), ud2, (size_t)n2 * 8); memcpy(D2.data(), d2, (size_t)n2 * 32); }
+        int nm = 0;
+        int rc = nav24_match_window_batch(ctx, 1, cap, K1.data(), U1.data(), D1.data(), &n1, K2.data(), U2.data(), D2.data(), &n2,
+                                          grid, window, nnratio, th_low, check_ori, M.data(), &nm);
+        if (rc < 0) return rc;
+        memcpy(matches12, M.data(), (size_t)n1 * 4);
+        return nm;
+    });
 }
 
 int nav24_match_window_frames(nav24_orb* ctx, int P, const int* pairs_ab, const nav24_grid_cfg* grid, float window,
                               float nnratio, int th_low, int check_ori, int32_t* matches12, int cap, int* n_matches) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results on the device");
-    if (P <= 0 || !pairs_ab || !grid_ok(grid)) return ctx->fail(NAV24_E_BADARG, "bad matcher argument");
-    const int oc = ctx->g.outCap;
-    if (matches12 && cap < oc) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
-    for (int p = 0; p < 2 * P; ++p)
-        if (pairs_ab[p] < 0 || pairs_ab[p] >= ctx->lastB) return ctx->fail(NAV24_E_BADARG, "frame index out of range");
-    cudaSetDevice(ctx->device);
-    int rc = ensure_match_scratch(ctx, P, oc, grid);
-    if (rc != NAV24_OK) return rc;
-    CK(ctx->mPairs.ensure((size_t)P * 8));
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->mPairs.ptr, pairs_ab, (size_t)P * 8, cudaMemcpyHostToDevice, s));
-    MatchArgs a{};
-    fill_match_args(ctx, a, grid, window, nnratio, th_low, check_ori, oc);
-    a.k1 = a.k2 = ctx->p.outKp; a.d1 = a.d2 = ctx->p.outDesc;
-    a.ud1 = a.ud2 = ctx->cam.model != NAV24_CAM_PINHOLE ? ctx->p.outUd : nullptr;
-    a.n1 = a.n2 = ctx->p.nOut; a.stride1 = a.stride2 = oc; a.pairs = (const int*)ctx->mPairs.ptr;
-    ctx->launches += launch_match_window(a, P, s);
-    CK(cudaGetLastError());
-    if (!matches12 && !n_matches) return NAV24_OK;      // fully asynchronous: results stay on the device
-    if (matches12)
-        CK(cudaMemcpy2DAsync(matches12, (size_t)cap * 4, a.matches12, (size_t)oc * 4, (size_t)oc * 4, P, cudaMemcpyDeviceToHost, s));
-    std::vector<int> nm(P);
-    CK(cudaMemcpyAsync(nm.data(), a.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    int total = 0;
-    for (int p = 0; p < P; ++p) { if (n_matches) n_matches[p] = nm[p]; total += nm[p]; }
-    return total;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results on the device");
+        if (P <= 0 || !pairs_ab || !grid_ok(grid)) return ctx->fail(NAV24_E_BADARG, "bad matcher argument");
+        const int oc = ctx->g.outCap;
+        if (matches12 && cap < oc) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
+        for (int p = 0; p < 2 * P; ++p)
+            if (pairs_ab[p] < 0 || pairs_ab[p] >= ctx->lastB) return ctx->fail(NAV24_E_BADARG, "frame index out of range");
+        cudaSetDevice(ctx->device);
+        int rc = ensure_match_scratch(ctx, P, oc, grid);
+        if (rc != NAV24_OK) return rc;
+        CK(ctx->mPairs.ensure((size_t)P * 8));
+        cudaStream_t s = ctx->stream;
+        CK(cudaMemcpyAsync(ctx->mPairs.ptr, pairs_ab, (size_t)P * 8, cudaMemcpyHostToDevice, s));
+        MatchArgs a{};
+        fill_match_args(ctx, a, grid, window, nnratio, th_low, check_ori, oc);
+        a.k1 = a.k2 = ctx->p.outKp; a.d1 = a.d2 = ctx->p.outDesc;
+        a.ud1 = a.ud2 = ctx->cam.model != NAV24_CAM_PINHOLE ? ctx->p.outUd : nullptr;
+        a.n1 = a.n2 = ctx->p.nOut; a.stride1 = a.stride2 = oc; a.pairs = (const int*)ctx->mPairs.ptr;
+        ctx->launches += launch_match_window(a, P, s);
+        CK(cudaGetLastError());
+        if (!matches12 && !n_matches) return NAV24_OK;      // fully asynchronous: results stay on the device
+        if (matches12)
+            CK(cudaMemcpy2DAsync(matches12, (size_t)cap * 4, a.matches12, (size_t)oc * 4, (size_t)oc * 4, P, cudaMemcpyDeviceToHost, s));
+        std::vector<int> nm(P);
+        CK(cudaMemcpyAsync(nm.data(), a.nMatches, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        int total = 0;
+        for (int p = 0; p < P; ++p) { if (n_matches) n_matches[p] = nm[p]; total += nm[p]; }
+        return total;
+    });
 }
 
 static bool camera_ok(const nav24_camera* c) {
@@ -1300,19 +1395,21 @@ static bool camera_ok(const nav24_camera* c) {
 }
 
 int nav24_undistort_points(nav24_orb* ctx, const nav24_camera* cam, const float* xy, int n, float* ud_xy) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!camera_ok(cam) || n < 0 || (n > 0 && (!xy || !ud_xy))) return ctx->fail(NAV24_E_BADARG, "bad undistort argument");
-    if (n == 0) return NAV24_OK;
-    cudaSetDevice(ctx->device);
-    CK(ctx->bUdTmp.ensure((size_t)n * 16));
-    float* dIn = (float*)ctx->bUdTmp.ptr; float* dOut = dIn + 2 * (size_t)n;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(dIn, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    ctx->launches += launch_undistort_points(*cam, dIn, n, dOut, s);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ud_xy, dOut, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return NAV24_OK;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!camera_ok(cam) || n < 0 || (n > 0 && (!xy || !ud_xy))) return ctx->fail(NAV24_E_BADARG, "bad undistort argument");
+        if (n == 0) return NAV24_OK;
+        cudaSetDevice(ctx->device);
+        CK(ctx->bUdTmp.ensure((size_t)n * 16));
+        float* dIn = (float*)ctx->bUdTmp.ptr; float* dOut = dIn + 2 * (size_t)n;
+        cudaStream_t s = ctx->stream;
+        CK(cudaMemcpyAsync(dIn, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        ctx->launches += launch_undistort_points(*cam, dIn, n, dOut, s);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ud_xy, dOut, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return NAV24_OK;
+    });
 }
 
 int nav24_orb_set_camera(nav24_orb* ctx, const nav24_camera* cam) {
@@ -1325,57 +1422,61 @@ int nav24_orb_set_camera(nav24_orb* ctx, const nav24_camera* cam) {
 }
 
 int nav24_orb_fetch_undistorted(nav24_orb* ctx, float* ud_xy, int cap) {
-    if (!ctx || !ud_xy) return NAV24_E_BADARG;
-    if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results on the device");
-    cudaSetDevice(ctx->device);
-    int rc = check_device_error(ctx);      // synchronises ctx->stream (which joined the other compute streams)
-    if (rc != NAV24_OK) return rc;
-    const int oc = ctx->g.outCap, c = std::min(cap, oc), B = ctx->lastB;
-    if (ctx->cam.model != NAV24_CAM_PINHOLE) {
-        CK(cudaMemcpy2D(ud_xy, (size_t)cap * 8, ctx->p.outUd, (size_t)oc * 8, (size_t)c * 8, B, cudaMemcpyDeviceToHost));
-    } else {                             // identity: the detected coordinates
-        std::vector<nav24_kp> k((size_t)B * oc);
-        CK(cudaMemcpy(k.data(), ctx->p.outKp, k.size() * sizeof(nav24_kp), cudaMemcpyDeviceToHost));
-        std::vector<int> n(B);
-        CK(cudaMemcpy(n.data(), ctx->p.nOut, (size_t)B * 4, cudaMemcpyDeviceToHost));
-        for (int f = 0; f < B; ++f)
-            for (int i = 0; i < std::min(n[f], c); ++i) {
-                ud_xy[((size_t)f * cap + i) * 2] = k[(size_t)f * oc + i].x;
-                ud_xy[((size_t)f * cap + i) * 2 + 1] = k[(size_t)f * oc + i].y;
-            }
-    }
-    return NAV24_OK;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx || !ud_xy) return NAV24_E_BADARG;
+        if (!ctx->lastValid) return ctx->fail(NAV24_E_BADARG, "no detect results on the device");
+        cudaSetDevice(ctx->device);
+        int rc = check_device_error(ctx);      // synchronises ctx->stream (which joined the other compute streams)
+        if (rc != NAV24_OK) return rc;
+        const int oc = ctx->g.outCap, c = std::min(cap, oc), B = ctx->lastB;
+        if (ctx->cam.model != NAV24_CAM_PINHOLE) {
+            CK(cudaMemcpy2D(ud_xy, (size_t)cap * 8, ctx->p.outUd, (size_t)oc * 8, (size_t)c * 8, B, cudaMemcpyDeviceToHost));
+        } else {                             // identity: the detected coordinates
+            std::vector<nav24_kp> k((size_t)B * oc);
+            CK(cudaMemcpy(k.data(), ctx->p.outKp, k.size() * sizeof(nav24_kp), cudaMemcpyDeviceToHost));
+            std::vector<int> n(B);
+            CK(cudaMemcpy(n.data(), ctx->p.nOut, (size_t)B * 4, cudaMemcpyDeviceToHost));
+            for (int f = 0; f < B; ++f)
+                for (int i = 0; i < std::min(n[f], c); ++i) {
+                    ud_xy[((size_t)f * cap + i) * 2] = k[(size_t)f * oc + i].x;
+                    ud_xy[((size_t)f * cap + i) * 2 + 1] = k[(size_t)f * oc + i].y;
+                }
+        }
+        return NAV24_OK;
+    });
 }
 
 int nav24_match_bf_knn2(nav24_orb* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int norm, float ratio,
                         int32_t* idx0, int32_t* idx1, float* dist0, float* dist1, uint8_t* pass) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (n1 < 0 || n2 < 0 || (norm != NAV24_NORM_HAMMING && norm != NAV24_NORM_L2_U8)) return ctx->fail(NAV24_E_BADARG, "bad argument");
-    if (n1 == 0) return 0;
-    if (!d1 || (n2 > 0 && !d2) || !idx0 || !idx1 || !dist0 || !dist1 || !pass) return ctx->fail(NAV24_E_BADARG, "null pointer");
-    cudaSetDevice(ctx->device);
-    CK(ctx->mD1.ensure((size_t)n1 * 32)); CK(ctx->mD2.ensure((size_t)std::max(n2, 1) * 32));
-    CK(ctx->mI0.ensure((size_t)n1 * 4)); CK(ctx->mI1.ensure((size_t)n1 * 4));
-    CK(ctx->mF0.ensure((size_t)n1 * 4)); CK(ctx->mF1.ensure((size_t)n1 * 4)); CK(ctx->mPass.ensure((size_t)n1));
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->mD1.ptr, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
-    if (n2) CK(cudaMemcpyAsync(ctx->mD2.ptr, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
-    CK(ctx->bUdTmp.ensure((size_t)bf_knn2_segments(n1, n2) * n1 * sizeof(int4)));      // (scratch shared with nav24_undistort_points)
-    CK(cudaEventRecord(ctx->evT[0], s));
-    ctx->launches += launch_bf_knn2((const uint8_t*)ctx->mD1.ptr, n1, (const uint8_t*)ctx->mD2.ptr, n2, norm, ratio,
-                                    (int*)ctx->mI0.ptr, (int*)ctx->mI1.ptr, (float*)ctx->mF0.ptr, (float*)ctx->mF1.ptr,
-                                    (uint8_t*)ctx->mPass.ptr, (int4*)ctx->bUdTmp.ptr, s);
-    CK(cudaEventRecord(ctx->evT[1], s));      // nav24_debug_last_kernel_ms: device time of the two kernels
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(idx0, ctx->mI0.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(idx1, ctx->mI1.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(dist0, ctx->mF0.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(dist1, ctx->mF1.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(pass, ctx->mPass.ptr, (size_t)n1, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    int np = 0;
-    for (int i = 0; i < n1; ++i) np += pass[i];
-    return np;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (n1 < 0 || n2 < 0 || (norm != NAV24_NORM_HAMMING && norm != NAV24_NORM_L2_U8)) return ctx->fail(NAV24_E_BADARG, "bad argument");
+        if (n1 == 0) return 0;
+        if (!d1 || (n2 > 0 && !d2) || !idx0 || !idx1 || !dist0 || !dist1 || !pass) return ctx->fail(NAV24_E_BADARG, "null pointer");
+        cudaSetDevice(ctx->device);
+        CK(ctx->mD1.ensure((size_t)n1 * 32)); CK(ctx->mD2.ensure((size_t)std::max(n2, 1) * 32));
+        CK(ctx->mI0.ensure((size_t)n1 * 4)); CK(ctx->mI1.ensure((size_t)n1 * 4));
+        CK(ctx->mF0.ensure((size_t)n1 * 4)); CK(ctx->mF1.ensure((size_t)n1 * 4)); CK(ctx->mPass.ensure((size_t)n1));
+        cudaStream_t s = ctx->stream;
+        CK(cudaMemcpyAsync(ctx->mD1.ptr, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+        if (n2) CK(cudaMemcpyAsync(ctx->mD2.ptr, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+        CK(ctx->bUdTmp.ensure((size_t)bf_knn2_segments(n1, n2) * n1 * sizeof(int4)));      // (scratch shared with nav24_undistort_points)
+        CK(cudaEventRecord(ctx->evT[0], s));
+        ctx->launches += launch_bf_knn2((const uint8_t*)ctx->mD1.ptr, n1, (const uint8_t*)ctx->mD2.ptr, n2, norm, ratio,
+                                        (int*)ctx->mI0.ptr, (int*)ctx->mI1.ptr, (float*)ctx->mF0.ptr, (float*)ctx->mF1.ptr,
+                                        (uint8_t*)ctx->mPass.ptr, (int4*)ctx->bUdTmp.ptr, s);
+        CK(cudaEventRecord(ctx->evT[1], s));      // nav24_debug_last_kernel_ms: device time of the two kernels
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(idx0, ctx->mI0.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(idx1, ctx->mI1.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(dist0, ctx->mF0.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(dist1, ctx->mF1.ptr, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(pass, ctx->mPass.ptr, (size_t)n1, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        int np = 0;
+        for (int i = 0; i < n1; ++i) np += pass[i];
+        return np;
+    });
 }
 
 int nav24_debug_last_kernel_ms(nav24_orb* ctx, float* ms) {
@@ -1387,20 +1488,22 @@ int nav24_debug_last_kernel_ms(nav24_orb* ctx, float* ms) {
 }
 
 int nav24_debug_sort_u32(nav24_orb* ctx, const uint32_t* keys, int n, int32_t* perm) {
-    if (!ctx) return NAV24_E_BADARG;
-    if (!keys || !perm || n < 0) return ctx->fail(NAV24_E_BADARG, "bad argument");
-    if (n == 0) return NAV24_OK;
-    cudaSetDevice(ctx->device);
-    std::vector<unsigned long long> r(n);
-    for (int i = 0; i < n; ++i) r[i] = ((unsigned long long)keys[i] << 32) | (unsigned)i;
-    CK(ctx->mCand.ensure((size_t)n * 8));
-    CK(cudaMemcpyAsync(ctx->mCand.ptr, r.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (launch_debug_sort((unsigned long long*)ctx->mCand.ptr, n, ctx->stream) < 0) return ctx->fail(NAV24_E_CAPACITY, "too many records");
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(r.data(), ctx->mCand.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n; ++i) perm[i] = (int32_t)(r[i] & 0xffffffffu);
-    return NAV24_OK;
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (!keys || !perm || n < 0) return ctx->fail(NAV24_E_BADARG, "bad argument");
+        if (n == 0) return NAV24_OK;
+        cudaSetDevice(ctx->device);
+        std::vector<unsigned long long> r(n);
+        for (int i = 0; i < n; ++i) r[i] = ((unsigned long long)keys[i] << 32) | (unsigned)i;
+        CK(ctx->mCand.ensure((size_t)n * 8));
+        CK(cudaMemcpyAsync(ctx->mCand.ptr, r.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (launch_debug_sort((unsigned long long*)ctx->mCand.ptr, n, ctx->stream) < 0) return ctx->fail(NAV24_E_CAPACITY, "too many records");
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(r.data(), ctx->mCand.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; ++i) perm[i] = (int32_t)(r[i] & 0xffffffffu);
+        return NAV24_OK;
+    });
 }
 
 int nav24_host_alloc(size_t bytes, void** out) {

@@ -115,8 +115,10 @@ int ref_quadtree(const float* xyr, int n, int minX, int maxX, int minY, int maxY
 int ref_match_window(const ref_kp* k1, const float* ud1, const uint8_t* d1, int n1, const ref_kp* k2, const float* ud2,
                      const uint8_t* d2, int n2, int imgW, int imgH, const float* bounds4, float nnratio, int checkOri,
                      int* matches12) {
-    GridProbe::reset();
-    OB::FeatureGrid::setImageBounds(cv::Size(imgW, imgH), std::vector<float>(bounds4, bounds4 + 4));
+    if (imgW > 0) {      // imgW <= 0: keep the grid configuration of the last call (worker threads of bench.py share one)
+        GridProbe::reset();
+        OB::FeatureGrid::setImageBounds(cv::Size(imgW, imgH), std::vector<float>(bounds4, bounds4 + 4));
+    }
     FramePtr f1 = make_frame(k1, ud1, d1, n1), f2 = make_frame(k2, ud2, d2, n2);
     OP::FtAssocOrbSlam m(nnratio, checkOri != 0);
     std::vector<int> v = m.matchV(f1, f2);

@@ -124,7 +124,9 @@ def quadtree(xyr, minX, maxX, minY, maxY, N):
 
 
 def match_window(k1, ud1, d1, k2, ud2, d2, W, H, bounds=None, nnratio=0.6, check_ori=True):
-    """FeatureGrid::setImageBounds(Size(W, H), bounds) + FtAssocOrbSlam::matchV(frame1, frame2)."""
+    """FeatureGrid::setImageBounds(Size(W, H), bounds) + FtAssocOrbSlam::matchV(frame1, frame2).  W <= 0 keeps the grid
+    configuration of the previous call (the reference configures it once per process; bench.py's worker threads set it
+    once and then match concurrently)."""
     k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2)
     ud1 = np.ascontiguousarray(ud1, np.float32); ud2 = np.ascontiguousarray(ud2, np.float32)
     d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)

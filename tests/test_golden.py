@@ -82,12 +82,20 @@ def test_cuda_matches_golden(path, cuda_required):
                 assert len(ctx.level_keypoints(f, l)) == g[f"f{f}_level_count"][l]
         assert bad <= DESC_TOL * int(n.sum()), f"{bad} descriptors differ from the cv2 fixtures"
         if len(frames) > 1:
+            # unconditional: with bit-equal descriptors the frozen answer, otherwise (inside the 0.1 % tolerance) the
+            # oracle matcher on the GPU's own descriptors
+            from oracle import orb_oracle as oo
+
+            def want(key, **kw):
+                if bad == 0:
+                    return g[key]
+                k1, k2 = kps[0, :n[0]], kps[1, :n[1]]
+                return oo.match_window(k1, np.stack([k1["x"], k1["y"]], 1), desc[0, :n[0]], k2,
+                                       np.stack([k2["x"], k2["y"]], 1), desc[1, :n[1]], oo.grid_for(W, H), **kw)
             m, nm = ctx.match_window_frames([(0, 1)], capi.grid_for(W, H))
-            if bad == 0:
-                assert np.array_equal(m[0, :n[0]], g["matches12"])
+            assert np.array_equal(m[0, :n[0]], want("matches12"))
             m2, _ = ctx.match_window_frames([(0, 1)], capi.grid_for(W, H), check_ori=False)
-            if bad == 0:
-                assert np.array_equal(m2[0, :n[0]], g["matches12_noori"])
+            assert np.array_equal(m2[0, :n[0]], want("matches12_noori", check_ori=False))
             d1 = g["f0_desc"][:400]; d2 = g["f1_desc"][:500]
             for norm in (0, 1):
                 i0, i1, f0, f1, ps = ctx.match_bf_knn2(d1, d2, norm, 0.7)

@@ -26,7 +26,19 @@ CASES = [  # H, W, nFeatures, seed, lowtex
     (260, 340, 300, 5, True),         # near the minimum size
     (300, 900, 700, 9, False),        # 3:1 panorama, nIni = 3
     (2160, 3840, 8000, 24, False),    # config 4 (4K stress): 108 x 60 cells at level 0, 18 FAST segments per cell row
+    (376, 1241, 10000, 33, False),    # config 2 in the front end's x5 init mode (FE_SlamMonoV.cpp:247): 2172 nodes at level 0
+    (2160, 3840, 40000, 25, False),   # config 4 in the x5 mode: 8687 level-0 nodes
+    (2160, 3840, 60000, 26, False),   # 13030 level-0 nodes: more sort records than the 12000 the CTA sorts in shared memory -> the global-memory sort path
 ]
+
+
+def _oracle_matches_on(kps, desc, n, a, b, grid, **kw):
+    """The oracle matcher on the GPU's OWN keypoints and descriptors of frames a, b: a valid expectation even when a
+    descriptor differs from the oracle's inside the 0.1 % tolerance, so match assertions never have to be gated on
+    descriptor equality (keypoints are asserted byte-equal separately)."""
+    k1, k2 = kps[a, :n[a]], kps[b, :n[b]]
+    return oo.match_window(k1, np.stack([k1["x"], k1["y"]], 1), desc[a, :n[a]], k2, np.stack([k2["x"], k2["y"]], 1),
+                           desc[b, :n[b]], grid, **kw)
 
 
 @pytest.fixture(scope="module")
@@ -192,6 +204,50 @@ def test_window_matcher_parity(ctxs):
             assert (ref >= 0).sum() > 20
 
 
+def test_config1_sequence_100_frames(ctxs):
+    """BASELINE.json configs[0] as SURVEY 8(d) spells it: 752x480, 1000 keypoints, 100 frames (frame t shifted by
+    (2t, t) px), every frame against the oracle, frame 0 matched against frames 1, 10, 50, 99."""
+    H, W, nf = 480, 752, 1000
+    fr = sequence(H, W, 24, 100, step=(2, 1))
+    ctx = _ctx(ctxs, nf)
+    pairs = [(0, 1), (0, 10), (0, 50), (0, 99)]
+    n, mono, kps, desc, m, nm = ctx.detect_match_batch(fr, pairs, capi.grid_for(W, H))
+    o = oo.OrbOracle(nf)
+    bad = 0
+    for f in range(len(fr)):
+        mo, ko, do = o.detect(fr[f])
+        assert mono[f] == mo and n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes(), f
+        bad += int((desc[f, :n[f]] != do).any(axis=1).sum())
+    assert bad <= DESC_TOL * int(n.sum())
+    for q, (a, b) in enumerate(pairs):
+        want = _oracle_matches_on(kps, desc, n, a, b, oo.grid_for(W, H))
+        assert np.array_equal(m[q, :n[a]], want) and nm[q] == (want >= 0).sum()
+    assert nm[0] > 100
+
+
+def test_cuda_equals_reference_build(ctxs):
+    """The CUDA path against the REFERENCE's own classes (oracle/_ref, compiled unchanged from /root/reference and
+    carried to this box prebuilt) with no restatement in between: detect and matchV on a KITTI-shaped stereo pair."""
+    from oracle import ref_lib as rl
+    if not rl.available():
+        pytest.skip("oracle/_ref/libnav24_ref.so did not travel to this box")
+    H, W, nf = 376, 1241, 2000
+    fr = sequence(H, W, 42, 2, step=(11, 0))
+    ctx = _ctx(ctxs, nf)
+    n, mono, kps, desc, m, nm = ctx.detect_match_batch(fr, [(0, 1)], capi.grid_for(W, H))
+    r = rl.RefOrb(nf)
+    bad = 0
+    for f in range(2):
+        mr, kr, dr = r.detect(fr[f])
+        assert mono[f] == mr and n[f] == len(kr) and kps[f, :n[f]].tobytes() == kr.tobytes()
+        bad += int((desc[f, :n[f]] != dr).any(axis=1).sum())
+    assert bad <= DESC_TOL * int(n.sum())
+    k1, k2 = kps[0, :n[0]], kps[1, :n[1]]
+    want = rl.match_window(k1, np.stack([k1["x"], k1["y"]], 1), desc[0, :n[0]], k2, np.stack([k2["x"], k2["y"]], 1),
+                           desc[1, :n[1]], W, H)
+    assert np.array_equal(m[0, :n[0]], want) and nm[0] == (want >= 0).sum() and nm[0] > 100
+
+
 def test_window_matcher_adversarial(ctxs):
     """Many near-identical descriptors: steals, ties and the >32-candidate slow path."""
     ctx = _ctx(ctxs, 1000)
@@ -274,10 +330,10 @@ def test_fused_detect_match_chunked(ctxs, monkeypatch):
                 mo, ko, do = ref[f]
                 assert mono[f] == mo and n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes()
                 exact &= np.array_equal(desc[f, :n[f]], do)
-            if exact:
-                for q, (a, b) in enumerate(pairs):
-                    assert np.array_equal(m[q, :n[a]], mref[q]), (chunk, q)
-                    assert nm[q] == (mref[q] >= 0).sum()
+            for q, (a, b) in enumerate(pairs):
+                want = mref[q] if exact else _oracle_matches_on(kps, desc, n, a, b, grid_o)
+                assert np.array_equal(m[q, :n[a]], want), (chunk, q)
+                assert nm[q] == (want >= 0).sum()
             # device-resident form, twice back to back (asynchronous), then fetch
             padded = np.zeros((len(fr), H, 1248), np.uint8); padded[:, :, :W] = fr
             dptr = capi.C.c_void_p()
@@ -327,10 +383,7 @@ def test_batch_schedule_invariance_at_bench_scale(ctxs, monkeypatch):
     for f, (mo, ko, do) in ref.items():
         assert mono[f] == mo and kps[f, :n[f]].tobytes() == ko.tobytes()
     for q, (a, b) in ((48, (0, 95)), (49, (7, 40))):
-        (_, k1, d1), (_, k2, d2) = ref[a], ref[b]
-        if np.array_equal(desc[a, :n[a]], d1) and np.array_equal(desc[b, :n[b]], d2):
-            mref = oo.match_window(k1, np.stack([k1["x"], k1["y"]], 1), d1, k2, np.stack([k2["x"], k2["y"]], 1), d2, oo.grid_for(W, H))
-            assert np.array_equal(m[q, :n[a]], mref)
+        assert np.array_equal(m[q, :n[a]], _oracle_matches_on(kps, desc, n, a, b, oo.grid_for(W, H)))
 
     # two contexts driven from two host threads at once (bench.py's e2e loop) give the same answers
     out = [None, None]
@@ -374,8 +427,7 @@ def test_4k_pair_detect_and_match(cuda_required):
         (_, k1, d1), (_, k2, d2) = ref
         mref = oo.match_window(k1, np.stack([k1["x"], k1["y"]], 1), d1, k2, np.stack([k2["x"], k2["y"]], 1), d2, oo.grid_for(W, H))
         assert (mref >= 0).sum() > 200
-        if exact:
-            assert np.array_equal(m[0, :n[0]], mref)
+        assert np.array_equal(m[0, :n[0]], mref if exact else _oracle_matches_on(kps, desc, n, 0, 1, oo.grid_for(W, H)))
     finally:
         ctx.close()
 

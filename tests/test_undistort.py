@@ -112,15 +112,21 @@ def test_cuda_fused_detect_undistort_match(cuda_required):
         assert kps[0, :n[0]].tobytes() == g["f0_kps"].tobytes() and kps[1, :n[1]].tobytes() == g["f1_kps"].tobytes()
         ud = ctx.fetch_undistorted(2)
         assert ud[0, :n[0]].tobytes() == G["match_ud1"].tobytes() and ud[1, :n[1]].tobytes() == G["match_ud2"].tobytes()
-        if np.array_equal(desc[0, :n[0]], g["f0_desc"]) and np.array_equal(desc[1, :n[1]], g["f1_desc"]):
-            assert np.array_equal(m[0, :n[0]], G["match_matches12"])
+        exact = np.array_equal(desc[0, :n[0]], g["f0_desc"]) and np.array_equal(desc[1, :n[1]], g["f1_desc"])
+
+        def want(frozen, ud1, ud2, ogrid):      # unconditional: the frozen answer, or the oracle on the GPU's own descriptors
+            if exact:
+                return frozen
+            return oo.match_window(kps[0, :n[0]], ud1, desc[0, :n[0]], kps[1, :n[1]], ud2, desc[1, :n[1]], ogrid)
+        assert np.array_equal(m[0, :n[0]], want(G["match_matches12"], ud[0, :n[0]], ud[1, :n[1]],
+                                                oo.grid_for(752, 480, tuple(float(x) for x in b))))
         # the separate device-resident matcher sees the same coordinates
         m2, _ = ctx.match_window_frames([(0, 1)], grid)
         assert np.array_equal(m2[0, :n[0]], m[0, :n[0]])
         # back to pinhole: the plain fixture answer
         ctx.set_camera(None)
         n, mono, kps, desc, m, nm = ctx.detect_match_batch(frames, [(0, 1)], capi.grid_for(752, 480))
-        if np.array_equal(desc[0, :n[0]], g["f0_desc"]) and np.array_equal(desc[1, :n[1]], g["f1_desc"]):
-            assert np.array_equal(m[0, :n[0]], g["matches12"])
+        xy = [np.stack([kps[f, :n[f]]["x"], kps[f, :n[f]]["y"]], 1) for f in range(2)]
+        assert np.array_equal(m[0, :n[0]], want(g["matches12"], xy[0], xy[1], oo.grid_for(752, 480)))
     finally:
         ctx.close()

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (ncu --set full) into one row per launch: duration, DRAM bytes, throughput %,
-occupancy, registers, top stall.  Usage: python tools/ncu_summary.py gpurun_out/prof_X.ncu-rep [out.md]"""
+occupancy, registers, pipe utilisation, instruction counts.
+Usage: python tools/ncu_summary.py gpurun_out/prof_X.ncu-rep [out.md [frames_per_launch]]
+The first line of out.md records the frames one launch processed (bench.py scales DRAM bytes per frame from it)."""
 import csv
 import io
 import subprocess
@@ -24,6 +26,11 @@ WANT = [
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
     ("smsp__inst_executed.sum", "inst"),
+    ("smsp__thread_inst_executed.sum", "tinst"),
+    ("sm__inst_executed_pipe_xu.sum", "xu_inst"),          # POPC / F2I / MUFU issue here on sm_100 (BASELINE metric: the pipe that issues POPC)
+    ("sm__inst_executed_pipe_alu.sum", "alu_inst"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
 ]
 
 
@@ -59,7 +66,7 @@ def main():
                     cells.append(f"{to_us(v, u):.1f}us")
                 elif s.startswith("dram_"):
                     cells.append(f"{to_bytes(v, u) / 1e6:.1f}MB")
-                elif s == "inst":
+                elif s in ("inst", "tinst", "xu_inst", "alu_inst", "smem_conflicts", "smem_wavefronts"):
                     cells.append(f"{float(v.replace(',', '')) / 1e6:.1f}M")
                 else:
                     cells.append(f"{float(v.replace(',', '')):.1f}" if "." in v else v)
@@ -67,6 +74,8 @@ def main():
                 cells.append(v)
         out.append("| " + " | ".join(cells) + " |")
     s = "\n".join(out)
+    if len(sys.argv) > 3:
+        s = f"<!-- frames_per_launch: {int(sys.argv[3])} -->\n" + s
     print(s)
     if len(sys.argv) > 2:
         open(sys.argv[2], "w").write(s + "\n")
