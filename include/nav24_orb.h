@@ -223,6 +223,29 @@ int nav24_debug_last_kernel_ms(nav24_orb* ctx, float* ms);
  * whatever std::sort leaves, which the device code must reproduce exactly. */
 int nav24_debug_sort_u32(nav24_orb* ctx, const uint32_t* keys, int n, int32_t* perm);
 
+/* ---- image ingest ------------------------------------------------------------------------ */
+/* A ring of pinned host slots the camera decodes into directly, replacing the four full-image host copies the
+ * reference makes per frame (cv::imread + image.clone() at core/sensor/camera/Camera.cpp:454-455, the clone in
+ * core/sensorData/Image.hpp:22, two more clones + cv::cvtColor at core/frontEnd/FE_SlamMonoV.cpp:90-94): the frame
+ * goes from the decoder's output buffer to the device in one asynchronous copy, and colour frames (channels = 3,
+ * interleaved BGR as cv::imread / cv::imdecode produce) are converted to grey ON THE DEVICE with cv::cvtColor's
+ * COLOR_BGR2GRAY fixed point, so detect sees CV_8UC1 as OP_FtDtOrbSlam.cpp:853 asserts.  channels = 1: grey. */
+typedef struct nav24_ingest nav24_ingest;
+int nav24_ingest_create(nav24_orb* ctx, int width, int height, int channels, int n_slots, nav24_ingest** out);
+void nav24_ingest_destroy(nav24_ingest* ring);
+/* Host address of slot `slot` (height rows of width*channels bytes, tightly packed); NULL when out of range. */
+uint8_t* nav24_ingest_slot(nav24_ingest* ring, int slot);
+size_t nav24_ingest_slot_bytes(const nav24_ingest* ring);
+/* detect (and, with pairs, windowed matching: pairs_ab index the frames of THIS call) on slots [first_slot,
+ * first_slot + n_frames); arguments and results as nav24_orb_detect_batch / nav24_orb_detect_match_batch.  The grey
+ * level 0 the device computed is readable with nav24_orb_get_level(ctx, frame, 0, 0, ...). */
+int nav24_ingest_detect(nav24_ingest* ring, int first_slot, int n_frames, nav24_kp* kps, uint8_t* desc, int cap,
+                        int* n_out, int* mono_out);
+int nav24_ingest_detect_match(nav24_ingest* ring, int first_slot, int n_frames, nav24_kp* kps, uint8_t* desc, int cap,
+                              int* n_out, int* mono_out, int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid,
+                              float window, float nnratio, int th_low, int check_ori, int32_t* matches12, int mcap,
+                              int* n_matches);
+
 /* ---- memory helpers (so that a C/C++ host needs no CUDA headers) --------------------------- */
 int nav24_host_alloc(size_t bytes, void** out);   /* pinned host memory: makes detect_batch copies asynchronous */
 int nav24_host_free(void* p);

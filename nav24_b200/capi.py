@@ -109,6 +109,13 @@ def lib():
     L.nav24_match_bf_knn2.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp]
     L.nav24_debug_sort_u32.argtypes = [vp, vp, C.c_int, vp]
     L.nav24_debug_last_kernel_ms.argtypes = [vp, vp]
+    L.nav24_ingest_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.nav24_ingest_destroy.argtypes = [vp]; L.nav24_ingest_destroy.restype = None
+    L.nav24_ingest_slot.argtypes = [vp, C.c_int]; L.nav24_ingest_slot.restype = vp
+    L.nav24_ingest_slot_bytes.argtypes = [vp]; L.nav24_ingest_slot_bytes.restype = C.c_size_t
+    L.nav24_ingest_detect.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    L.nav24_ingest_detect_match.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(GridCfg),
+                                            C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, vp]
     L.nav24_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.nav24_host_free.argtypes = [vp]
     L.nav24_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -385,3 +392,50 @@ class OrbContext:
         f0 = np.zeros(n1, np.float32); f1 = np.zeros(n1, np.float32); ps = np.zeros(n1, np.uint8)
         self._check(self.L.nav24_match_bf_knn2(self.h, _p(d1), n1, _p(d2), len(d2), norm, ratio, _p(i0), _p(i1), _p(f0), _p(f1), _p(ps)))
         return i0, i1, f0, f1, ps
+
+
+class IngestRing:
+    """nav24_ingest: pinned slots the camera decodes into (grey or interleaved BGR), detect without a second host copy."""
+
+    def __init__(self, ctx, width, height, channels, n_slots):
+        self.ctx, self.w, self.h, self.ch, self.n = ctx, width, height, channels, n_slots
+        self.h_ = C.c_void_p()
+        ctx._check(ctx.L.nav24_ingest_create(ctx.h, width, height, channels, n_slots, C.byref(self.h_)))
+
+    def close(self):
+        if getattr(self, "h_", None):
+            self.ctx.L.nav24_ingest_destroy(self.h_)
+            self.h_ = None
+
+    __del__ = close
+
+    def slot(self, k):
+        """numpy view of slot k: [H, W] (grey) or [H, W, 3] (BGR)."""
+        ptr = self.ctx.L.nav24_ingest_slot(self.h_, k)
+        if not ptr:
+            raise IndexError("slot outside the ring")
+        nb = self.ctx.L.nav24_ingest_slot_bytes(self.h_)
+        buf = (C.c_uint8 * nb).from_address(ptr)
+        shape = (self.h, self.w) if self.ch == 1 else (self.h, self.w, 3)
+        return np.frombuffer(buf, np.uint8).reshape(shape)
+
+    def detect_match(self, first, n_frames, pairs=(), grid=None, window=100.0, nnratio=0.6, th_low=50, check_ori=True):
+        ctx = self.ctx
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        P = len(pairs)
+        # (the workspace must know the shape before max_keypoints is final: a first call may report E_CAPACITY)
+        cap = ctx.max_keypoints()
+        for _ in range(2):
+            kps = np.zeros((n_frames, cap), KP_DTYPE); desc = np.zeros((n_frames, cap, 32), np.uint8)
+            n = np.zeros(n_frames, np.int32); mono = np.zeros(n_frames, np.int32)
+            m = np.full((max(P, 1), max(cap, ctx.max_keypoints())), -1, np.int32); nm = np.zeros(max(P, 1), np.int32)
+            rc = ctx.L.nav24_ingest_detect_match(self.h_, first, n_frames, _p(kps), _p(desc), cap, _p(n), _p(mono), P,
+                                                 _p(pairs) if P else None, C.byref(grid) if grid is not None else None,
+                                                 window, nnratio, th_low, int(check_ori), _p(m) if P else None, m.shape[1],
+                                                 _p(nm) if P else None)
+            if rc == E_CAPACITY:
+                cap = max(ctx.max_keypoints(), int(n.max()) if n.max() > 0 else cap)
+                continue
+            break
+        ctx._check(rc)
+        return n, mono, kps, desc, m[:P], nm[:P]

@@ -630,7 +630,7 @@ namespace {
 struct MatchPlan;
 int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, size_t stride, size_t frame_stride,
                 const MatchPlan* mp, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
-                int32_t* matches12, int mcap, int* n_matches, int chunkOverride = 0, bool timedStages = false);
+                int32_t* matches12, int mcap, int* n_matches, int chunkOverride = 0, bool timedStages = false, int channels = 1);
 }  // namespace
 
 // ==========================================================================================
@@ -823,11 +823,13 @@ struct MatchPlan {
 //                         returns after enqueueing.
 int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, size_t stride, size_t frame_stride,
                 const MatchPlan* mp, nav24_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_out,
-                int32_t* matches12, int mcap, int* n_matches, int chunkOverride, bool timedStages) {
+                int32_t* matches12, int mcap, int* n_matches, int chunkOverride, bool timedStages, int channels) {
     const FrameGeom& g = ctx->g;
     const bool fromHost = hostGray != nullptr;
-    const bool tight = fromHost && (stride == (size_t)w) && (B == 1 || frame_stride == stride * (size_t)h);
-    const size_t tightFrame = (size_t)w * h;
+    // channels == 3: interleaved BGR frames (colour ingest), converted to grey on the device
+    const bool tight = fromHost && (stride == (size_t)w * channels) && (B == 1 || frame_stride == stride * (size_t)h);
+    const size_t tightFrame = (size_t)w * h * channels;
+    if (fromHost && channels != 1 && !tight) return ctx->fail(NAV24_E_BADARG, "BGR frames must be tightly packed (stride = 3 * width)");
     uint8_t* l0 = (uint8_t*)ctx->bL0.ptr;
     if (fromHost) {
         if (tight) CK(ctx->bL0Tight.ensure((size_t)ctx->wsB * tightFrame + 16));
@@ -944,7 +946,7 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
         if (graphed) {
             unsigned long long key = 1469598103934665603ull;
             for (unsigned long long v : {(unsigned long long)w, (unsigned long long)h, (unsigned long long)ctx->prm.n_features,
-                                         ctx->wsGen, (unsigned long long)ctx->cam.model, (unsigned long long)tight,
+                                         ctx->wsGen, (unsigned long long)ctx->cam.model, (unsigned long long)tight + 2ull * channels,
                                          (unsigned long long)(uintptr_t)cs})
                 key = (key ^ v) * 1099511628211ull;
             unsigned long long camBits = 0;
@@ -960,7 +962,8 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
                 if (eb != cudaSuccess && ctx->trace) fprintf(stderr, "[nav24 trace] begin capture failed: %s\n", cudaGetErrorString(eb));
                 if (eb == cudaSuccess) {
                     if (tight)
-                        ctx->launches += launch_repack((const uint8_t*)ctx->bL0Tight.ptr, w, h, l0, ctx->l0Pitch, 1, cs);
+                        ctx->launches += channels == 3 ? launch_bgr2gray((const uint8_t*)ctx->bL0Tight.ptr, w, h, l0, ctx->l0Pitch, 1, cs)
+                                                       : launch_repack((const uint8_t*)ctx->bL0Tight.ptr, w, h, l0, ctx->l0Pitch, 1, cs);
                     const int prc = run_pipeline(ctx, 0, 1, cs, false);
                     const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
                     if (prc == NAV24_OK && ee == cudaSuccess && graph &&
@@ -988,9 +991,12 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
             }
         }
         if (!replayed) {
-            if (fromHost && tight)
-                ctx->launches += launch_repack((const uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame, w, h,
-                                               l0 + (size_t)f0 * ctx->l0Pitch * h, ctx->l0Pitch, c, cs);
+            if (fromHost && tight) {
+                const uint8_t* src = (const uint8_t*)ctx->bL0Tight.ptr + f0 * tightFrame;
+                uint8_t* dst = l0 + (size_t)f0 * ctx->l0Pitch * h;
+                ctx->launches += channels == 3 ? launch_bgr2gray(src, w, h, dst, ctx->l0Pitch, c, cs)
+                                               : launch_repack(src, w, h, dst, ctx->l0Pitch, c, cs);
+            }
             rc = run_pipeline(ctx, f0, c, cs, stages);
             if (rc != NAV24_OK) return rc;
         }
@@ -1518,6 +1524,75 @@ int nav24_device_alloc(size_t bytes, void** out) {
 int nav24_device_free(void* p) { return cudaFree(p) == cudaSuccess ? NAV24_OK : NAV24_E_CUDA; }
 int nav24_memcpy_h2d(void* dst, const void* src, size_t bytes) {
     return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? NAV24_OK : NAV24_E_CUDA;
+}
+
+}  // extern "C"
+
+// ---- image ingest ---------------------------------------------------------------------------------
+struct nav24_ingest {
+    nav24_orb* ctx = nullptr;
+    int w = 0, h = 0, ch = 1, slots = 0;
+    size_t slotBytes = 0;
+    uint8_t* host = nullptr;      // pinned: [slots][h][w * ch]
+};
+
+extern "C" {
+
+int nav24_ingest_create(nav24_orb* ctx, int width, int height, int channels, int n_slots, nav24_ingest** out) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx || !out) return NAV24_E_BADARG;
+        *out = nullptr;
+        if (width <= 0 || height <= 0 || (channels != 1 && channels != 3) || n_slots <= 0)
+            return ctx->fail(NAV24_E_BADARG, "ingest ring: width, height > 0, channels 1 (grey) or 3 (BGR), slots > 0");
+        cudaSetDevice(ctx->device);
+        nav24_ingest* r = new nav24_ingest();
+        r->ctx = ctx; r->w = width; r->h = height; r->ch = channels; r->slots = n_slots;
+        r->slotBytes = (size_t)width * height * channels;
+        if (cudaHostAlloc((void**)&r->host, r->slotBytes * n_slots + 16, cudaHostAllocDefault) != cudaSuccess) {
+            delete r;
+            return ctx->fail(NAV24_E_NOMEM, "ingest ring: pinned allocation failed");
+        }
+        *out = r;
+        return NAV24_OK;
+    });
+}
+
+void nav24_ingest_destroy(nav24_ingest* ring) {
+    if (!ring) return;
+    if (ring->host) cudaFreeHost(ring->host);
+    delete ring;
+}
+
+uint8_t* nav24_ingest_slot(nav24_ingest* ring, int slot) {
+    return (ring && slot >= 0 && slot < ring->slots) ? ring->host + (size_t)slot * ring->slotBytes : nullptr;
+}
+size_t nav24_ingest_slot_bytes(const nav24_ingest* ring) { return ring ? ring->slotBytes : 0; }
+
+int nav24_ingest_detect_match(nav24_ingest* ring, int first_slot, int n_frames, nav24_kp* kps, uint8_t* desc, int cap, int* n_out,
+                              int* mono_out, int n_pairs, const int* pairs_ab, const nav24_grid_cfg* grid, float window,
+                              float nnratio, int th_low, int check_ori, int32_t* matches12, int mcap, int* n_matches) {
+    nav24_orb* ctx = ring ? ring->ctx : nullptr;
+    return guarded(ctx, [&]() -> int {
+        if (!ring || !ctx) return NAV24_E_BADARG;
+        if (first_slot < 0 || n_frames <= 0 || first_slot + n_frames > ring->slots)
+            return ctx->fail(NAV24_E_BADARG, "ingest: slot range outside the ring");
+        int rc = check_pairs(ctx, n_pairs, pairs_ab, n_frames, grid);
+        if (rc != NAV24_OK) return rc;
+        rc = ensure_workspace(ctx, ring->w, ring->h, n_frames);
+        if (rc != NAV24_OK) return rc;
+        if (matches12 && mcap < ctx->g.outCap) return ctx->fail(NAV24_E_CAPACITY, "matches12 capacity below nav24_orb_max_keypoints");
+        MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
+        const size_t stride = (size_t)ring->w * ring->ch;
+        return run_chunked(ctx, n_frames, ring->w, ring->h, ring->host + (size_t)first_slot * ring->slotBytes, stride,
+                           stride * ring->h, n_pairs > 0 ? &mp : nullptr, kps, desc, cap, n_out, mono_out, matches12, mcap,
+                           n_matches, 0, false, ring->ch);
+    });
+}
+
+int nav24_ingest_detect(nav24_ingest* ring, int first_slot, int n_frames, nav24_kp* kps, uint8_t* desc, int cap, int* n_out,
+                        int* mono_out) {
+    return nav24_ingest_detect_match(ring, first_slot, n_frames, kps, desc, cap, n_out, mono_out, 0, nullptr, nullptr, 0.f, 0.f, 0, 0,
+                                     nullptr, 0, nullptr);
 }
 
 }  // extern "C"

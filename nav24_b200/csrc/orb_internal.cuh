@@ -15,8 +15,11 @@ constexpr int kBlurTileRows = 35;                    // rows per warp tile of bl
 constexpr int kBlurCtaRows = 4 * kBlurTileRows;     // rows per CTA tile (four warp tiles stacked)
 constexpr int kBlurBoxW = 160, kBlurBoxH = kBlurCtaRows + 6;   // TMA box: 128 px + 16-byte aligned halos, 3 halo rows each side
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
-constexpr int kOriBoxW = 48, kOriBoxH = 31;    // TMA box of the orientation patch: 31 px + <= 15 px of alignment slack, 16-B multiple
-constexpr int kDescBoxW = 80, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px + <= 15 px of alignment slack = 52 -> 64 would do, but a 20-word row pitch spreads the hot central columns over all 32 banks (16 words: 5.2 wavefronts per gather)
+constexpr int kOriBoxW = 32, kOriBoxH = 31;    // TMA box of the orientation patch: 31 px rounded up to a 16-byte multiple; the box starts AT the patch (tensor-map
+                                               // coordinates are element-granular, only the box width has to be a multiple of 16 bytes)
+constexpr int kDescBoxW = 48, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px -> 48.  A 12-word row pitch costs 3.1 shared-memory wavefronts per gather
+                                               // of the rotated pattern, the same as the 20-word pitch of the round-1 80-byte box (16 words: 4.8); per keypoint
+                                               // 2768 bytes cross L2 instead of 4448 (describe_kernel ran at 70 % of L2 throughput)
 constexpr int kFastThreads = 256;   // threads per CTA of fast_band_kernel
 constexpr int kFastMaxSegCells = 8; // cells of one FAST segment (TMA boxes are <= 256 px wide, cells >= 35 px)
 constexpr int kFastQueueCap = 3072; // stage A survivors one CTA queues (typ. 700 of 8400 pixels); beyond: the dense path
@@ -138,6 +141,8 @@ constexpr int kResizeCtaRows = 64;     // target destination rows per CTA (4 war
 // launchers (orb_kernels.cu); each returns the number of kernels launched
 // tight (pitch = w) host-order frames -> 16-byte aligned pitch (TMA needs it); returns 1
 int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s);
+// tight interleaved BGR host-order frames -> grey at the aligned pitch (cv::cvtColor COLOR_BGR2GRAY fixed point); returns 1
+int launch_bgr2gray(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s);
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s);
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);

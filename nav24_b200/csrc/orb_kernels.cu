@@ -78,6 +78,35 @@ __global__ void __launch_bounds__(256) repack_kernel(const uint8_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// K0b  colour ingest: interleaved 8-bit BGR frames, as cv::imread / cv::imdecode leave them and as they
+// arrive from the host in ONE contiguous copy, -> grey level 0 at the 16-byte aligned pitch.  Replaces the
+// cv::cvtColor(img, gray, COLOR_BGR2GRAY) of FE_SlamMonoV.cpp:92-94 (whose result the reference then forgets to hand to
+// the detector, which asserts CV_8UC1 at OP_FtDtOrbSlam.cpp:853) with OpenCV's 15-bit fixed point
+//   grey = (3735 B + 19235 G + 9798 R + 16384) >> 15          (pinned against cv2 4.13, tests/test_ingest.py).
+// One thread = 4 pixels = 12 source bytes: the four aligned words covering them are shifted to byte 0 (3 SHF), every
+// pixel's (B, G, R) is brought to bytes 0..2 by one PRMT, B and G weigh in by one DP2A, R by one IMAD.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t* __restrict__ src, int w, int h, uint8_t* __restrict__ dst,
+                                                       int dPitch) {
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x4 >= w || y >= h) return;
+    const long long f = blockIdx.z;
+    const uint8_t* s0 = src + ((f * h + y) * (long long)w + x4) * 3;
+    const unsigned sh = ((unsigned)(uintptr_t)s0 & 3u) * 8u;
+    const unsigned* a = reinterpret_cast<const unsigned*>((uintptr_t)s0 & ~(uintptr_t)3);
+    // (the staging buffer has 16 bytes of slack: the last pixels of the last row may over-read)
+    const unsigned w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = __ldg(a + 3);
+    const unsigned lo = __funnelshift_r(w0, w1, sh), mid = __funnelshift_r(w1, w2, sh), hi = __funnelshift_r(w2, w3, sh);
+    // lo = B0 G0 R0 B1 | mid = G1 R1 B2 G2 | hi = R2 B3 G3 R3
+    const unsigned p0 = lo, p1 = __byte_perm(lo, mid, 0x0543), p2 = __byte_perm(mid, hi, 0x0432), p3 = hi >> 8;
+    const unsigned kBG = 3735u | (19235u << 16);
+    auto grey = [&](unsigned p) { return (__dp2a_lo(kBG, p, 16384u) + ((p >> 16) & 0xffu) * 9798u) >> 15; };
+    const unsigned out = grey(p0) | (grey(p1) << 8) | (grey(p2) << 16) | (grey(p3) << 24);
+    *reinterpret_cast<unsigned*>(dst + (f * h + y) * (long long)dPitch + x4) = out;      // pitch >= align128(w): the tail fits
+}
+
+// ------------------------------------------------------------------------------------------
 // K1  pyramid level l-1 -> l.  cv::resize(INTER_LINEAR) on CV_8UC1 = 11-bit fixed-point separable
 // bilinear; replaces ComputePyramid (OP_FtDtOrbSlam.cpp:936-960).
 // One CTA = 128 destination columns x 4*rows destination rows; its source pixels arrive as ONE TMA box (x start rounded
@@ -1136,24 +1165,28 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
                      : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-            "l"(&mapsBlur.m[l]), "r"((cx - 18) & ~15), "r"(cy - 18), "r"(f + p.frameBase), "r"(bar)
+            "l"(&mapsBlur.m[l]), "r"(cx - 18), "r"(cy - 18), "r"(f + p.frameBase), "r"(bar)
             : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                 dst + kDescOriOff),
-            "l"(&mapsOri.m[l]), "r"((cx - 15) & ~15), "r"(cy - 15), "r"(f + p.frameBase), "r"(bar)
+            "l"(&mapsOri.m[l]), "r"(cx - 15), "r"(cy - 15), "r"(f + p.frameBase), "r"(bar)
             : "memory");
     };
     // (keeping the lane's eight test pairs in registers across keypoints was measured slower: 96 registers per thread
     // cost more in occupancy than the 32 L1 wavefronts per keypoint cost in the load pipe)
     const float4* pat = reinterpret_cast<const float4*>(kPatternT.v) + lane;
-    int wpos[9], wrow[9];                       // orientation: word k*32+lane of the 31 x 9-word patch -> (tile word, v)
+    // orientation: the 31 x 8 words of the patch are dealt over the lanes, word k*32+lane -> (tile word, row v, weight entry);
+    // the box starts at the patch, so the weights (alignment 0 of the host table, 9 entries per row) are per-lane constants
+    int wpos[8], wrow[8];
+    uint2 wt[8];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int idx = min(k * 32 + lane, 278);
-        const int r = (idx * 57) >> 9, c = idx - r * 9;             // idx / 9 for idx < 288
-        wpos[k] = r * (kOriBoxW / 4) + c;
+    for (int k = 0; k < 8; ++k) {
+        const int idx = min(k * 32 + lane, 247);
+        const int r = idx >> 3, c = idx & 7;
+        wpos[k] = idx;
         wrow[k] = r - 15;
+        wt[k] = __ldg(reinterpret_cast<const uint2*>(p.oriTab) + r * 9 + c);
     }
 
     int lCur = 0, lNext = 0, lNext2 = 0;
@@ -1174,13 +1207,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         const LevelGeom& L = g.lv[l];
         const uint8_t* s_blur = &s_buf[wid][st][0];
         const uint8_t* s_ori = s_blur + kDescOriOff;
-        // this lane's orientation weights while the boxes land
-        const int off = (cx - 15) & 15;                                            // 0..15
-        const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279 + lane;
-        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori) + (off >> 2);
-        uint2 wt[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) wt[k] = __ldg(tab + min(k * 32, 278 - lane));
+        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori);
         {
             unsigned done = 0;
             const unsigned bar = bar0 + 8 * st, par = (phase >> st) & 1u;
@@ -1193,12 +1220,12 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             }
             phase ^= 1u << st;
         }
-        // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane;
-        // the lane's word positions and row numbers do not depend on the keypoint: wpos / wrow, set up once per warp)
+        // IC_Angle: integer moments of the 31-px disc by DP4A over the words of the patch (248 words, 8 per lane; word
+        // positions, row numbers and weights do not depend on the keypoint: set up once per warp)
         int m10 = 0, m01 = 0;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (k * 32 + lane < 279) {
+        for (int k = 0; k < 8; ++k) {
+            if (k * 32 + lane < 248) {
                 const unsigned w = ow[wpos[k]];
                 asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[k].x));      // u8 pixels x s8 offsets
                 m01 += wrow[k] * (int)__dp4a(w, wt[k].y, 0u);
@@ -1219,7 +1246,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         // bits (float bits = 0x4B400000 + n), one full-rate FADD instead of a quarter-rate F2I per coordinate (1024 per
         // keypoint); the bias of row and column is folded into the base address.
         const float kMagic = 12582912.f;
-        const unsigned pcA = smem_u32(s_blur) + (unsigned)(18 * kDescBoxW + 18 + ((cx - 18) & 15)) -
+        const unsigned pcA = smem_u32(s_blur) + (unsigned)(18 * kDescBoxW + 18) -
                              (unsigned)(kDescBoxW + 1) * 0x4B400000u;               // the keypoint, minus the biases
         unsigned val = 0;
 #pragma unroll
@@ -1259,6 +1286,12 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
 int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s) {
     dim3 grid((dPitch / 16 + 63) / 64, (h + 3) / 4, B), block(64, 4);
     repack_kernel<<<grid, block, 0, s>>>(src, w, h, dst, dPitch);
+    return 1;
+}
+
+int launch_bgr2gray(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s) {
+    dim3 grid((w + 255) / 256, (h + 3) / 4, B), block(64, 4);
+    bgr2gray_kernel<<<grid, block, 0, s>>>(src, w, h, dst, dPitch);
     return 1;
 }
 

@@ -60,6 +60,7 @@ def lib():
         L.orc_fast_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_int]
         L.orc_fast_atan2.restype = C.c_float
         L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_bgr2gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_quadtree.restype = C.c_int
         L.orc_quadtree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_sort_sized.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -178,6 +179,14 @@ def fast_u8(img, t):
     out = np.zeros((cap, 3), np.float32)
     n = lib().orc_fast_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], t, _p(out), cap)
     return out[:n].copy()
+
+
+def bgr2gray(bgr):
+    """cv::cvtColor(COLOR_BGR2GRAY) restatement on an [H, W, 3] uint8 image."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    out = np.zeros(bgr.shape[:2], np.uint8)
+    lib().orc_bgr2gray(_p(bgr), bgr.shape[1], bgr.shape[0], bgr.strides[0], _p(out), out.strides[0])
+    return out
 
 
 def fast_atan2(y, x):
