@@ -246,6 +246,23 @@ int nav24_ingest_detect_match(nav24_ingest* ring, int first_slot, int n_frames, 
                               float window, float nnratio, int th_low, int check_ori, int32_t* matches12, int mcap,
                               int* n_matches);
 
+/* ---- two-view RANSAC scoring -------------------------------------------------------------- */
+/* Replaces the scoring half of TwoViewReconstruction::FindHomography / FindFundamental
+ * (core/operators/mapInit/OP_2ViewReconstruction.cpp:266-365), which the reference runs in two std::threads (:133-134):
+ * CheckHomography (:447-530) and CheckFundamental (:532-610) of ALL n_hyp RANSAC hypotheses in one launch.
+ *   xy1, xy2      n_matches x (x, y): the matched keypoints in match order (mvKeys1[mvMatches12[i].first].pt, ...second)
+ *   H21, H12      n_hyp x 9 row-major: T2inv*Hn*T1 and its inverse per iteration (:302-303); NULL skips the homography
+ *   F21           n_hyp x 9 row-major: T2t*Fn*T1 (:354); NULL skips the fundamental matrix
+ *   sigma, th_h, th_f, th_score   mSigma, mThChiSqScore (5.991), mThChiSqF (3.841), mThChiSqScore
+ *   score_h/f     n_hyp floats, bit-equal to the reference's sequential float sums (IEEE single, no contraction)
+ *   inliers_h/f   optional n_hyp x n_matches bytes (vbCurrentInliers of every iteration)
+ *   best_h/f      optional: the iteration the reference's `if (currentScore > score)` loop keeps (-1: no score above 0)
+ * The minimal-set solvers (ComputeH21 / ComputeF21: 8-point SVDs) stay on the host. */
+int nav24_two_view_score(nav24_orb* ctx, const float* xy1, const float* xy2, int n_matches, const float* H21,
+                         const float* H12, const float* F21, int n_hyp, float sigma, float th_h, float th_f,
+                         float th_score, float* score_h, float* score_f, uint8_t* inliers_h, uint8_t* inliers_f,
+                         int* best_h, int* best_f);
+
 /* ---- memory helpers (so that a C/C++ host needs no CUDA headers) --------------------------- */
 int nav24_host_alloc(size_t bytes, void** out);   /* pinned host memory: makes detect_batch copies asynchronous */
 int nav24_host_free(void* p);

@@ -116,6 +116,8 @@ def lib():
     L.nav24_ingest_detect.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     L.nav24_ingest_detect_match.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, vp, C.POINTER(GridCfg),
                                             C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.nav24_two_view_score.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp,
+                                       vp, vp, ip, ip]
     L.nav24_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.nav24_host_free.argtypes = [vp]
     L.nav24_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -378,6 +380,25 @@ class OrbContext:
         self._check(self.L.nav24_match_window_frames(self.h, P, _p(pairs), C.byref(grid), window, nnratio, th_low, int(check_ori),
                                                      _p(m), cap, _p(nm)))
         return m, nm
+
+    def two_view_score(self, xy1, xy2, H21=None, H12=None, F21=None, sigma=1.0, th_h=5.991, th_f=3.841, th_score=5.991,
+                       want_inliers=True):
+        """CheckHomography / CheckFundamental of every hypothesis.  Returns dict(score_h, score_f, inliers_h, inliers_f,
+        best_h, best_f) (entries of a skipped model are None)."""
+        xy1 = np.ascontiguousarray(xy1, np.float32).reshape(-1, 2); xy2 = np.ascontiguousarray(xy2, np.float32).reshape(-1, 2)
+        n = len(xy1)
+        H21 = None if H21 is None else np.ascontiguousarray(H21, np.float32).reshape(-1, 9)
+        H12 = None if H12 is None else np.ascontiguousarray(H12, np.float32).reshape(-1, 9)
+        F21 = None if F21 is None else np.ascontiguousarray(F21, np.float32).reshape(-1, 9)
+        nh = len(H21) if H21 is not None else len(F21)
+        sh = np.zeros(nh, np.float32) if H21 is not None else None
+        sf = np.zeros(nh, np.float32) if F21 is not None else None
+        ih = np.zeros((nh, n), np.uint8) if (H21 is not None and want_inliers) else None
+        i_f = np.zeros((nh, n), np.uint8) if (F21 is not None and want_inliers) else None
+        bh, bf = C.c_int(-1), C.c_int(-1)
+        self._check(self.L.nav24_two_view_score(self.h, _p(xy1), _p(xy2), n, _p(H21), _p(H12), _p(F21), nh, sigma, th_h, th_f,
+                                                th_score, _p(sh), _p(sf), _p(ih), _p(i_f), C.byref(bh), C.byref(bf)))
+        return {"score_h": sh, "score_f": sf, "inliers_h": ih, "inliers_f": i_f, "best_h": bh.value, "best_f": bf.value}
 
     def debug_sort(self, keys):
         keys = np.ascontiguousarray(keys, np.uint32)

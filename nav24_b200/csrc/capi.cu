@@ -93,7 +93,8 @@ struct nav24_orb {
     TmaMaps mapsRs{};         // m[l]: resize source tiles over level l-1 (resize_kernel producing level l)
     TmaMaps mapsBlurSrc{};    // 160 x 146 source tiles of blur_kernel over the un-blurred levels
     TmaMaps mapsOri{};        // 48 x 31 orientation patches over the un-blurred levels (describe_kernel)
-    TmaMaps mapsBlur{};       // 64 x 37 descriptor patches over the blurred levels (describe_kernel)
+    TmaMaps mapsBlur{};       // 80 x 37 descriptor patches over the blurred levels (describe_kernel)
+    TmaMaps mapsBlurN{};      // 48 x 37: the narrow box for keypoints with little alignment slack
     const void* mapsBlurPtr = nullptr;
     int mapsB = 0;            // frame count the level>=1 maps were encoded for
     const void* mapsPyr = nullptr;
@@ -496,6 +497,9 @@ int encode_maps(nav24_orb* ctx, int B) {
             rc = encode_level_map(ctx, &ctx->mapsBlur.m[l], ctx->p.blur + g.lv[l].boff, g.lv[l].w, g.lv[l].h, ctx->wsB,
                                   g.lv[l].pitch, g.blurFrameBytes, kDescBoxW, kDescBoxH);
             if (rc != NAV24_OK) return rc;
+            rc = encode_level_map(ctx, &ctx->mapsBlurN.m[l], ctx->p.blur + g.lv[l].boff, g.lv[l].w, g.lv[l].h, ctx->wsB,
+                                  g.lv[l].pitch, g.blurFrameBytes, kDescBoxWN, kDescBoxH);
+            if (rc != NAV24_OK) return rc;
         }
         ctx->mapsB = ctx->wsB; ctx->mapsPyr = ctx->p.pyr; ctx->mapsBlurPtr = ctx->p.blur;
     }
@@ -531,7 +535,7 @@ int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
     if (stages) CK(cudaEventRecord(ctx->ev[2], s));
     ctx->launches += launch_quadtree(g, q, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[3], s));
-    ctx->launches += launch_describe(g, q, ctx->mapsBlurSrc, ctx->mapsOri, ctx->mapsBlur, C, s);
+    ctx->launches += launch_describe(g, q, ctx->mapsBlurSrc, ctx->mapsOri, ctx->mapsBlur, ctx->mapsBlurN, C, s);
     if (ctx->cam.model != NAV24_CAM_PINHOLE)      // Calibration::undistort between detect and matchV (FE_SlamMonoV.cpp:115)
         ctx->launches += launch_undistort_frames(ctx->cam, q.outKp, q.nOut, g.outCap, C, q.outUd, s);
     if (stages) CK(cudaEventRecord(ctx->ev[4], s));
@@ -1593,6 +1597,64 @@ int nav24_ingest_detect(nav24_ingest* ring, int first_slot, int n_frames, nav24_
                         int* mono_out) {
     return nav24_ingest_detect_match(ring, first_slot, n_frames, kps, desc, cap, n_out, mono_out, 0, nullptr, nullptr, 0.f, 0.f, 0, 0,
                                      nullptr, 0, nullptr);
+}
+
+}  // extern "C"
+
+// ---- two-view RANSAC scoring -------------------------------------------------------------------------
+extern "C" {
+
+int nav24_two_view_score(nav24_orb* ctx, const float* xy1, const float* xy2, int n_matches, const float* H21, const float* H12,
+                         const float* F21, int n_hyp, float sigma, float th_h, float th_f, float th_score, float* score_h,
+                         float* score_f, uint8_t* inliers_h, uint8_t* inliers_f, int* best_h, int* best_f) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx) return NAV24_E_BADARG;
+        if (n_matches < 0 || n_hyp < 0 || !(sigma > 0.f) || (n_matches > 0 && (!xy1 || !xy2)) || (H21 && !H12) || (H21 && !score_h) ||
+            (F21 && !score_f) || (!H21 && !F21))
+            return ctx->fail(NAV24_E_BADARG, "bad two-view scoring argument");
+        if (best_h) *best_h = -1;
+        if (best_f) *best_f = -1;
+        if (n_hyp == 0) return NAV24_OK;
+        cudaSetDevice(ctx->device);
+        const size_t nb = (size_t)std::max(n_matches, 1), hb = (size_t)n_hyp;
+        // device scratch (shared with the undistortion helpers): points | matrices | scores | inlier masks
+        const size_t oXy = 0, oM = oXy + 2 * nb * 8, oS = oM + 3 * hb * 36, oI = oS + 2 * hb * 4;
+        CK(ctx->bUdTmp.ensure(oI + 2 * hb * nb + 64));
+        char* d = (char*)ctx->bUdTmp.ptr;
+        float* dXy1 = (float*)(d + oXy); float* dXy2 = dXy1 + 2 * nb;
+        float* dH21 = (float*)(d + oM); float* dH12 = dH21 + 9 * hb; float* dF21 = dH12 + 9 * hb;
+        float* dSH = (float*)(d + oS); float* dSF = dSH + hb;
+        uint8_t* dIH = (uint8_t*)(d + oI); uint8_t* dIF = dIH + hb * nb;
+        cudaStream_t s = ctx->stream;
+        if (n_matches > 0) {
+            CK(cudaMemcpyAsync(dXy1, xy1, (size_t)n_matches * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(dXy2, xy2, (size_t)n_matches * 8, cudaMemcpyHostToDevice, s));
+        }
+        if (H21) {
+            CK(cudaMemcpyAsync(dH21, H21, hb * 36, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(dH12, H12, hb * 36, cudaMemcpyHostToDevice, s));
+        }
+        if (F21) CK(cudaMemcpyAsync(dF21, F21, hb * 36, cudaMemcpyHostToDevice, s));
+        if (n_matches > 0) {
+            ctx->launches += launch_two_view_score(dXy1, dXy2, n_matches, H21 ? dH21 : nullptr, H21 ? dH12 : nullptr, F21 ? dF21 : nullptr,
+                                                   n_hyp, sigma, th_h, th_f, th_score, dSH, dSF, inliers_h ? dIH : nullptr,
+                                                   inliers_f ? dIF : nullptr, s);
+            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemsetAsync(dSH, 0, 2 * hb * 4, s));      // no matches: every score is 0 (the reference's loops do not run)
+        }
+        if (H21) CK(cudaMemcpyAsync(score_h, dSH, hb * 4, cudaMemcpyDeviceToHost, s));
+        if (F21) CK(cudaMemcpyAsync(score_f, dSF, hb * 4, cudaMemcpyDeviceToHost, s));
+        if (H21 && inliers_h && n_matches > 0) CK(cudaMemcpyAsync(inliers_h, dIH, hb * n_matches, cudaMemcpyDeviceToHost, s));
+        if (F21 && inliers_f && n_matches > 0) CK(cudaMemcpyAsync(inliers_f, dIF, hb * n_matches, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        // `if (currentScore > score) keep` over the iterations (:307-312, :358-363): the first hypothesis with the highest
+        // score, and none when no score exceeds the initial 0
+        auto pick = [&](const float* sc) { int b = -1; float best = 0.f; for (int i = 0; i < n_hyp; ++i) if (sc[i] > best) { best = sc[i]; b = i; } return b; };
+        if (H21 && best_h) *best_h = pick(score_h);
+        if (F21 && best_f) *best_f = pick(score_f);
+        return NAV24_OK;
+    });
 }
 
 }  // extern "C"

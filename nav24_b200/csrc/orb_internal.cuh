@@ -15,11 +15,10 @@ constexpr int kBlurTileRows = 35;                    // rows per warp tile of bl
 constexpr int kBlurCtaRows = 4 * kBlurTileRows;     // rows per CTA tile (four warp tiles stacked)
 constexpr int kBlurBoxW = 160, kBlurBoxH = kBlurCtaRows + 6;   // TMA box: 128 px + 16-byte aligned halos, 3 halo rows each side
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)
-constexpr int kOriBoxW = 32, kOriBoxH = 31;    // TMA box of the orientation patch: 31 px rounded up to a 16-byte multiple; the box starts AT the patch (tensor-map
-                                               // coordinates are element-granular, only the box width has to be a multiple of 16 bytes)
-constexpr int kDescBoxW = 48, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px -> 48.  A 12-word row pitch costs 3.1 shared-memory wavefronts per gather
-                                               // of the rotated pattern, the same as the 20-word pitch of the round-1 80-byte box (16 words: 4.8); per keypoint
-                                               // 2768 bytes cross L2 instead of 4448 (describe_kernel ran at 70 % of L2 throughput)
+constexpr int kOriBoxW = 48, kOriBoxH = 31;    // TMA box of the orientation patch: 31 px + <= 15 px of alignment slack, 16-B multiple
+constexpr int kDescBoxW = 80, kDescBoxH = 37;   // TMA box of the descriptor patch: 37 px + <= 15 px of alignment slack = 52 -> 64 would do, but a 20-word row pitch
+                                               // spreads the hot central columns over all 32 banks (16 words: 4.8 wavefronts per gather instead of 3.1)
+constexpr int kDescBoxWN = 48;                  // narrow box of the descriptor patch for keypoints whose alignment slack is <= 11 px (12-word pitch: 3.1 too)
 constexpr int kFastThreads = 256;   // threads per CTA of fast_band_kernel
 constexpr int kFastMaxSegCells = 8; // cells of one FAST segment (TMA boxes are <= 256 px wide, cells >= 35 px)
 constexpr int kFastQueueCap = 3072; // stage A survivors one CTA queues (typ. 700 of 8400 pixels); beyond: the dense path
@@ -147,7 +146,7 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
 int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, const TmaMaps& mapsOri, const TmaMaps& mapsBlur,
-                    int B, cudaStream_t s);
+                    const TmaMaps& mapsBlurN, int B, cudaStream_t s);
 int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s);   // test hook (stdsort_warp.cuh)
 
 // matchers (match_kernels.cu)
@@ -174,5 +173,10 @@ int launch_bf_knn2(const uint8_t* d1, int n1, const uint8_t* d2, int n2, int nor
 // camera models (camera_kernels.cu): Calibration::undistort on the device
 int launch_undistort_points(const nav24_camera& cam, const float* xy, int n, float* out, cudaStream_t s);
 int launch_undistort_frames(const nav24_camera& cam, const nav24_kp* kps, const int* nOut, int cap, int B, float* ud, cudaStream_t s);
+
+// two-view RANSAC scoring (camera_kernels.cu): CheckHomography / CheckFundamental of every hypothesis in one launch
+int launch_two_view_score(const float* xy1, const float* xy2, int n, const float* H21, const float* H12, const float* F21, int nHyp,
+                          float sigma, float thH, float thF, float thScore, float* scoreH, float* scoreF, uint8_t* inH, uint8_t* inF,
+                          cudaStream_t s);
 
 }  // namespace nav24

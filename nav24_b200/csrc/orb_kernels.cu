@@ -1127,7 +1127,8 @@ constexpr int kDescStage = (kDescOriOff + kOriBoxW * kOriBoxH + 127) / 128 * 128
 
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                                    const __grid_constant__ TmaMaps mapsOri,
-                                                                   const __grid_constant__ TmaMaps mapsBlur) {
+                                                                   const __grid_constant__ TmaMaps mapsBlur,
+                                                                   const __grid_constant__ TmaMaps mapsBlurN) {
     __shared__ __align__(128) uint8_t s_buf[kDescWarps][2][kDescStage];
     __shared__ __align__(8) unsigned long long s_bar[kDescWarps][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1158,35 +1159,36 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
     }
     __syncwarp();
     // lane 0: both boxes of the keypoint at level l, level coordinates (cx, cy) -> stage st
+    // The box start must be 16-byte aligned in x (an unaligned start coordinate of a u8 tensor faults), so a 37-px patch
+    // needs 37 + slack columns, slack = (cx - 18) & 15: the narrow 48-byte box when slack <= 11 (3 keypoints of 4), the
+    // 80-byte box otherwise.  Both row pitches cost 3.1 shared-memory wavefronts per gather of the rotated pattern (a
+    // 64-byte pitch: 4.8); the narrow box takes 40 % fewer bytes through L2 and the shared-memory fill.
     auto issue = [&](int l, int cx, int cy, int st) {
         const unsigned bar = bar0 + 8 * st, dst = smem_u32(&s_buf[wid][st][0]);
+        const bool narrow = ((cx - 18) & 15) <= kDescBoxWN - 37;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"((unsigned)(kDescBoxW * kDescBoxH + kOriBoxW * kOriBoxH))
+                     "r"((unsigned)((narrow ? kDescBoxWN : kDescBoxW) * kDescBoxH + kOriBoxW * kOriBoxH))
                      : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-            "l"(&mapsBlur.m[l]), "r"(cx - 18), "r"(cy - 18), "r"(f + p.frameBase), "r"(bar)
+            "l"(narrow ? &mapsBlurN.m[l] : &mapsBlur.m[l]), "r"((cx - 18) & ~15), "r"(cy - 18), "r"(f + p.frameBase), "r"(bar)
             : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                 dst + kDescOriOff),
-            "l"(&mapsOri.m[l]), "r"(cx - 15), "r"(cy - 15), "r"(f + p.frameBase), "r"(bar)
+            "l"(&mapsOri.m[l]), "r"((cx - 15) & ~15), "r"(cy - 15), "r"(f + p.frameBase), "r"(bar)
             : "memory");
     };
     // (keeping the lane's eight test pairs in registers across keypoints was measured slower: 96 registers per thread
     // cost more in occupancy than the 32 L1 wavefronts per keypoint cost in the load pipe)
     const float4* pat = reinterpret_cast<const float4*>(kPatternT.v) + lane;
-    // orientation: the 31 x 8 words of the patch are dealt over the lanes, word k*32+lane -> (tile word, row v, weight entry);
-    // the box starts at the patch, so the weights (alignment 0 of the host table, 9 entries per row) are per-lane constants
-    int wpos[8], wrow[8];
-    uint2 wt[8];
+    int wpos[9], wrow[9];                       // orientation: word k*32+lane of the 31 x 9-word patch -> (tile word, v)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int idx = min(k * 32 + lane, 247);
-        const int r = idx >> 3, c = idx & 7;
-        wpos[k] = idx;
+    for (int k = 0; k < 9; ++k) {
+        const int idx = min(k * 32 + lane, 278);
+        const int r = (idx * 57) >> 9, c = idx - r * 9;             // idx / 9 for idx < 288
+        wpos[k] = r * (kOriBoxW / 4) + c;
         wrow[k] = r - 15;
-        wt[k] = __ldg(reinterpret_cast<const uint2*>(p.oriTab) + r * 9 + c);
     }
 
     int lCur = 0, lNext = 0, lNext2 = 0;
@@ -1207,7 +1209,13 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         const LevelGeom& L = g.lv[l];
         const uint8_t* s_blur = &s_buf[wid][st][0];
         const uint8_t* s_ori = s_blur + kDescOriOff;
-        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori);
+        // this lane's orientation weights while the boxes land
+        const int off = (cx - 15) & 15;                                            // 0..15
+        const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279 + lane;
+        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori) + (off >> 2);
+        uint2 wt[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wt[k] = __ldg(tab + min(k * 32, 278 - lane));
         {
             unsigned done = 0;
             const unsigned bar = bar0 + 8 * st, par = (phase >> st) & 1u;
@@ -1220,12 +1228,12 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             }
             phase ^= 1u << st;
         }
-        // IC_Angle: integer moments of the 31-px disc by DP4A over the words of the patch (248 words, 8 per lane; word
-        // positions, row numbers and weights do not depend on the keypoint: set up once per warp)
+        // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane;
+        // the lane's word positions and row numbers do not depend on the keypoint: wpos / wrow, set up once per warp)
         int m10 = 0, m01 = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k * 32 + lane < 248) {
+        for (int k = 0; k < 9; ++k) {
+            if (k * 32 + lane < 279) {
                 const unsigned w = ow[wpos[k]];
                 asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[k].x));      // u8 pixels x s8 offsets
                 m01 += wrow[k] * (int)__dp4a(w, wt[k].y, 0u);
@@ -1246,8 +1254,9 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         // bits (float bits = 0x4B400000 + n), one full-rate FADD instead of a quarter-rate F2I per coordinate (1024 per
         // keypoint); the bias of row and column is folded into the base address.
         const float kMagic = 12582912.f;
-        const unsigned pcA = smem_u32(s_blur) + (unsigned)(18 * kDescBoxW + 18) -
-                             (unsigned)(kDescBoxW + 1) * 0x4B400000u;               // the keypoint, minus the biases
+        const unsigned bp = ((cx - 18) & 15) <= kDescBoxWN - 37 ? (unsigned)kDescBoxWN : (unsigned)kDescBoxW;      // row pitch of this keypoint's box
+        const unsigned pcA = smem_u32(s_blur) + 18u * bp + (unsigned)(18 + ((cx - 18) & 15)) -
+                             (bp + 1u) * 0x4B400000u;               // the keypoint, minus the biases
         unsigned val = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1257,8 +1266,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             const unsigned r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(q4.z, b), __fmul_rn(q4.w, a)), kMagic));
             const unsigned q1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(q4.z, a), __fmul_rn(q4.w, b)), kMagic));
             unsigned t0, t1;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(pcA + r0 * (unsigned)kDescBoxW + q0));
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(pcA + r1 * (unsigned)kDescBoxW + q1));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(pcA + r0 * bp + q0));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(pcA + r1 * bp + q1));
             val |= (unsigned)(t0 < t1) << j;
         }
         LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + sCur;
@@ -1385,7 +1394,7 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
 }
 
 int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, const TmaMaps& mapsOri, const TmaMaps& mapsBlur,
-                    int B, cudaStream_t s) {
+                    const TmaMaps& mapsBlurN, int B, cudaStream_t s) {
     int n = 0;
     {
         dim3 grid(g.blurTiles, B);
@@ -1393,7 +1402,7 @@ int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlu
         ++n;
     }
     dim3 grid((g.kpPerFrame + kDescWarps * kDescSlots - 1) / (kDescWarps * kDescSlots), B);
-    describe_kernel<<<grid, kDescWarps * 32, 0, s>>>(g, p, mapsOri, mapsBlur);
+    describe_kernel<<<grid, kDescWarps * 32, 0, s>>>(g, p, mapsOri, mapsBlur, mapsBlurN);
     return n + 1;
 }
 

@@ -72,6 +72,10 @@ def lib():
                                      C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_match_bf_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_check_homography.restype = C.c_float
+        L.orc_check_homography.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.orc_check_fundamental.restype = C.c_float
+        L.orc_check_fundamental.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_undistort_radtan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_undistort_kb8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -249,3 +253,21 @@ def undistort(model, K4, D4, xy):
     fn = lib().orc_undistort_radtan if model == CAM_RADTAN else lib().orc_undistort_kb8
     fn(_p(K4), _p(D4), _p(xy), len(xy), _p(out))
     return out
+
+
+def check_homography(H21, H12, xy1, xy2, sigma=1.0, th=5.991):
+    """TwoViewReconstruction::CheckHomography restatement: (score float32, inliers uint8[n])."""
+    H21 = np.ascontiguousarray(H21, np.float32); H12 = np.ascontiguousarray(H12, np.float32)
+    xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+    inl = np.zeros(max(1, len(xy1)), np.uint8)
+    s = lib().orc_check_homography(_p(H21), _p(H12), _p(xy1), _p(xy2), len(xy1), sigma, th, _p(inl))
+    return np.float32(s), inl[:len(xy1)]
+
+
+def check_fundamental(F21, xy1, xy2, sigma=1.0, th=3.841, th_score=5.991):
+    """TwoViewReconstruction::CheckFundamental restatement: (score float32, inliers uint8[n])."""
+    F21 = np.ascontiguousarray(F21, np.float32)
+    xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+    inl = np.zeros(max(1, len(xy1)), np.uint8)
+    s = lib().orc_check_fundamental(_p(F21), _p(xy1), _p(xy2), len(xy1), sigma, th, th_score, _p(inl))
+    return np.float32(s), inl[:len(xy1)]

@@ -1,0 +1,134 @@
+"""two-view RANSAC scoring (TwoViewReconstruction::CheckHomography / CheckFundamental,
+core/operators/mapInit/OP_2ViewReconstruction.cpp:447-610) for all hypotheses in one launch.
+
+Oracle: oracle/orb_oracle.cpp restates both functions in plain IEEE float (-ffp-contract=off).  PARITY UNPINNED by the
+reference build: OP_2ViewReconstruction.cpp needs cv::SVDecomp, cv::Mat algebra and DBoW2's DUtils::Random, none of
+which exist in this image, so oracle/_ref cannot contain it; a float64 numpy evaluation of the same formulas bounds the
+oracle instead (CPU test below).  The CUDA path must equal the oracle BIT FOR BIT: scores are sequential float sums in
+match order and the kernel keeps that order."""
+import numpy as np
+import pytest
+
+from oracle import orb_oracle as oo
+
+
+def scene(seed, n=400, planar=False, outliers=0.3):
+    """Matched points of two views of a random 3-D scene (pixels, float32), 200 homography hypotheses (H21, H12) and 200
+    fundamental-matrix hypotheses, perturbed around the true ones."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[458.0, 0, 367.0], [0, 457.0, 248.0], [0, 0, 1]])
+    X = np.c_[rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), (np.full(n, 5.0) if planar else rng.uniform(3, 9, n))]
+    ang = 0.05
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([0.3, 0.02, 0.05])
+    x1 = (K @ X.T).T; x1 = x1[:, :2] / x1[:, 2:]
+    x2 = (K @ (R @ X.T + t[:, None])).T; x2 = x2[:, :2] / x2[:, 2:]
+    x1 += rng.normal(0, 0.5, x1.shape); x2 += rng.normal(0, 0.5, x2.shape)
+    bad = rng.random(n) < outliers
+    x2[bad] = rng.uniform(0, [752, 480], (bad.sum(), 2))
+    # true homography of the plane z = 5 and the true fundamental matrix
+    nrm = np.array([0, 0, 1.0]); d = 5.0
+    Ht = K @ (R + np.outer(t, nrm) / d) @ np.linalg.inv(K)
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Ft = np.linalg.inv(K).T @ tx @ R @ np.linalg.inv(K)
+    H21, H12, F21 = [], [], []
+    for i in range(200):
+        s = 0.0 if i == 17 else rng.choice([1e-4, 1e-3, 1e-2, 1e-1])
+        H = (Ht / Ht[2, 2]) * (1 + s * rng.normal(0, 1, (3, 3)))
+        H21.append(H.astype(np.float32)); H12.append(np.linalg.inv(H.astype(np.float32)).astype(np.float32))
+        F = (Ft / np.abs(Ft).max()) * (1 + s * rng.normal(0, 1, (3, 3)))
+        F21.append(F.astype(np.float32))
+    return (x1.astype(np.float32), x2.astype(np.float32), np.stack(H21).reshape(-1, 9), np.stack(H12).reshape(-1, 9),
+            np.stack(F21).reshape(-1, 9))
+
+
+def test_oracle_against_float64():
+    """The float restatement against the same formulas in float64 numpy: scores agree to float rounding, inlier flags may
+    differ only where a chi-square sits on the threshold."""
+    x1, x2, H21, H12, F21 = scene(1)
+    u1, v1, u2, v2 = [a.astype(np.float64) for a in (x1[:, 0], x1[:, 1], x2[:, 0], x2[:, 1])]
+    for h in (17, 3, 120):
+        s, inl = oo.check_homography(H21[h], H12[h], x1, x2)
+        A, Ai = H21[h].astype(np.float64).reshape(3, 3), H12[h].astype(np.float64).reshape(3, 3)
+        w = Ai[2, 0] * u2 + Ai[2, 1] * v2 + Ai[2, 2]
+        c1 = (u1 - (Ai[0, 0] * u2 + Ai[0, 1] * v2 + Ai[0, 2]) / w) ** 2 + (v1 - (Ai[1, 0] * u2 + Ai[1, 1] * v2 + Ai[1, 2]) / w) ** 2
+        w = A[2, 0] * u1 + A[2, 1] * v1 + A[2, 2]
+        c2 = (u2 - (A[0, 0] * u1 + A[0, 1] * v1 + A[0, 2]) / w) ** 2 + (v2 - (A[1, 0] * u1 + A[1, 1] * v1 + A[1, 2]) / w) ** 2
+        ref = np.where(c1 <= 5.991, 5.991 - c1, 0).sum() + np.where(c2 <= 5.991, 5.991 - c2, 0).sum()
+        assert abs(float(s) - ref) <= 2e-3 * max(1.0, ref)
+        assert (inl != ((c1 <= 5.991) & (c2 <= 5.991))).sum() <= 2
+        s, inl = oo.check_fundamental(F21[h], x1, x2)
+        F = F21[h].astype(np.float64).reshape(3, 3)
+        a2, b2, c2_ = [F[r, 0] * u1 + F[r, 1] * v1 + F[r, 2] for r in range(3)]
+        d1 = (a2 * u2 + b2 * v2 + c2_) ** 2 / (a2 * a2 + b2 * b2)
+        a1, b1, c1_ = [F[0, c] * u2 + F[1, c] * v2 + F[2, c] for c in range(3)]
+        d2 = (a1 * u1 + b1 * v1 + c1_) ** 2 / (a1 * a1 + b1 * b1)
+        ref = np.where(d1 <= 3.841, 5.991 - d1, 0).sum() + np.where(d2 <= 3.841, 5.991 - d2, 0).sum()
+        assert abs(float(s) - ref) <= 2e-3 * max(1.0, ref)
+        assert (inl != ((d1 <= 3.841) & (d2 <= 3.841))).sum() <= 2
+    # the unperturbed hypothesis of the planar scene explains most matches
+    x1, x2, H21, H12, F21 = scene(2, planar=True)
+    s, inl = oo.check_homography(H21[17], H12[17], x1, x2)
+    assert inl.sum() > 0.5 * len(x1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,planar", [(1, 400, False), (2, 400, True), (3, 1, False), (4, 2500, False), (5, 1024, True), (6, 1025, False)])
+def test_cuda_scores_equal_oracle(seed, n, planar, cuda_required):
+    from nav24_b200 import capi
+    x1, x2, H21, H12, F21 = scene(seed, n, planar)
+    ctx = capi.OrbContext(1000)
+    try:
+        r = ctx.two_view_score(x1, x2, H21, H12, F21)
+        sh = np.zeros(200, np.float32); sf = np.zeros(200, np.float32)
+        for h in range(200):
+            sh[h], ih = oo.check_homography(H21[h], H12[h], x1, x2)
+            sf[h], i_f = oo.check_fundamental(F21[h], x1, x2)
+            assert np.array_equal(r["inliers_h"][h], ih), f"homography inliers of hypothesis {h}"
+            assert np.array_equal(r["inliers_f"][h], i_f), f"fundamental inliers of hypothesis {h}"
+        assert r["score_h"].tobytes() == sh.tobytes(), "homography scores are not bit-equal"
+        assert r["score_f"].tobytes() == sf.tobytes(), "fundamental scores are not bit-equal"
+
+        def keep(sc):      # the reference's `if (currentScore > score)` loop
+            b, best = -1, np.float32(0)
+            for i, v in enumerate(sc):
+                if v > best:
+                    b, best = i, v
+            return b
+        assert r["best_h"] == keep(sh) and r["best_f"] == keep(sf)
+        # one model at a time, no inlier masks
+        r2 = ctx.two_view_score(x1, x2, F21=F21, want_inliers=False)
+        assert r2["score_h"] is None and r2["score_f"].tobytes() == sf.tobytes() and r2["best_f"] == r["best_f"]
+        r3 = ctx.two_view_score(x1, x2, H21, H12, want_inliers=False)
+        assert r3["score_f"] is None and r3["score_h"].tobytes() == sh.tobytes()
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_two_view_edge_cases(cuda_required):
+    from nav24_b200 import capi
+    x1, x2, H21, H12, F21 = scene(9, 50)
+    ctx = capi.OrbContext(1000)
+    try:
+        r = ctx.two_view_score(x1[:0], x2[:0], H21, H12, F21)                # no matches: all scores 0, nothing kept
+        assert not r["score_h"].any() and not r["score_f"].any() and r["best_h"] == -1 and r["best_f"] == -1
+        with pytest.raises(capi.Nav24Error) as e:
+            ctx.two_view_score(x1, x2, H21, None, None)                       # H21 without H12
+        assert e.value.code == capi.E_BADARG
+        with pytest.raises(capi.Nav24Error):
+            ctx.two_view_score(x1, x2, H21, H12, F21, sigma=0.0)
+        # matches on real detections: frame 0 vs frame 1 of a shifted sequence, pure translation => the identity-plus-shift
+        # homography explains the matches
+        from nav24_b200.synth import sequence
+        fr = sequence(480, 752, 5, 2, step=(6, 2))
+        n, mono, kps, desc, m, nm = ctx.detect_match_batch(fr, [(0, 1)], capi.grid_for(752, 480))
+        i1 = np.nonzero(m[0, :n[0]] >= 0)[0]; i2 = m[0, i1]
+        p1 = np.stack([kps[0, i1]["x"], kps[0, i1]["y"]], 1); p2 = np.stack([kps[1, i2]["x"], kps[1, i2]["y"]], 1)
+        H = np.array([[1, 0, -6], [0, 1, -2], [0, 0, 1]], np.float32)
+        r = ctx.two_view_score(p1, p2, H.reshape(1, 9), np.linalg.inv(H).astype(np.float32).reshape(1, 9))
+        s, inl = oo.check_homography(H.reshape(9), np.linalg.inv(H).astype(np.float32).reshape(9), p1, p2)
+        assert r["score_h"][0].tobytes() == np.float32(s).tobytes() and np.array_equal(r["inliers_h"][0], inl)
+        assert inl.sum() > 0.8 * len(p1)
+    finally:
+        ctx.close()
