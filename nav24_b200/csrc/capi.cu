@@ -220,6 +220,7 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         if (L.nIni < 1) return ctx->fail(NAV24_E_GEOMETRY, "image taller than 2:1, the quadtree has no root node");
         L.hX = (float)(L.maxBX - minBX) / (float)L.nIni;
         L.nodeCap = align_up(std::max(4 * L.nIni, L.quota + 3) + 4, 4);
+        if (L.nodeCap > 65535) return ctx->fail(NAV24_E_GEOMETRY, "more than 65535 quadtree nodes per level (node indices are 16-bit)");
         L.nodeOff = nodeOff;
         nodeOff += L.nodeCap;
         L.kpOff = kpOff;

@@ -628,60 +628,37 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
 //   new list = reverse(children in creation order) ++ (old list minus split parents)
 // which is what push_front of each child + erase of the parent produce.
 // ------------------------------------------------------------------------------------------
+// bytes of the sort scratch for `cap` records: records | two u16 position lists | leaf-start bit mask | two range lists of
+// sort_block (>= the 192-int stack of sort_warp), rounded to 16 (see stdsort_warp.cuh)
+__host__ __device__ inline size_t quadtree_sort_bytes(int cap) {
+    const size_t rng = (size_t)(2 * (3 * (cap / 16 + 2) + 1)) > 192 ? (size_t)(2 * (3 * (cap / 16 + 2) + 1)) : 192;
+    return ((size_t)cap * 12 + (size_t)((cap + 31) / 32) * 4 + rng * 4 + 16 + 15) / 16 * 16;
+}
+
 __device__ __forceinline__ int quadrant_of(const QNode& n, int x, int y) {
     const int mx = n.x0 + ((n.x1 - n.x0 + 1) >> 1);     // UL.x + ceil(w/2)  (:386)
     const int my = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
     return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
 }
 
-template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency)
-__global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
-                                                       int sortSmemCap) {
-    extern __shared__ unsigned long long s_sort[];
-    __shared__ int s_scan[33];
-    __shared__ int s_K, s_nexp;
-
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int l = blockIdx.x, f = blockIdx.y;
+// Working tables of one (level, frame).  The ordered keys and the node of every key are STREAMED (coalesced, index i)
+// and stay in global memory; the tables that are accessed at random through the node index — the two node lists, the
+// child counts (atomics), per-node scratch, best key per node (atomics) — live in the CTA's shared memory when
+// SM = true (typed through this template so that every access compiles to LDS / STS / ATOMS; a run-time choice
+// between spaces makes the pointers generic: +24 registers and slower) and in the per-frame global slabs when SM = false
+// (levels whose node tables do not fit, e.g. the x5 feature mode or 4K level 0).  Measured: with the keys in shared memory
+// as well the CTA needs 72 KB, three CTAs per SM instead of seven, and the kernel — bound by barrier and dependent-access
+// latency, not by bandwidth — got 23 % slower instead of faster.
+template <int NT, bool SM>
+__device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& p, const int l, const int f, const int n,
+                                             const int sortSmemCap, unsigned long long* s_sort, int* s_scan, int* s_K, int* s_nexp,
+                                             const RawRec* __restrict__ keys, unsigned short* __restrict__ nodeOfKey, QNode* cur, QNode* nxt,
+                                             int* childCnt, int* aux, unsigned* best) {
+    const int tid = threadIdx.x, nth = NT;
     const LevelGeom& L = g.lv[l];
-    const long long fr = (long long)f * g.rawPerFrame + L.rawOff;
     const long long fn = (long long)f * g.nodesPerFrame + L.nodeOff;
-    const uint2* cinfo = p.cellInfo + (long long)f * g.totalCells + L.cellBase;
-    int* cdst = p.cellDst + (long long)f * g.totalCells + L.cellBase;
-    const RawRec* raw = p.raw + fr;
-    RawRec* keys = p.keys + fr;
-    int* nodeOfKey = p.nodeOfKey + fr;
-    QNode* cur = p.nodesA + fn;
-    QNode* nxt = p.nodesB + fn;
-    int* childCnt = p.childCnt + 4 * fn;
-    int* aux = p.nodeAux + fn;
-    unsigned long long* best = p.best + fn;
     unsigned long long* sortRec = p.sortRec + fn;
     LevelKp* lkp = p.lkp + (long long)f * g.kpPerFrame + L.kpOff;
-
-    // (a) bring the per-cell lists into the reference order: cells row-major, row-major inside a cell
-    const int nC = L.nCols * L.nRows;
-    int n = 0;
-    for (int base = 0; base < nC; base += nth) {
-        const int c = base + tid;
-        const int cnt = c < nC ? (int)cinfo[c].y : 0;
-        int tot;
-        const int ex = block_excl_scan(cnt, &tot, s_scan);
-        if (c < nC) cdst[c] = n + ex;
-        n += tot;
-    }
-    __syncthreads();
-    for (int c = tid >> 5; c < nC; c += nth >> 5) {
-        const uint2 ci = cinfo[c];
-        const int d = cdst[c];
-        for (int k = tid & 31; k < (int)ci.y; k += 32) keys[d + k] = raw[ci.x + k];
-    }
-    if (tid == 0) p.rawTotal[f * g.nlevels + l] = n;
-    __syncthreads();
-    if (n == 0) {
-        if (tid == 0) p.levelCount[f * g.nlevels + l] = 0;
-        return;
-    }
 
     // (b) root nodes (:505-547)
     const int N = L.quota, nIni = L.nIni;
@@ -691,7 +668,7 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
     for (int i = tid; i < n; i += nth) {
         int r = (int)__fdiv_rn((float)keys[i].x, hX);
         if (r >= nIni || r < 0) { atomicOr(p.err, ERR_ROOT_RANGE); r = nIni - 1; }
-        nodeOfKey[i] = r;
+        nodeOfKey[i] = (unsigned short)r;
         atomicAdd(&childCnt[r], 1);
     }
     __syncthreads();
@@ -713,7 +690,7 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
         size += tot;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += nth) nodeOfKey[i] = aux[nodeOfKey[i]];
+    for (int i = tid; i < n; i += nth) nodeOfKey[i] = (unsigned short)aux[nodeOfKey[i]];
     __syncthreads();
 
     // (c) split passes (:555-700)
@@ -721,12 +698,15 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
     while (!finish) {
         const int prevSize = size;
         for (int k = tid; k < 4 * size; k += nth) childCnt[k] = 0;
-        if (tid == 0) { s_nexp = 0; s_K = 0x7fffffff; }
+        if (tid == 0) { *s_nexp = 0; *s_K = 0x7fffffff; }
         __syncthreads();
         for (int i = tid; i < n; i += nth) {
             const int nd = nodeOfKey[i];
             const QNode q = cur[nd];
-            if (q.count > 1) atomicAdd(&childCnt[nd * 4 + quadrant_of(q, keys[i].x, keys[i].y)], 1);
+            if (q.count > 1) {
+                const RawRec k = keys[i];
+                atomicAdd(&childCnt[nd * 4 + quadrant_of(q, k.x, k.y)], 1);
+            }
         }
         __syncthreads();
 
@@ -795,11 +775,11 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
                 }
                 int tot;
                 const int ex = block_excl_scan(d, &tot, s_scan);
-                if (pp < m && size + runD + ex + d >= N) atomicMin(&s_K, pp + 1);
+                if (pp < m && size + runD + ex + d >= N) atomicMin(s_K, pp + 1);
                 runD += tot;
             }
             __syncthreads();
-            const int K = min(s_K, m);
+            const int K = min(*s_K, m);
             for (int nd = tid; nd < size; nd += nth) aux[nd] = -0x40000000;   // "not split" marker
             __syncthreads();
             for (int base = 0; base < K; base += nth) {
@@ -838,9 +818,11 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
             if (a >= 0) {
                 const int mx = q.x0 + ((q.x1 - q.x0 + 1) >> 1), my = q.y0 + ((q.y1 - q.y0 + 1) >> 1);
                 int cidx = a;
+                const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);
+                const int cnts[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int cnt = childCnt[nd * 4 + k];
+                    const int cnt = cnts[k];
                     if (cnt > 0) {
                         QNode ch;
                         ch.x0 = (k & 1) ? (short)mx : q.x0;  ch.x1 = (k & 1) ? q.x1 : (short)mx;
@@ -855,35 +837,37 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
                 nxt[C + (-a - 1)] = q;
             }
         }
-        if (nexp) atomicAdd(&s_nexp, nexp);
+        if (nexp) atomicAdd(s_nexp, nexp);
         for (int i = tid; i < n; i += nth) {
             const int nd = nodeOfKey[i];
             const int a = aux[nd];
             if (a >= 0) {
-                const int k = quadrant_of(cur[nd], keys[i].x, keys[i].y);
+                const RawRec kk = keys[i];
+                const int k = quadrant_of(cur[nd], kk.x, kk.y);
                 const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);      // one load instead of k dependent ones
                 const int cidx = a + (k > 0 && cc.x > 0) + (k > 1 && cc.y > 0) + (k > 2 && cc.z > 0);
-                nodeOfKey[i] = C - 1 - cidx;
+                nodeOfKey[i] = (unsigned short)(C - 1 - cidx);
             } else {
-                nodeOfKey[i] = C + (-a - 1);
+                nodeOfKey[i] = (unsigned short)(C + (-a - 1));
             }
         }
         __syncthreads();
         { QNode* t = cur; cur = nxt; nxt = t; }
         size = C + U;
         if (size >= N || size == prevSize) finish = true;
-        else if (!phase2 && size + 3 * s_nexp > N) phase2 = true;
+        else if (!phase2 && size + 3 * *s_nexp > N) phase2 = true;
         __syncthreads();   // s_nexp is reset at the top of the next pass
     }
 
-    // (d) best response per node, first key wins ties (:703-722); add the border (:829-836)
-    for (int nd = tid; nd < size; nd += nth) best[nd] = 0ull;
+    // (d) best response per node, first key wins ties (:703-722); add the border (:829-836).  One 32-bit atomicMax:
+    // score (<= 255) in the top byte, 0xFFFFFF - key index below it (n < 2^19).
+    for (int nd = tid; nd < size; nd += nth) best[nd] = 0u;
     __syncthreads();
     for (int i = tid; i < n; i += nth)
-        atomicMax(&best[nodeOfKey[i]], ((unsigned long long)keys[i].score << 32) | (unsigned)(0xffffffffu - (unsigned)i));
+        atomicMax(&best[nodeOfKey[i]], ((unsigned)keys[i].score << 24) | (0xffffffu - (unsigned)i));
     __syncthreads();
     for (int nd = tid; nd < size; nd += nth) {
-        const unsigned i = 0xffffffffu - (unsigned)(best[nd] & 0xffffffffu);
+        const unsigned i = 0xffffffu - (best[nd] & 0xffffffu);
         const RawRec k = keys[i];
         LevelKp o;
         o.x = (unsigned short)(k.x + kMinBorder); o.y = (unsigned short)(k.y + kMinBorder);
@@ -891,6 +875,64 @@ __global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ Fr
         lkp[nd] = o;
     }
     if (tid == 0) p.levelCount[f * g.nlevels + l] = size;
+}
+
+// Shared-memory table sizes of quadtree_kernel (nodeCap 0: the node tables stay in global memory)
+struct QtSmem { int sortCap, nodeCap; };
+
+template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency)
+__global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
+    extern __shared__ __align__(16) unsigned long long s_sort[];
+    __shared__ int s_scan[33];
+    __shared__ int s_K, s_nexp;
+
+    const int tid = threadIdx.x, nth = NT;
+    const int l = blockIdx.x, f = blockIdx.y;
+    const LevelGeom& L = g.lv[l];
+    const long long fr = (long long)f * g.rawPerFrame + L.rawOff;
+    const long long fn = (long long)f * g.nodesPerFrame + L.nodeOff;
+    const uint2* cinfo = p.cellInfo + (long long)f * g.totalCells + L.cellBase;
+    int* cdst = p.cellDst + (long long)f * g.totalCells + L.cellBase;
+    const RawRec* raw = p.raw + fr;
+    RawRec* gkeys = p.keys + fr;
+
+    // (a) bring the per-cell lists into the reference order: cells row-major, row-major inside a cell
+    const int nC = L.nCols * L.nRows;
+    int n = 0;
+    for (int base = 0; base < nC; base += nth) {
+        const int c = base + tid;
+        const int cnt = c < nC ? (int)cinfo[c].y : 0;
+        int tot;
+        const int ex = block_excl_scan(cnt, &tot, s_scan);
+        if (c < nC) cdst[c] = n + ex;
+        n += tot;
+    }
+    __syncthreads();
+    // shared-memory node tables behind the sort scratch: child counts (16-byte aligned) | node lists A, B | aux | best
+    unsigned char* tb = reinterpret_cast<unsigned char*>(s_sort) + quadtree_sort_bytes(qs.sortCap);
+    int* sChild = reinterpret_cast<int*>(tb);
+    QNode* sA = reinterpret_cast<QNode*>(sChild + 4 * qs.nodeCap);
+    QNode* sB = sA + qs.nodeCap;
+    int* sAux = reinterpret_cast<int*>(sB + qs.nodeCap);
+    unsigned* sBest = reinterpret_cast<unsigned*>(sAux + qs.nodeCap);
+    const bool useSm = L.nodeCap <= qs.nodeCap;      // CTA-uniform
+    for (int c = tid >> 5; c < nC; c += nth >> 5) {
+        const uint2 ci = cinfo[c];
+        const int d = cdst[c];
+        for (int k = tid & 31; k < (int)ci.y; k += 32) gkeys[d + k] = raw[ci.x + k];
+    }
+    if (tid == 0) p.rawTotal[f * g.nlevels + l] = n;
+    __syncthreads();
+    if (n == 0) {
+        if (tid == 0) p.levelCount[f * g.nlevels + l] = 0;
+        return;
+    }
+    unsigned short* nok = reinterpret_cast<unsigned short*>(p.nodeOfKey + fr);
+    if (useSm)
+        quadtree_run<NT, true>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, sA, sB, sChild, sAux, sBest);
+    else
+        quadtree_run<NT, false>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, p.nodesA + fn, p.nodesB + fn,
+                                p.childCnt + 4 * fn, p.nodeAux + fn, reinterpret_cast<unsigned*>(p.best + fn));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1345,12 +1387,6 @@ int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B
     return 1;
 }
 
-// records | two u16 position lists | leaf-start bit mask | range stack  (see stdsort_warp.cuh)
-// records | two u16 position lists | leaf-start bit mask | two range lists of sort_block (>= the 192-int stack of sort_warp)
-static size_t quadtree_smem_bytes(int cap) {
-    return (size_t)cap * 12 + (size_t)((cap + 31) / 32) * 4 + (size_t)std::max(192, 2 * (3 * (cap / 16 + 2) + 1)) * 4 + 16;
-}
-
 // test hook: std::sort of n records (key = high 32 bits) by one warp, in shared memory
 namespace {
 __global__ void __launch_bounds__(256) debug_sort_kernel(unsigned long long* recs, int n, int cap) {
@@ -1370,7 +1406,7 @@ __global__ void __launch_bounds__(256) debug_sort_kernel(unsigned long long* rec
 
 int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s) {
     const int cap = (n + 3) & ~3;
-    const size_t smem = quadtree_smem_bytes(cap);
+    const size_t smem = quadtree_sort_bytes(cap);
     if (smem > 200 * 1024) return -1;
     cudaFuncSetAttribute(debug_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     debug_sort_kernel<<<1, (n & 1) ? 32 : 256, smem, s>>>(d_recs, n, cap);      // odd n: the one-warp version, even n: the CTA version
@@ -1380,15 +1416,24 @@ int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s) {
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
     int maxNode = 0;
     for (int l = 0; l < g.nlevels; ++l) maxNode = max(maxNode, g.lv[l].nodeCap);
-    int cap = (min(maxNode, 12000) + 3) & ~3;      // records sorted in shared memory; larger levels sort in global memory
-    size_t smem = quadtree_smem_bytes(cap);
+    QtSmem qs{};
+    qs.sortCap = (min(maxNode, 12000) + 3) & ~3;      // records sorted in shared memory; larger levels sort in global memory
+    size_t smem = quadtree_sort_bytes(qs.sortCap);
+    // Node tables in shared memory (52 bytes per node) when those of the largest level fit a 32 KB CTA together with the sort
+    // scratch: seven CTAs per SM, the same occupancy as with global tables (the kernel lives on overlapping barriers).
+    const size_t budget = 32 * 1024;
+    const size_t nodeBytes = (size_t)maxNode * 52;
+    if (smem + nodeBytes <= budget) {
+        qs.nodeCap = maxNode;
+        smem += nodeBytes;
+    }
     cudaFuncSetAttribute(quadtree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(quadtree_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid(g.nlevels, B);
     // 256 threads per (level, frame) when the batch fills the GPU (128: 5 % faster alone, slower in the chunked host
     // pipeline); a small batch (single-camera latency) has few CTAs, so each gets 1024 threads for its parallel passes
-    if (g.nlevels * B < 2 * 148) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, cap);
-    else quadtree_kernel<256><<<grid, 256, smem, s>>>(g, p, cap);
+    if (g.nlevels * B < 2 * 148) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, qs);
+    else quadtree_kernel<256><<<grid, 256, smem, s>>>(g, p, qs);
     order_kernel<<<B, 256, 0, s>>>(g, p);
     return 2;
 }
