@@ -18,6 +18,10 @@
 //   OB::FeatureGrid cfg sensorData/observation/FeatureGrid.cpp:100    FeatureGridCfg (explicit, not process-global)
 //   Calibration         sensor/camera/Calibration.cpp:135-233         CalibrationB200 (undistort, computeImageBounds)
 //   vector<ObsPtr>      OP_FtDtOrbSlam.cpp:925-931, Point2D.hpp:37-69 OB::ObservationStore (struct of arrays, same accessors)
+//   imread + clones     sensor/camera/Camera.cpp:454-455, Image.hpp:22,   IngestRingB200 (pinned slots the decoder writes into, device
+//                       frontEnd/FE_SlamMonoV.cpp:90-94                   BGR -> grey)
+//   CheckHomography /   operators/mapInit/OP_2ViewReconstruction.cpp      OP::TwoViewScorerB200 (all RANSAC hypotheses in one call)
+//   CheckFundamental    :447-610
 //
 // There is no CPU fallback: constructing FtDtOrbB200 without a CUDA device throws std::runtime_error.
 #pragma once
@@ -396,6 +400,79 @@ private:
     std::shared_ptr<FtDtOrbB200> mpOwner;
     int mNorm;
     float mRatio;
+};
+
+}  // namespace OP
+// ---- image ingest ---------------------------------------------------------------------------------
+// The pinned slots CamOffline::run decodes into (cv::imdecode(..., &slotMat)) instead of imread + four clones; colour
+// slots are converted to grey on the device.  detect(slot, frame) is FtDtOrbB200::detectSoA on a slot.
+class IngestRingB200 {
+public:
+    IngestRingB200(const std::shared_ptr<OP::FtDtOrbB200>& det, int width, int height, int channels, int slots)
+        : mpDet(det), mW(width), mH(height), mCh(channels), mSlots(slots) {
+        if (nav24_ingest_create(det->handle(), width, height, channels, slots, &mRing) != NAV24_OK)
+            throw std::runtime_error(std::string("IngestRingB200: ") + nav24_last_error_string(det->handle()));
+    }
+    ~IngestRingB200() { nav24_ingest_destroy(mRing); }
+    IngestRingB200(const IngestRingB200&) = delete;
+    IngestRingB200& operator=(const IngestRingB200&) = delete;
+
+    uint8_t* slot(int k) { return nav24_ingest_slot(mRing, k); }
+    size_t slotBytes() const { return nav24_ingest_slot_bytes(mRing); }
+    int slots() const { return mSlots; }
+
+    // detect on slot k into the frame's observation store; returns monoIndex or -1 (like FtDt::detect)
+    int detect(int k, FramePtr& pFrame) {
+        auto st = std::make_shared<OB::ObservationStore>();
+        const int cap = nav24_orb_max_keypoints(mpDet->handle());
+        st->reserve((size_t)cap);
+        int n = 0, mono = 0;
+        int rc = nav24_ingest_detect(mRing, k, 1, st->keypoints(), st->descriptors(), cap, &n, &mono);
+        if (rc == NAV24_E_CAPACITY) {      // the first call of a shape learns the exact bound
+            st->reserve((size_t)nav24_orb_max_keypoints(mpDet->handle()));
+            rc = nav24_ingest_detect(mRing, k, 1, st->keypoints(), st->descriptors(), nav24_orb_max_keypoints(mpDet->handle()), &n, &mono);
+        }
+        if (rc < 0) return -1;
+        st->setSize((size_t)n);
+        pFrame->setObservationStore(st);
+        return mono;
+    }
+
+private:
+    std::shared_ptr<OP::FtDtOrbB200> mpDet;
+    nav24_ingest* mRing = nullptr;
+    int mW, mH, mCh, mSlots;
+};
+
+namespace OP {
+
+// ---- two-view RANSAC scoring ------------------------------------------------------------------
+// TwoViewReconstruction::CheckHomography / CheckFundamental (OP_2ViewReconstruction.cpp:447-610) for every iteration of
+// FindHomography / FindFundamental at once; members mirror Params2VR (OP_2ViewReconstruction.hpp:46-65).
+class TwoViewScorerB200 {
+public:
+    explicit TwoViewScorerB200(const std::shared_ptr<FtDtOrbB200>& det, float sigma = 1.f) : mpDet(det), mSigma(sigma) {}
+
+    struct Result { std::vector<float> scoreH, scoreF; std::vector<uint8_t> inliersH, inliersF; int bestH = -1, bestF = -1; };
+
+    // xy1 / xy2: n matched points (x, y); H21 / H12 / F21: nHyp x 9 row-major (F21 or the H pair may be empty)
+    bool score(const std::vector<float>& xy1, const std::vector<float>& xy2, const std::vector<float>& H21,
+               const std::vector<float>& H12, const std::vector<float>& F21, Result& r) const {
+        const int n = (int)(xy1.size() / 2), nHyp = (int)(std::max(H21.size(), F21.size()) / 9);
+        r = Result();
+        if (!H21.empty()) { r.scoreH.resize(nHyp); r.inliersH.resize((size_t)nHyp * n); }
+        if (!F21.empty()) { r.scoreF.resize(nHyp); r.inliersF.resize((size_t)nHyp * n); }
+        return nav24_two_view_score(mpDet->handle(), xy1.data(), xy2.data(), n, H21.empty() ? nullptr : H21.data(),
+                                    H12.empty() ? nullptr : H12.data(), F21.empty() ? nullptr : F21.data(), nHyp, mSigma, mThChiSqScore,
+                                    mThChiSqF, mThChiSqScore, r.scoreH.data(), r.scoreF.data(), r.inliersH.data(), r.inliersF.data(),
+                                    &r.bestH, &r.bestF) == NAV24_OK;
+    }
+
+    float mThChiSqScore = 5.991f, mThChiSqF = 3.841f;      // DEF_TH_CHISQ_SCORE, DEF_TH_CHISQ_F
+
+private:
+    std::shared_ptr<FtDtOrbB200> mpDet;
+    float mSigma;
 };
 
 }  // namespace OP

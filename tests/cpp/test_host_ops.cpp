@@ -122,6 +122,52 @@ int main(int argc, char** argv) {
                      std::chrono::duration<double, std::micro>(t2 - t1).count() / reps, sink);
     }
     std::fwrite(&soaOk, 4, 1, fo);
+
+    // image ingest: the frames go through the pinned slot ring (grey slots here; colour slots are covered
+    // by tests/test_ingest.py) and must give the observations of the plain detect() above
+    int ringOk = 1;
+    {
+        IngestRingB200 ring(pOrbDetector, w, h, 1, n + 1);
+        for (int f = 0; f < n; ++f) std::memcpy(ring.slot(f + 1), img.data() + (size_t)f * h * w, (size_t)h * w);
+        for (int f = 0; f < n; ++f) {
+            FramePtr pFrame = std::make_shared<FrameMonoGrid>(f * 0.05, nullptr, w, h, (size_t)w);
+            if (ring.detect(f + 1, pFrame) < 0) { ringOk = 0; break; }
+            const OB::ObservationStore& st = *pFrame->getObservationStore();
+            const auto& obs = frames[f]->getObservations();
+            if (st.size() != obs.size()) ringOk = 0;
+            for (size_t i = 0; i < st.size() && ringOk; ++i)
+                if (std::memcmp(&st[i].getKeyPoint(), &obs[i]->getKeyPoint(), sizeof(nav24_kp)) != 0 ||
+                    std::memcmp(st[i].getDescriptor(), obs[i]->getDescriptor().data(), 32) != 0) ringOk = 0;
+        }
+        if (ring.slot(n + 1) != nullptr) ringOk = 0;      // out of range
+    }
+    std::fwrite(&ringOk, 4, 1, fo);
+
+    // two-view RANSAC scoring on the matches of frames 0 and 1: two homography and two fundamental
+    // hypotheses (the true image shift of the synthetic sequence and a perturbed one); scores go to the checker
+    if (n >= 2) {
+        const std::vector<int>& m12 = frames[1]->getMatches()->mvMatches12;
+        std::vector<float> xy1, xy2;
+        const auto& o1 = frames[0]->getObservations(); const auto& o2 = frames[1]->getObservations();
+        for (size_t i = 0; i < m12.size(); ++i)
+            if (m12[i] >= 0) {
+                xy1.push_back(o1[i]->getKeyPoint().x); xy1.push_back(o1[i]->getKeyPoint().y);
+                xy2.push_back(o2[m12[i]]->getKeyPoint().x); xy2.push_back(o2[m12[i]]->getKeyPoint().y);
+            }
+        const float dx = -4.f, dy = -1.f;      // frame 1 is frame 0 shifted by (4, 1) px
+        const std::vector<float> H21 = {1, 0, dx, 0, 1, dy, 0, 0, 1, 1.001f, 0.0005f, dx + 0.7f, -0.0004f, 0.999f, dy - 0.4f, 1e-6f, -1e-6f, 1};
+        const std::vector<float> H12 = {1, 0, -dx, 0, 1, -dy, 0, 0, 1, 0.999f, -0.0005f, -dx - 0.7f, 0.0004f, 1.001f, -dy + 0.4f, -1e-6f, 1e-6f, 1};
+        const std::vector<float> F21 = {0, 0, dy, 0, 0, -dx, -dy, dx, 0, 1e-7f, 0, dy * 1.1f, 0, 0, -dx, -dy, dx * 0.9f, 1e-3f};
+        OP::TwoViewScorerB200 scorer(pOrbDetector, 1.f);
+        OP::TwoViewScorerB200::Result r;
+        const int ok = scorer.score(xy1, xy2, H21, H12, F21, r) ? 1 : 0;
+        const int nm = (int)(xy1.size() / 2);
+        std::fwrite(&ok, 4, 1, fo); std::fwrite(&nm, 4, 1, fo);
+        std::fwrite(H21.data(), 4, 18, fo); std::fwrite(H12.data(), 4, 18, fo); std::fwrite(F21.data(), 4, 18, fo);
+        std::fwrite(r.scoreH.data(), 4, 2, fo); std::fwrite(r.scoreF.data(), 4, 2, fo);
+        std::fwrite(&r.bestH, 4, 1, fo); std::fwrite(&r.bestF, 4, 1, fo);
+        std::fwrite(r.inliersH.data(), 1, 2 * (size_t)nm, fo); std::fwrite(r.inliersF.data(), 1, 2 * (size_t)nm, fo);
+    }
     std::fclose(fo);
     return 0;
 }

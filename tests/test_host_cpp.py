@@ -68,8 +68,11 @@ def test_host_ops_match_oracle(tmp_path, cuda_required, H, W, nf, scale):
         assert k.tobytes() == ko.tobytes()
         assert int((d != do).any(axis=1).sum()) <= 1e-3 * nobs
         ref.append((ko, d.copy(), np.array_equal(d, do)))      # the program's OWN descriptors feed the oracle matcher below
+    m01 = None
     for f in range(1, n):
         n1 = int(take(np.int32, 1)[0]); m = take(np.int32, n1)
+        if f == 1:
+            m01 = m.copy()
         (k1, d1, e1), (k2, d2, e2) = ref[0], ref[f]
         ud1 = np.stack([k1["x"], k1["y"]], 1); ud2 = np.stack([k2["x"], k2["y"]], 1)
         mref = oo.match_window(k1, ud1, d1, k2, ud2, d2, oo.grid_for(W, H))
@@ -93,3 +96,21 @@ def test_host_ops_match_oracle(tmp_path, cuda_required, H, W, nf, scale):
     mref = oo.match_window(k1, uds[0], d1, k2, uds[1], d2, oo.grid_for(W, H, tuple(float(x) for x in b)))
     assert np.array_equal(m, mref)
     assert int(take(np.int32, 1)[0]) == 1           # the struct-of-arrays store gives identical observations and matches
+    assert int(take(np.int32, 1)[0]) == 1           # the ingest ring (pinned slots) gives identical observations
+    # two-view scoring of the frame 0 / frame 1 matches: scores bit-equal to the oracle's CheckHomography / CheckFundamental
+    ok, nm = take(np.int32, 2)
+    assert ok == 1
+    H21 = take(np.float32, 18).reshape(2, 9); H12 = take(np.float32, 18).reshape(2, 9); F21 = take(np.float32, 18).reshape(2, 9)
+    sH = take(np.float32, 2); sF = take(np.float32, 2)
+    bestH, bestF = take(np.int32, 2)
+    inH = take(np.uint8, 2 * nm).reshape(2, nm); inF = take(np.uint8, 2 * nm).reshape(2, nm)
+    (k1, _, _), (k2, _, _) = ref[0], ref[1]
+    i1 = np.nonzero(m01 >= 0)[0]; i2 = m01[i1]
+    assert len(i1) == nm
+    xy1 = np.stack([k1["x"][i1], k1["y"][i1]], 1); xy2 = np.stack([k2["x"][i2], k2["y"][i2]], 1)
+    for hyp in range(2):
+        s, inl = oo.check_homography(H21[hyp], H12[hyp], xy1, xy2)
+        assert np.float32(s).tobytes() == sH[hyp].tobytes() and np.array_equal(inl, inH[hyp])
+        s, inl = oo.check_fundamental(F21[hyp], xy1, xy2)
+        assert np.float32(s).tobytes() == sF[hyp].tobytes() and np.array_equal(inl, inF[hyp])
+    assert bestH == int(np.argmax(sH)) and inH[0].sum() > 0.8 * nm and bestF == int(np.argmax(sF))

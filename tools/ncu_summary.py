@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (ncu --set full) into one row per launch: duration, DRAM bytes, throughput %,
-occupancy, registers, pipe utilisation, instruction counts.
+occupancy, registers, pipe utilisation (xu% = the pipe POPC / F2I / MUFU issue on: the "integer-pipe utilisation for matching"
+BASELINE.json's metric asks for), warp- and thread-level instruction counts, shared-memory wavefronts and bank conflicts.
 Usage: python tools/ncu_summary.py gpurun_out/prof_X.ncu-rep [out.md [frames_per_launch]]
 The first line of out.md records the frames one launch processed (bench.py scales DRAM bytes per frame from it)."""
 import csv
@@ -26,9 +27,8 @@ WANT = [
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
     ("smsp__inst_executed.sum", "inst"),
-    ("smsp__thread_inst_executed.sum", "tinst"),
-    ("sm__inst_executed_pipe_xu.sum", "xu_inst"),          # POPC / F2I / MUFU issue here on sm_100 (BASELINE metric: the pipe that issues POPC)
-    ("sm__inst_executed_pipe_alu.sum", "alu_inst"),
+    ("sass__thread_inst_executed_true_per_opcode", "tinst"),      # thread-level instructions executed (predicated-off lanes not counted)
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
 ]
@@ -66,7 +66,7 @@ def main():
                     cells.append(f"{to_us(v, u):.1f}us")
                 elif s.startswith("dram_"):
                     cells.append(f"{to_bytes(v, u) / 1e6:.1f}MB")
-                elif s in ("inst", "tinst", "xu_inst", "alu_inst", "smem_conflicts", "smem_wavefronts"):
+                elif s in ("inst", "tinst", "smem_conflicts", "smem_wavefronts"):
                     cells.append(f"{float(v.replace(',', '')) / 1e6:.1f}M")
                 else:
                     cells.append(f"{float(v.replace(',', '')):.1f}" if "." in v else v)
