@@ -341,9 +341,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     unsigned* kmask = reinterpret_cast<unsigned*>(s_dyn + sm.offMask);
     unsigned short* queue = reinterpret_cast<unsigned short*>(s_dyn + sm.offQueue);
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ int s_q, s_nw, s_ovf, s_empty;
-    __shared__ int s_off[kFastMaxSegCells];
-    __shared__ unsigned short s_rowpre[kFastMaxSegCells][kMaxCellTile];      // keypoints of the cell above each row
+    __shared__ int s_q, s_ovf, s_empty;
     constexpr int NT = kFastThreads, NW = kFastThreads / 32, P = kFastPitch, PW = kFastPitch / 4;
 
     const int tid = threadIdx.x, f = blockIdx.y;
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_q = 0; s_nw = 0; s_ovf = 0; s_empty = 0;
+        s_q = 0; s_ovf = 0; s_empty = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -502,21 +500,6 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
             }
             return false;
         };
-        // ordered emit of one keypoint: its slot is its rank in the row-major order of its cell (the order cv::FAST
-        // reports) = keypoints of the cell above its row + keypoints of the cell to its left in the row
-        auto emit = [&](int e) {
-            const int row = (e >> 8) - 3, xx = (e & (P - 1)) - c_lo;
-            const int k = (int)__umulhi((unsigned)xx, L.magicW), x0 = k * wCell;
-            int rank = s_rowpre[k][row];
-            if (xx > x0) rank += mask_range_count(kmask + row * wpr, x0, xx);
-            RawRec r;
-            r.x = (unsigned short)(xx + xBase);
-            r.y = (unsigned short)(row + yBase);
-            r.score = smap[e]; r.pad = 0;
-            const int base = s_off[k];
-            if (base >= 0) outL[base + rank] = r;
-        };
-        int wlo = 0, wwin = 0;                       // this warp's keypoints of the pass: queue[wlo, wwin)
         const bool dense = s_ovf != 0;
         if (!dense) {
             // stage B: exact score of the survivors.  Each warp owns a contiguous slice of the queue and compacts the
@@ -540,16 +523,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                 wpos += __popc(m);
             }
             __syncthreads();                                             // the score map is complete
-            // stage C over the warp's corners; the keypoints are compacted to the front of the slice the same way
-            wlo = wwin = lo;
-            for (int base = lo; base < wpos; base += 32) {
-                const int qi = base + lane;
-                const int e = qi < wpos ? queue[qi] : 0;
-                const bool win = qi < wpos && nms(e);
-                const unsigned m = __ballot_sync(0xffffffffu, win);
-                if (win) queue[wwin + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
-                wwin += __popc(m);
-            }
+            // stage C over the warp's corners: the keypoints (strict 3x3 maxima) are marked in the bit mask
+            for (int qi = lo + lane; qi < wpos; qi += 32) nms(queue[qi]);
         } else {
             // dense path (rare: the survivors of stage A did not fit the queue, e.g. an image of pure noise): score every
             // interior pixel (in pass 2: of the empty cells), then NMS over the score map
@@ -560,57 +535,86 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                     const int s = fast_score(tile + e, P);
                     if (s >= th) smap[e] = (uint8_t)s;
                 }
-            if (tid == 0) s_nw = 0;
             __syncthreads();
             for (int row = 3; row < 3 + ih; ++row)
                 for (int xx = tid; xx < iw; xx += NT) {
                     if (pass && !((emptyCells >> __umulhi((unsigned)xx, L.magicW)) & 1u)) continue;
                     const int e = row * P + c_lo + xx;
-                    if (smap[e] && nms(e)) queue[atomicAdd(&s_nw, 1)] = (unsigned short)e;      // (the queue holds >= wcap entries)
+                    if (smap[e]) nms(e);
                 }
         }
         __syncthreads();
-        // keypoints per cell and above each row of the cell: one warp per cell, lanes over the rows.  A cell whose
-        // count is final appends to the level's raw list with one global atomic.
+        // count and ordered emit, one warp per cell, a lane per row (two rounds for cells higher than 32 rows): the lane
+        // reads its row of the cell out of the bit mask (<= 3 words, the cell's column range masked in), the warp scans the
+        // row counts, a cell whose count is final takes its place in the level's raw list with ONE global atomic, and every
+        // lane writes its row's keypoints at (cell offset + keypoints above its row) by walking its set bits — the row-major
+        // order inside the cell that cv::FAST reports, without a rank computation per keypoint.
         const bool lastPass = pass || minTh >= iniTh;
         for (int k = wid; k < nv; k += NW) {
             if (pass && !((emptyCells >> k) & 1u)) continue;
             const int x0 = k * wCell, x1 = min(x0 + wCell, iw);
+            const int wlo = x0 >> 5, nwd = ((x1 - 1) >> 5) - wlo + 1;                      // 1..3 mask words per row
+            const unsigned mFirst = 0xffffffffu << (x0 & 31), mLast = 0xffffffffu >> (31 - ((x1 - 1) & 31));
+            unsigned mw[2][3];
+            int pre[2];
             int run = 0;
-            for (int r0 = 0; r0 < ih; r0 += 32) {
-                const int row = r0 + lane;
-                const int n = row < ih ? mask_range_count(kmask + row * wpr, x0, x1) : 0;
-                int incl = n;
+#pragma unroll
+            for (int rd = 0; rd < 2; ++rd) {
+                const int row = rd * 32 + lane;
+                int cnt = 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    unsigned m = (row < ih && j < nwd) ? kmask[row * wpr + wlo + j] : 0u;
+                    if (j == 0) m &= mFirst;
+                    if (j == nwd - 1) m &= mLast;
+                    mw[rd][j] = m;
+                    cnt += __popc(m);
+                }
+                int incl = cnt;
 #pragma unroll
                 for (int ofs = 1; ofs < 32; ofs <<= 1) {
                     const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
                     if (lane >= ofs) incl += t;
                 }
-                if (row < ih) s_rowpre[k][row] = (unsigned short)(run + incl - n);
+                pre[rd] = run + incl - cnt;
                 run += __shfl_sync(0xffffffffu, incl, 31);
+                if (ih <= 32) { mw[1][0] = mw[1][1] = mw[1][2] = 0u; pre[1] = 0; break; }      // warp-uniform
             }
+            int base = 0;
             if (lane == 0) {
                 if (run == 0 && !lastPass) {
                     atomicOr(&s_empty, 1 << k);      // :787 "if(vKeysCell.empty())" -> retry at minThFAST
                 } else {
-                    int base = 0;
                     if (run > 0) {
                         base = atomicAdd(p.rawCount + f * g.nlevels + l, run);
                         if (base + run > L.rawCap) { atomicOr(p.err, ERR_RAW_OVERFLOW); base = -1; }
                     }
-                    s_off[k] = base;
                     info[k] = base >= 0 ? make_uint2((unsigned)base, (unsigned)run) : make_uint2(0u, 0u);
+                }
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (run == 0 || base < 0) continue;                                            // warp-uniform
+#pragma unroll
+            for (int rd = 0; rd < 2; ++rd) {
+                const int row = rd * 32 + lane;
+                RawRec* o = outL + base + pre[rd];
+                const uint8_t* srow = smap + (row + 3) * P + c_lo;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    unsigned m = mw[rd][j];
+                    while (m) {
+                        const int xx = ((wlo + j) << 5) + __ffs(m) - 1;
+                        m &= m - 1;
+                        RawRec r;
+                        r.x = (unsigned short)(xx + xBase);
+                        r.y = (unsigned short)(row + yBase);
+                        r.score = srow[xx]; r.pad = 0;
+                        *o++ = r;
+                    }
                 }
             }
         }
         __syncthreads();
-        // every keypoint of this pass lies in a cell whose count became final in this pass: write them out
-        if (!dense) {
-            for (int qi = wlo + lane; qi < wwin; qi += 32) emit(queue[qi]);
-        } else {
-            const int nw = s_nw;
-            for (int t = tid; t < nw; t += NT) emit(queue[t]);
-        }
         emptyCells = (unsigned)s_empty;
         if (lastPass || emptyCells == 0u) break;
         __syncthreads();                             // the queue is refilled by the next pass

@@ -8,4 +8,4 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
     2> gpurun_out/bench_${tag}.err | tail -1 | tee gpurun_out/bench_${tag}.json | cut -c1-300
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload seq64 --steps 5 --warmup 3 \
     2> gpurun_out/bench_seq_${tag}.err | tail -1 | tee gpurun_out/bench_seq_${tag}.json | cut -c1-300
-tail -3 gpurun_out/bench_${tag}.err gpurun_out/bench_seq_${tag}.err
+tail -n 3 gpurun_out/bench_${tag}.err; tail -n 3 gpurun_out/bench_seq_${tag}.err
