@@ -9,10 +9,9 @@ def find(s):
         if s in l: return i + 1
     return None
 marks = [('fast_score', 'int fast_score('), ('gt_any2', 'unsigned gt_any2('), ('mask_range_count', 'int mask_range_count('),
-         ('setup', 'void __launch_bounds__(kFastThreads) fast_band_kernel'), ('stageA', 'for (int pass = 0; pass < 2; ++pass)'),
+         ('setup', 'fast_band_kernel(const __grid_constant__ FrameGeom g'), ('stageA', 'for (int pass = 0; pass < 2; ++pass)'),
          ('nms+emit bodies', 'auto nms = [&]'), ('stageB', 'if (!dense) {'), ('stageC', 'stage C over the warp'),
-         ('dense', '// dense path (rare'), ('count', '// keypoints per cell and above each row'),
-         ('emit', '// every keypoint of this pass lies in a cell'), ('end', '// K3  quadtree distribution')]
+         ('dense', '// dense path (rare'), ('count+emit', '// count and ordered emit, one warp per cell'), ('end', '// K3  quadtree distribution')]
 marks = [(n, find(s)) for n, s in marks if find(s)]
 tot = {}
 for line in txt.split('\n'):
