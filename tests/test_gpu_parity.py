@@ -354,6 +354,75 @@ def test_fused_detect_match_chunked(ctxs, monkeypatch):
             ctx.close()
 
 
+def test_async_device_calls_with_changing_pairs_and_features(monkeypatch, cuda_required):
+    """Back-to-back ASYNCHRONOUS device-resident calls whose pair counts, pair lists and feature counts change between
+    calls (the front end toggles scaleNumFeatures(5) / (0.2), FE_SlamMonoV.cpp:136,176,247): the pair-table slots are fixed
+    size and guarded per slot, and the extra streams may not run ahead across a change of geometry."""
+    H, W = 376, 1241
+    fr = sequence(H, W, 61, 8, step=(5, 0))
+    padded = np.zeros((len(fr), H, 1248), np.uint8); padded[:, :, :W] = fr
+    monkeypatch.setenv("NAV24_RESIDENT_CHUNK", "3")          # several chunks on several streams: the run-ahead path
+    ctx = capi.OrbContext(2000)
+    try:
+        dptr = capi.C.c_void_p()
+        assert ctx.L.nav24_device_alloc(padded.nbytes, capi.C.byref(dptr)) == 0
+        assert ctx.L.nav24_memcpy_h2d(dptr, padded.ctypes.data_as(capi.C.c_void_p), padded.nbytes) == 0
+        grid = capi.grid_for(W, H)
+        calls = [(2000, [(0, 1), (2, 3), (4, 5), (6, 7), (1, 2)]), (2000, [(7, 0), (3, 4)]), (400, [(0, 7), (1, 6), (2, 5), (3, 4), (4, 3), (5, 2), (6, 1)]),
+                 (2000, [(5, 6)]), (10000, [(0, 1), (1, 2), (2, 3)])]
+        for nf, pairs in calls:                                # enqueue everything without a host synchronisation in between
+            ctx.set_num_features(nf)
+            ctx.detect_match_device(dptr.value, len(fr), W, H, 1248, 1248 * H, pairs, grid)
+        nf, pairs = calls[-1]
+        n, mono, kps, desc = ctx.fetch(len(fr))
+        m, nm = ctx.match_fetch(len(pairs))
+        o = oo.OrbOracle(nf)
+        for f in (0, 1, 2, 3):
+            mo, ko, do = o.detect(fr[f])
+            assert mono[f] == mo and n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes()
+        for q, (a, b) in enumerate(pairs):
+            want = _oracle_matches_on(kps, desc, n, a, b, oo.grid_for(W, H))
+            assert np.array_equal(m[q, :n[a]], want) and nm[q] == (want >= 0).sum()
+        # the same sequence of calls with a synchronisation after each gives the same final answer
+        for nf2, pairs2 in calls:
+            ctx.set_num_features(nf2)
+            ctx.detect_match_device(dptr.value, len(fr), W, H, 1248, 1248 * H, pairs2, grid)
+            ctx.sync()
+        n2, mono2, kps2, desc2 = ctx.fetch(len(fr))
+        m2, nm2 = ctx.match_fetch(len(pairs))
+        assert np.array_equal(n2, n) and np.array_equal(nm2, nm) and np.array_equal(m2, m)
+        for f in range(len(fr)):
+            assert kps2[f, :n[f]].tobytes() == kps[f, :n[f]].tobytes()
+        ctx.L.nav24_device_free(dptr)
+    finally:
+        ctx.close()
+
+
+def test_stage_timers_only_after_detect_device(ctxs):
+    """nav24_orb_stage_ms covers nav24_orb_detect_device only: after any other detect call it must say so instead of
+    returning the timings of an older call."""
+    ctx = capi.OrbContext(500)
+    try:
+        img = synth(260, 340, 3)
+        ctx.detect(img)
+        with pytest.raises(capi.Nav24Error) as e:
+            ctx.stage_ms()
+        assert e.value.code == capi.E_BADARG
+        padded = np.zeros((1, 260, 352), np.uint8); padded[0, :, :340] = img
+        dptr = capi.C.c_void_p()
+        assert ctx.L.nav24_device_alloc(padded.nbytes, capi.C.byref(dptr)) == 0
+        assert ctx.L.nav24_memcpy_h2d(dptr, padded.ctypes.data_as(capi.C.c_void_p), padded.nbytes) == 0
+        ctx.detect_device(dptr.value, 1, 340, 260, 352, 352 * 260)
+        ms = ctx.stage_ms()
+        assert (ms > 0).all() and ms[4] >= ms[:4].sum() * 0.9
+        ctx.detect(img)
+        with pytest.raises(capi.Nav24Error):
+            ctx.stage_ms()
+        ctx.L.nav24_device_free(dptr)
+    finally:
+        ctx.close()
+
+
 def test_batch_schedule_invariance_at_bench_scale(ctxs, monkeypatch):
     """A bench-sized batch (96 KITTI frames, 48 stereo pairs + pairs that span chunks): the result must not depend on
     how the host pipeline cuts it (tapered chunks on three streams vs one uniform chunk), and sampled frames / pairs
