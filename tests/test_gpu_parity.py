@@ -390,7 +390,9 @@ def test_async_device_calls_with_changing_pairs_and_features(monkeypatch, cuda_r
             ctx.sync()
         n2, mono2, kps2, desc2 = ctx.fetch(len(fr))
         m2, nm2 = ctx.match_fetch(len(pairs))
-        assert np.array_equal(n2, n) and np.array_equal(nm2, nm) and np.array_equal(m2, m)
+        assert np.array_equal(n2, n) and np.array_equal(nm2, nm)
+        for q, (a, b) in enumerate(pairs):
+            assert np.array_equal(m2[q, :n[a]], m[q, :n[a]])          # (entries beyond a frame's keypoint count are not written)
         for f in range(len(fr)):
             assert kps2[f, :n[f]].tobytes() == kps[f, :n[f]].tobytes()
         ctx.L.nav24_device_free(dptr)
