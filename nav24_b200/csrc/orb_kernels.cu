@@ -1423,9 +1423,14 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     QtSmem qs{};
     qs.sortCap = (min(maxNode, 12000) + 3) & ~3;      // records sorted in shared memory; larger levels sort in global memory
     size_t smem = quadtree_sort_bytes(qs.sortCap);
-    // Node tables in shared memory (52 bytes per node) when those of the largest level fit a 32 KB CTA together with the sort
-    // scratch: seven CTAs per SM, the same occupancy as with global tables (the kernel lives on overlapping barriers).
-    const size_t budget = 32 * 1024;
+    // Node tables in shared memory (52 bytes per node) when those of the largest level fit the CTA's budget together with the
+    // sort scratch.  A batch that fills the GPU (256-thread CTAs) gets 32 KB: seven CTAs per SM, the same occupancy as with
+    // global tables (the kernel lives on overlapping barriers).  A small batch (1024-thread CTAs, single-camera latency) has
+    // at most two CTAs per SM anyway: 100 KB each, or 200 KB when the whole grid is one wave of one CTA per SM — enough
+    // for level 0 of a 4K frame (1744 nodes) or of the x5 feature mode.
+    const int nCta = g.nlevels * B;
+    const bool big = nCta < 2 * 148;
+    const size_t budget = !big ? 32 * 1024 : (nCta <= 148 ? 200 * 1024 : 100 * 1024);
     const size_t nodeBytes = (size_t)maxNode * 52;
     if (smem + nodeBytes <= budget) {
         qs.nodeCap = maxNode;
@@ -1436,7 +1441,7 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     dim3 grid(g.nlevels, B);
     // 256 threads per (level, frame) when the batch fills the GPU (128: 5 % faster alone, slower in the chunked host
     // pipeline); a small batch (single-camera latency) has few CTAs, so each gets 1024 threads for its parallel passes
-    if (g.nlevels * B < 2 * 148) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, qs);
+    if (big) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, qs);
     else quadtree_kernel<256><<<grid, 256, smem, s>>>(g, p, qs);
     order_kernel<<<B, 256, 0, s>>>(g, p);
     return 2;
