@@ -361,13 +361,13 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         ctx->tabs.assign(nl, ResizeTab{});
         for (int l = 1; l < nl; ++l) {
             ResizeTab& T = ctx->tabs[l];
-            T = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l], 0, 0, 0};
+            T = ResizeTab{dOfs + oX[l], dAb + oX[l], dOfs + oY[l], dAb + oY[l], 0, 0, 0, 0};
             // warp strip: `rows` destination rows; CTA tile: 128 x 4*rows destination pixels (the level's rows dealt evenly
             // over the CTA rows); the TMA box over the source level covers the CTA tile (x start rounded down to 16 bytes,
             // and the three aligned words each thread reads)
             const int* xo = allOfs.data() + oX[l]; const int* yo = allOfs.data() + oY[l];
             const int dw = g.lv[l].w, dh = g.lv[l].h;
-            const int ctaRows = (dh + kResizeCtaRows - 1) / kResizeCtaRows;
+            const int ctaRows = (dh + kResizeCtaRows - 1) / kResizeCtaRows;      // (64 rows per CTA measured best of 16 .. 128)
             T.rows = std::max(1, std::min(kResizeMaxRows, ((dh + ctaRows - 1) / ctaRows + 3) / 4));
             int needW = 0, needH = 0;
             for (int x0 = 0; x0 < dw; x0 += 128) {
@@ -378,6 +378,19 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
                 needH = std::max(needH, yo[std::min(y0 + 4 * T.rows - 1, dh - 1)] + 2 - yo[y0]);
             T.boxW = needW <= 192 ? 192 : 256;
             T.boxH = needH;
+            // resize8_kernel: pixels 0..3 of a group of eight tap bytes [d, d+1] of the shifted word pair (0, 1), pixels 4..7
+            // of the pair (1, 2): d + 1 <= 7 resp. 4 <= d and d + 1 <= 11, with d = xofs[x] - xofs[group start]; and the
+            // 128-column half must fit the 192-byte box.  The TMA box start of a half is its first column's source offset
+            // rounded down to 16, so the two boxes of a CTA are encoded with the same map.
+            bool wide = T.boxW == 192;
+            for (int x8 = 0; x8 < dw && wide; x8 += 8) {
+                for (int k = 0; k < 8 && x8 + k < dw; ++k) {
+                    const int d = xo[x8 + k] - xo[x8];
+                    if (k < 4 ? d + 1 > 7 : (d < 4 || d + 1 > 11)) wide = false;
+                }
+                if ((xo[x8] & ~3) + 16 - (xo[x8 & ~127] & ~15) > 192) wide = false;      // the four-word window inside the half's box
+            }
+            T.wide = wide ? 1 : 0;
             if (needW > 256 || needH > 256) return ctx->fail(NAV24_E_GEOMETRY, "scale factor too large for the resize tile");
         }
         std::vector<FastSeg> segs;

@@ -132,6 +132,7 @@ struct ResizeTab {           // per level >= 1: source offsets and 11-bit coeffi
     const int* xofs; const short2* xab; const int* yofs; const short2* yab;
     int rows;                // destination rows per warp strip (<= kResizeMaxRows)
     int boxW, boxH;          // TMA box over the SOURCE level that covers one CTA tile (128 x 4*rows destination pixels)
+    int wide;                // 1: every group of eight destination pixels fits resize8_kernel's shared four-word window
 };
 
 constexpr int kResizeMaxRows = 32;     // destination rows of one warp strip of resize_kernel (one lane per row's constants)

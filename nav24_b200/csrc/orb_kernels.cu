@@ -262,6 +262,159 @@ stateBA:
 #undef NAV24_VROW
 }
 
+// The same resize with EIGHT destination pixels per thread: a half-warp covers 128 destination columns, a warp 256, a CTA
+// 256 columns x 4*rows rows fed by TWO TMA boxes side by side (one per 128-column half, each as in resize_kernel).  The
+// eight pixels share one source window of four aligned words — pixels 0..3 tap the shifted word pair (0, 1), pixels 4..7
+// the pair (1, 2) — and all the per-row control (row table load, state branch, pointer update, one 8-byte store), which was
+// a third of resize_kernel's instructions.  The shared window needs a source step below ~1.28 px per destination pixel
+// (true for the reference's 1.2 pyramid); the host checks every pixel group of a level (ResizeTab::wide) and launches
+// resize_kernel for levels that do not qualify.
+template <int BOXW>
+__global__ void __launch_bounds__(128) resize8_kernel(const __grid_constant__ CUtensorMap srcMap, int frameBase,
+                                                      uint8_t* __restrict__ dst, int dPitch, long long dFrame, int dw, int dh,
+                                                      ResizeTab t) {
+    extern __shared__ __align__(128) uint8_t s_rs[];       // [2][boxH][BOXW] source tiles of the two 128-column halves
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint2 s_yt[4][kResizeMaxRows];              // per warp strip: (source row inside the tile, b0 | b1 << 16) per destination row
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int rows = t.rows;
+    const int x0c = blockIdx.x * 256, y0c = blockIdx.y * 4 * rows;
+    const bool twoBoxes = x0c + 128 < dw;
+    const int half = lane >> 4;
+    const int xh = x0c + 128 * half;                       // first destination column of this lane's half
+    const int tileY0 = __ldg(t.yofs + y0c);
+    const unsigned barAddr = smem_u32(&bar);
+    const unsigned tileBytes = (unsigned)(BOXW * t.boxH);
+    const unsigned tileStride = (tileBytes + 127u) & ~127u;      // TMA destinations are 128-byte aligned
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(twoBoxes ? 2u * tileBytes : tileBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                smem_u32(s_rs)),
+            "l"(&srcMap), "r"(__ldg(t.xofs + x0c) & ~15), "r"(tileY0), "r"((int)blockIdx.z + frameBase), "r"(barAddr)
+            : "memory");
+        if (twoBoxes)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                    smem_u32(s_rs) + tileStride),
+                "l"(&srcMap), "r"(__ldg(t.xofs + x0c + 128) & ~15), "r"(tileY0), "r"((int)blockIdx.z + frameBase), "r"(barAddr)
+                : "memory");
+    }
+    const int x8 = xh + (lane & 15) * 8;
+    const int y0 = y0c + wid * rows;
+    if (y0 >= dh) return;                                  // warp-uniform
+    const int nrows = min(rows, dh - y0);
+    if (lane < nrows) {
+        const int yl = y0 + lane;
+        s_yt[wid][lane] = make_uint2((unsigned)(__ldg(t.yofs + yl) - tileY0),
+                                     __ldg(reinterpret_cast<const unsigned*>(t.yab) + yl));      // b0 | b1 << 16, both in [0, 2048]
+    }
+    // per-thread horizontal constants (columns beyond the level are clamped: their results are never stored)
+    const bool active = x8 < dw;
+    const int s0 = __ldg(t.xofs + min(x8, dw - 1));
+    const int tileX0 = __ldg(t.xofs + min(xh, dw - 1)) & ~15;
+    const unsigned shift = (unsigned)(s0 & 3) * 8u;
+    unsigned sel[8], ab[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int x = min(x8 + k, dw - 1);
+        int d = __ldg(t.xofs + x) - s0;                    // pixels 0..3: 0..6 inside the word pair (0, 1); 4..7: 4..10 -> 0..6 inside (1, 2)
+        d = k < 4 ? min(d, 6) : min(max(d - 4, 0), 6);
+        sel[k] = (unsigned)d | ((unsigned)(d + 1) << 4);
+        ab[k] = __ldg(reinterpret_cast<const unsigned*>(t.xab) + x);      // (a0, a1) as two u16 (both in [0, 2048])
+    }
+    const unsigned rpa = smem_u32(s_rs) + (half ? tileStride : 0u) + (unsigned)((s0 & ~3) - tileX0);      // the thread's window in tile row 0
+    __syncwarp();
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(barAddr), "r"(0u)
+                : "memory");
+        }
+    }
+#define NAV24_HROW8(i, h)                                                                                             \
+    {                                                                                                                 \
+        const unsigned a_ = rpa + (unsigned)(i) * (unsigned)BOXW;                                                     \
+        unsigned w0_, w1_, w2_, w3_;                                                                                  \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0_) : "r"(a_));                                                \
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1_) : "r"(a_));                                              \
+        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2_) : "r"(a_));                                              \
+        asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3_) : "r"(a_));                                             \
+        const unsigned lo_ = __funnelshift_r(w0_, w1_, shift), mid_ = __funnelshift_r(w1_, w2_, shift),               \
+                       hi_ = __funnelshift_r(w2_, w3_, shift);                                                        \
+        _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                                               \
+            unsigned tt_;                                                                                             \
+            if (k < 4) asm("prmt.b32 %0, %1, %2, %3;" : "=r"(tt_) : "r"(lo_), "r"(mid_), "r"(sel[k]));                \
+            else asm("prmt.b32 %0, %1, %2, %3;" : "=r"(tt_) : "r"(mid_), "r"(hi_), "r"(sel[k]));                      \
+            h[k] = __dp2a_lo(ab[k], tt_, 0u) >> 4;                                                                    \
+        }                                                                                                             \
+    }
+#define NAV24_VROW8(T, B, yc)                                                                                         \
+    {                                                                                                                 \
+        const unsigned c0_ = (yc) << 16, c1_ = (yc) & 0xffff0000u;                                                    \
+        unsigned v_[8];                                                                                               \
+        _Pragma("unroll") for (int k = 0; k < 8; ++k) v_[k] = __umulhi(T[k], c0_) + __umulhi(B[k], c1_) + 2u;         \
+        const unsigned p01_ = (v_[0] | (v_[1] << 16)) >> 2, p23_ = (v_[2] | (v_[3] << 16)) >> 2;                      \
+        const unsigned p45_ = (v_[4] | (v_[5] << 16)) >> 2, p67_ = (v_[6] | (v_[7] << 16)) >> 2;                      \
+        if (active) *reinterpret_cast<uint2*>(dp) = make_uint2(__byte_perm(p01_, p23_, 0x6420), __byte_perm(p45_, p67_, 0x6420)); \
+        dp += dPitch;                                                                                                 \
+    }
+    uint8_t* dp = dst + (long long)blockIdx.z * dFrame + (long long)y0 * dPitch + x8;
+    const uint2* yt = s_yt[wid];
+    unsigned A[8], B[8];
+    int cur = (int)yt[0].x;
+    NAV24_HROW8(cur, A)
+    NAV24_HROW8(cur + 1, B)
+    int j = 0;
+stateAB:
+    for (; j < nrows; ++j) {
+        const uint2 y = yt[j];
+        const int sy = (int)y.x;
+        if (sy == cur + 1) {                               // warp-uniform
+            NAV24_HROW8(sy + 1, A)
+            cur = sy;
+            NAV24_VROW8(B, A, y.y)
+            ++j;
+            goto stateBA;
+        }
+        if (sy != cur) {
+            NAV24_HROW8(sy, A)
+            NAV24_HROW8(sy + 1, B)
+            cur = sy;
+        }
+        NAV24_VROW8(A, B, y.y)
+    }
+    return;
+stateBA:
+    for (; j < nrows; ++j) {
+        const uint2 y = yt[j];
+        const int sy = (int)y.x;
+        if (sy == cur + 1) {
+            NAV24_HROW8(sy + 1, B)
+            cur = sy;
+            NAV24_VROW8(A, B, y.y)
+            ++j;
+            goto stateAB;
+        }
+        if (sy != cur) {
+            NAV24_HROW8(sy, B)
+            NAV24_HROW8(sy + 1, A)
+            cur = sy;
+        }
+        NAV24_VROW8(B, A, y.y)
+    }
+#undef NAV24_HROW8
+#undef NAV24_VROW8
+}
+
 // ------------------------------------------------------------------------------------------
 // K2  FAST-9/16 per cell with threshold fallback.  One CTA per (segment, frame); a segment is a run of up to
 // kFastMaxSegCells horizontally adjacent cells of one cell row (FastSeg, built on the host).
@@ -1355,15 +1508,22 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
     // (function attributes are per device and this library serves several devices and host threads: set on every call)
     cudaFuncSetAttribute(resize_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(resize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(resize8_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& D = g.lv[l];
         const ResizeTab& T = tabs[l];
-        dim3 grid((D.w + 127) / 128, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
-        const size_t smem = (size_t)((T.boxW * T.boxH + 127) / 128 * 128);
-        if (T.boxW == 192)
-            resize_kernel<192><<<grid, 128, smem, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
-        else
-            resize_kernel<256><<<grid, 128, smem, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
+        const size_t tile = (size_t)((T.boxW * T.boxH + 127) / 128 * 128);
+        if (T.wide) {      // eight pixels per thread: 256-column CTAs, two source boxes
+            dim3 grid((D.w + 255) / 256, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
+            resize8_kernel<192><<<grid, 128, 2 * tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch,
+                                                                                        g.pyrFrameBytes, D.w, D.h, T);
+        } else {
+            dim3 grid((D.w + 127) / 128, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
+            if (T.boxW == 192)
+                resize_kernel<192><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
+            else
+                resize_kernel<256><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
+        }
         ++n;
     }
     return n;
