@@ -1037,8 +1037,9 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
 // Shared-memory table sizes of quadtree_kernel (nodeCap 0: the node tables stay in global memory)
 struct QtSmem { int sortCap, nodeCap; };
 
-template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency)
-__global__ void __launch_bounds__(NT) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
+template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency; one CTA
+                       // per SM is enough there, so it may use 64 registers: the default bound of 32 spilled 616 bytes of loads)
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
     extern __shared__ __align__(16) unsigned long long s_sort[];
     __shared__ int s_scan[33];
     __shared__ int s_K, s_nexp;
@@ -1589,7 +1590,9 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     // at most two CTAs per SM anyway: 100 KB each, or 200 KB when the whole grid is one wave of one CTA per SM — enough
     // for level 0 of a 4K frame (1744 nodes) or of the x5 feature mode.
     const int nCta = g.nlevels * B;
-    const bool big = nCta < 2 * 148;
+    // (measured: between one and two waves the 1024-thread CTAs win on 4K frames — 47 k keys at level 0 — and lose on
+    // KITTI-sized ones, where seven 256-thread CTAs per SM overlap their barriers better)
+    const bool big = nCta <= 148 || (nCta < 2 * 148 && (long long)g.lv[0].w * g.lv[0].h >= 1500000);
     const size_t budget = !big ? 32 * 1024 : (nCta <= 148 ? 200 * 1024 : 100 * 1024);
     const size_t nodeBytes = (size_t)maxNode * 52;
     if (smem + nodeBytes <= budget) {
