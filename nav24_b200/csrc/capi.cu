@@ -199,13 +199,15 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
         if (L.wCell + 6 > kMaxCellTile || L.hCell + 6 > kMaxCellTile) return ctx->fail(NAV24_E_GEOMETRY, "FAST cell larger than the kernel tile");
         // FAST segments: runs of cells of one cell row whose tile (interior + 3-px rim + <= 16 px of alignment slack)
         // fits one TMA box (<= 256 px wide); the cells of a row are dealt evenly over the segments
-        const int fit = std::min(kFastMaxSegCells, (kFastPitch - 22) / L.wCell);
+        // ... and whose cells x rows fit one round of the CTA's threads (the count + emit step has a thread per cell row)
+        const int fit = std::max(1, std::min(std::min(kFastMaxSegCells, (kFastPitch - 22) / L.wCell), kFastThreads / L.hCell));
         L.segsPerRow = (L.nCols + fit - 1) / fit;
         L.segCols = (L.nCols + L.segsPerRow - 1) / L.segsPerRow;
         L.segsPerRow = (L.nCols + L.segCols - 1) / L.segCols;
         L.boxW = kFastPitch;
         L.boxH = L.hCell + 6;
         L.magicW = 0xFFFFFFFFu / (unsigned)L.wCell + 1u;
+        L.magicH = 0xFFFFFFFFu / (unsigned)L.hCell + 1u;
         L.cellBase = cellBase;
         L.blurTileBase = stripBase;
         stripBase += ((L.w + 127) / 128) * ((L.h + kBlurCtaRows - 1) / kBlurCtaRows);

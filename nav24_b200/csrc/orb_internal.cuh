@@ -38,6 +38,7 @@ struct LevelGeom {
     int segCols, segsPerRow; // FAST segment = segCols horizontally adjacent cells of one cell row (the last may hold fewer)
     int boxW, boxH;          // TMA box of one FAST segment: kFastPitch x (hCell+6)
     unsigned magicW;         // 0xFFFFFFFF / wCell + 1: floor(n / wCell) = umulhi(n, magicW) for n < 65536
+    unsigned magicH;         // the same for hCell
     int cellBase;            // first cell id of this level inside the per-frame cell table
     int blurTileBase;        // first CTA tile (128 px x kBlurCtaRows rows) of this level in blur_kernel
     int rawCap;              // raw-corner capacity of this level (records)

@@ -495,6 +495,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     unsigned short* queue = reinterpret_cast<unsigned short*>(s_dyn + sm.offQueue);
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_q, s_ovf, s_empty;
+    __shared__ int s_scan[33];
+    __shared__ int s_cellFirst[kFastMaxSegCells], s_cellEnd[kFastMaxSegCells], s_cellBase[kFastMaxSegCells];
     constexpr int NT = kFastThreads, NW = kFastThreads / 32, P = kFastPitch, PW = kFastPitch / 4;
 
     const int tid = threadIdx.x, f = blockIdx.y;
@@ -697,72 +699,67 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                 }
         }
         __syncthreads();
-        // count and ordered emit, one warp per cell, a lane per row (two rounds for cells higher than 32 rows): the lane
-        // reads its row of the cell out of the bit mask (<= 3 words, the cell's column range masked in), the warp scans the
-        // row counts, a cell whose count is final takes its place in the level's raw list with ONE global atomic, and every
-        // lane writes its row's keypoints at (cell offset + keypoints above its row) by walking its set bits — the row-major
-        // order inside the cell that cv::FAST reports, without a rank computation per keypoint.
+        // count and ordered emit by the whole CTA in ONE round: a thread per (cell, row) — the host sizes the segments so that
+        // cells x rows <= 256 — reads its row of its cell out of the bit mask (<= 3 words, the cell's column range masked
+        // in); one block scan gives every row its offset, the first and last row of a cell turn that into offsets inside
+        // the cell and the cell's count; a cell whose count is final takes its place in the level's raw list with ONE global
+        // atomic, and every thread writes its row's keypoints at (cell offset + keypoints above its row) by walking its
+        // set bits — the row-major order inside the cell that cv::FAST reports, without a rank computation per keypoint.
         const bool lastPass = pass || minTh >= iniTh;
-        for (int k = wid; k < nv; k += NW) {
-            if (pass && !((emptyCells >> k) & 1u)) continue;
+        {
+            const int hC = L.hCell;
+            const int k = (int)__umulhi((unsigned)tid, L.magicH), row = tid - k * hC;      // tid / hCell (tid < 65536)
+            const bool item = k < nv && row < ih && !(pass && !((emptyCells >> k) & 1u));
             const int x0 = k * wCell, x1 = min(x0 + wCell, iw);
             const int wlo = x0 >> 5, nwd = ((x1 - 1) >> 5) - wlo + 1;                      // 1..3 mask words per row
-            const unsigned mFirst = 0xffffffffu << (x0 & 31), mLast = 0xffffffffu >> (31 - ((x1 - 1) & 31));
-            unsigned mw[2][3];
-            int pre[2];
-            int run = 0;
+            unsigned mw[3];
+            int cnt = 0;
 #pragma unroll
-            for (int rd = 0; rd < 2; ++rd) {
-                const int row = rd * 32 + lane;
-                int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    unsigned m = (row < ih && j < nwd) ? kmask[row * wpr + wlo + j] : 0u;
-                    if (j == 0) m &= mFirst;
-                    if (j == nwd - 1) m &= mLast;
-                    mw[rd][j] = m;
-                    cnt += __popc(m);
-                }
-                int incl = cnt;
-#pragma unroll
-                for (int ofs = 1; ofs < 32; ofs <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, ofs);
-                    if (lane >= ofs) incl += t;
-                }
-                pre[rd] = run + incl - cnt;
-                run += __shfl_sync(0xffffffffu, incl, 31);
-                if (ih <= 32) { mw[1][0] = mw[1][1] = mw[1][2] = 0u; pre[1] = 0; break; }      // warp-uniform
+            for (int j = 0; j < 3; ++j) {
+                unsigned m = (item && j < nwd) ? kmask[row * wpr + wlo + j] : 0u;
+                if (j == 0) m &= 0xffffffffu << (x0 & 31);
+                if (j == nwd - 1) m &= 0xffffffffu >> (31 - ((x1 - 1) & 31));
+                mw[j] = m;
+                cnt += __popc(m);
             }
-            int base = 0;
-            if (lane == 0) {
+            int tot;
+            const int ex = block_excl_scan(cnt, &tot, s_scan);
+            if (k < nv && row == 0) s_cellFirst[k] = ex;                                   // (rows 0 and ih-1 exist for every valid cell)
+            if (k < nv && row == ih - 1) s_cellEnd[k] = ex + cnt;
+            __syncthreads();
+            if (tid < nv && !(pass && !((emptyCells >> tid) & 1u))) {
+                const int run = s_cellEnd[tid] - s_cellFirst[tid];
                 if (run == 0 && !lastPass) {
-                    atomicOr(&s_empty, 1 << k);      // :787 "if(vKeysCell.empty())" -> retry at minThFAST
+                    atomicOr(&s_empty, 1 << tid);      // :787 "if(vKeysCell.empty())" -> retry at minThFAST
+                    s_cellBase[tid] = -1;
                 } else {
+                    int base = 0;
                     if (run > 0) {
                         base = atomicAdd(p.rawCount + f * g.nlevels + l, run);
                         if (base + run > L.rawCap) { atomicOr(p.err, ERR_RAW_OVERFLOW); base = -1; }
                     }
-                    info[k] = base >= 0 ? make_uint2((unsigned)base, (unsigned)run) : make_uint2(0u, 0u);
+                    s_cellBase[tid] = base;
+                    info[tid] = base >= 0 ? make_uint2((unsigned)base, (unsigned)run) : make_uint2(0u, 0u);
                 }
             }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (run == 0 || base < 0) continue;                                            // warp-uniform
+            __syncthreads();
+            if (cnt > 0) {
+                const int base = s_cellBase[k];
+                if (base >= 0) {
+                    RawRec* o = outL + base + (ex - s_cellFirst[k]);
+                    const uint8_t* srow = smap + (row + 3) * P + c_lo;
 #pragma unroll
-            for (int rd = 0; rd < 2; ++rd) {
-                const int row = rd * 32 + lane;
-                RawRec* o = outL + base + pre[rd];
-                const uint8_t* srow = smap + (row + 3) * P + c_lo;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    unsigned m = mw[rd][j];
-                    while (m) {
-                        const int xx = ((wlo + j) << 5) + __ffs(m) - 1;
-                        m &= m - 1;
-                        RawRec r;
-                        r.x = (unsigned short)(xx + xBase);
-                        r.y = (unsigned short)(row + yBase);
-                        r.score = srow[xx]; r.pad = 0;
-                        *o++ = r;
+                    for (int j = 0; j < 3; ++j) {
+                        unsigned m = mw[j];
+                        while (m) {
+                            const int xx = ((wlo + j) << 5) + __ffs(m) - 1;
+                            m &= m - 1;
+                            RawRec r;
+                            r.x = (unsigned short)(xx + xBase);
+                            r.y = (unsigned short)(row + yBase);
+                            r.score = srow[xx]; r.pad = 0;
+                            *o++ = r;
+                        }
                     }
                 }
             }
