@@ -854,13 +854,22 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
         for (int k = tid; k < 4 * size; k += nth) childCnt[k] = 0;
         if (tid == 0) { *s_nexp = 0; *s_K = 0x7fffffff; }
         __syncthreads();
-        for (int i = tid; i < n; i += nth) {
-            const int nd = nodeOfKey[i];
-            const QNode q = cur[nd];
-            if (q.count > 1) {
-                const RawRec k = keys[i];
-                atomicAdd(&childCnt[nd * 4 + quadrant_of(q, k.x, k.y)], 1);
+        // (four keys per thread and trip: the global loads of a trip are issued together, so a pass pays the L2 latency
+        // of the streamed key arrays once per four keys instead of once per key)
+        for (int i0 = tid; i0 < n; i0 += 4 * nth) {
+            int nd[4]; unsigned kxy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nth;
+                nd[u] = i < n ? (int)nodeOfKey[i] : -1;
+                kxy[u] = i < n ? *reinterpret_cast<const unsigned*>(keys + i) : 0u;      // x | y << 16
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (nd[u] >= 0) {
+                    const QNode q = cur[nd[u]];
+                    if (q.count > 1) atomicAdd(&childCnt[nd[u] * 4 + quadrant_of(q, (int)(kxy[u] & 0xffffu), (int)(kxy[u] >> 16))], 1);
+                }
         }
         __syncthreads();
 
@@ -992,18 +1001,28 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
             }
         }
         if (nexp) atomicAdd(s_nexp, nexp);
-        for (int i = tid; i < n; i += nth) {
-            const int nd = nodeOfKey[i];
-            const int a = aux[nd];
-            if (a >= 0) {
-                const RawRec kk = keys[i];
-                const int k = quadrant_of(cur[nd], kk.x, kk.y);
-                const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);      // one load instead of k dependent ones
-                const int cidx = a + (k > 0 && cc.x > 0) + (k > 1 && cc.y > 0) + (k > 2 && cc.z > 0);
-                nodeOfKey[i] = (unsigned short)(C - 1 - cidx);
-            } else {
-                nodeOfKey[i] = (unsigned short)(C + (-a - 1));
+        for (int i0 = tid; i0 < n; i0 += 4 * nth) {
+            int nd[4]; unsigned kxy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nth;
+                nd[u] = i < n ? (int)nodeOfKey[i] : -1;
+                kxy[u] = i < n ? *reinterpret_cast<const unsigned*>(keys + i) : 0u;
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (nd[u] >= 0) {
+                    const int a = aux[nd[u]];
+                    int to;
+                    if (a >= 0) {
+                        const int k = quadrant_of(cur[nd[u]], (int)(kxy[u] & 0xffffu), (int)(kxy[u] >> 16));
+                        const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd[u] * 4);      // one load instead of k dependent ones
+                        to = C - 1 - (a + (k > 0 && cc.x > 0) + (k > 1 && cc.y > 0) + (k > 2 && cc.z > 0));
+                    } else {
+                        to = C + (-a - 1);
+                    }
+                    nodeOfKey[i0 + u * nth] = (unsigned short)to;
+                }
         }
         __syncthreads();
         { QNode* t = cur; cur = nxt; nxt = t; }
