@@ -54,6 +54,12 @@ struct nav24_orb {
     cudaStream_t stream = nullptr, copyStream = nullptr, outStream = nullptr;
     cudaStream_t xstream[kMaxStreams] = {nullptr, nullptr, nullptr, nullptr};      // [0] = stream; [1..] extra compute streams
     cudaEvent_t evJoinX[kMaxStreams] = {nullptr, nullptr, nullptr, nullptr};
+    // one side stream per compute stream: the blur of a SMALL chunk (it needs only the pyramid) runs there, next to the
+    // latency-bound quadtree of the same chunk: single KITTI frame 0.207 -> 0.198 ms.  Batches that fill the GPU gain nothing
+    // from it (measured: 6.52 vs 6.54 ms per 1024 frames), so they keep the whole chain on one stream (NAV24_BLUR_FORK=0: never)
+    cudaStream_t sstream[kMaxStreams] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evFork[kMaxStreams] = {nullptr, nullptr, nullptr, nullptr}, evBlur[kMaxStreams] = {nullptr, nullptr, nullptr, nullptr};
+    int blurFork = 1;
     int nStreams = 3;                          // compute streams the chunks rotate over (NAV24_STREAMS)
     int taper = 1;                             // host pipeline: short first and last chunks (NAV24_TAPER=0: uniform)
     std::vector<cudaEvent_t> evIn, evDone;      // per chunk of the host-buffer pipeline (no timing)
@@ -537,7 +543,7 @@ int encode_maps(nav24_orb* ctx, int B) {
 
 // enqueue the per-frame chain for frames [f0, f0+C) on stream s; no host synchronisation.  With stages = true the
 // five stage events of this run are recorded (nav24_orb_stage_ms).
-int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
+int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages, int si = -1) {
     const FrameGeom& g = ctx->g;
     const DevPtrs q = chunk_ptrs(ctx, f0);
     if (stages) {
@@ -549,9 +555,20 @@ int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages) {
     if (stages) CK(cudaEventRecord(ctx->ev[1], s));
     ctx->launches += launch_fast(g, q, ctx->maps, C, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);
     if (stages) CK(cudaEventRecord(ctx->ev[2], s));
+    // the blur reads only the pyramid: on the side stream of compute stream si it runs next to the quadtree (which is
+    // bound by barrier and dependent-access latency); small chunks only, see nav24_orb::sstream
+    const bool fork = ctx->blurFork && C <= 4 && si >= 0 && ctx->sstream[si] && !stages;
+    if (fork) {
+        CK(cudaEventRecord(ctx->evFork[si], s));
+        CK(cudaStreamWaitEvent(ctx->sstream[si], ctx->evFork[si], 0));
+        ctx->launches += launch_blur(g, q, ctx->mapsBlurSrc, C, ctx->sstream[si]);
+        CK(cudaEventRecord(ctx->evBlur[si], ctx->sstream[si]));
+    }
     ctx->launches += launch_quadtree(g, q, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[3], s));
-    ctx->launches += launch_describe(g, q, ctx->mapsBlurSrc, ctx->mapsOri, ctx->mapsBlur, ctx->mapsBlurN, C, s);
+    if (fork) CK(cudaStreamWaitEvent(s, ctx->evBlur[si], 0));
+    else ctx->launches += launch_blur(g, q, ctx->mapsBlurSrc, C, s);
+    ctx->launches += launch_describe(g, q, ctx->mapsOri, ctx->mapsBlur, ctx->mapsBlurN, C, s);
     if (ctx->cam.model != NAV24_CAM_PINHOLE)      // Calibration::undistort between detect and matchV (FE_SlamMonoV.cpp:115)
         ctx->launches += launch_undistort_frames(ctx->cam, q.outKp, q.nOut, g.outCap, C, q.outUd, s);
     if (stages) CK(cudaEventRecord(ctx->ev[4], s));
@@ -689,6 +706,7 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
     if (const char* e = getenv("NAV24_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= nav24_orb::kMaxStreams) ctx->nStreams = v; }
     if (const char* e = getenv("NAV24_TAPER")) ctx->taper = atoi(e);
     if (const char* e = getenv("NAV24_RESIDENT_CHUNK")) { const int v = atoi(e); if (v > 0) ctx->residentChunk = v; }
+    if (const char* e = getenv("NAV24_BLUR_FORK")) ctx->blurFork = atoi(e);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->xstream[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->xstream[2], cudaStreamNonBlocking) != cudaSuccess ||
@@ -705,6 +723,11 @@ int nav24_orb_create(const nav24_orb_params* params, int device, nav24_orb** out
         cudaEventCreateWithFlags(&ctx->evSlotDone[1], cudaEventDisableTiming) != cudaSuccess)
         return NAV24_E_CUDA;
     ctx->xstream[0] = ctx->stream;
+    for (int i = 0; i < nav24_orb::kMaxStreams; ++i)
+        if (cudaStreamCreateWithFlags(&ctx->sstream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->evFork[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->evBlur[i], cudaEventDisableTiming) != cudaSuccess)
+            return NAV24_E_CUDA;
     for (auto& r : ctx->evRing) for (auto& e : r) cudaEventCreate(&e);
     for (auto& e : ctx->evT) cudaEventCreate(&e);
     return NAV24_OK;
@@ -733,6 +756,11 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     for (auto& e : ctx->evT) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->evIn) cudaEventDestroy(e);
     for (auto& e : ctx->evDone) cudaEventDestroy(e);
+    for (int i = 0; i < nav24_orb::kMaxStreams; ++i) {
+        if (ctx->sstream[i]) cudaStreamDestroy(ctx->sstream[i]);
+        if (ctx->evFork[i]) cudaEventDestroy(ctx->evFork[i]);
+        if (ctx->evBlur[i]) cudaEventDestroy(ctx->evBlur[i]);
+    }
     if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->evPrevEnd) cudaEventDestroy(ctx->evPrevEnd);
@@ -984,7 +1012,7 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
                     if (tight)
                         ctx->launches += channels == 3 ? launch_bgr2gray((const uint8_t*)ctx->bL0Tight.ptr, w, h, l0, ctx->l0Pitch, 1, cs)
                                                        : launch_repack((const uint8_t*)ctx->bL0Tight.ptr, w, h, l0, ctx->l0Pitch, 1, cs);
-                    const int prc = run_pipeline(ctx, 0, 1, cs, false);
+                    const int prc = run_pipeline(ctx, 0, 1, cs, false, k % nS);
                     const cudaError_t ee = cudaStreamEndCapture(cs, &graph);
                     if (prc == NAV24_OK && ee == cudaSuccess && graph &&
                         cudaGraphInstantiate(&ctx->graphExec, graph, 0) == cudaSuccess) {
@@ -1017,7 +1045,7 @@ int run_chunked(nav24_orb* ctx, int B, int w, int h, const uint8_t* hostGray, si
                 ctx->launches += channels == 3 ? launch_bgr2gray(src, w, h, dst, ctx->l0Pitch, c, cs)
                                                : launch_repack(src, w, h, dst, ctx->l0Pitch, c, cs);
             }
-            rc = run_pipeline(ctx, f0, c, cs, stages);
+            rc = run_pipeline(ctx, f0, c, cs, stages, k % nS);
             if (rc != NAV24_OK) return rc;
         }
         const int np = firstOfChunk[k + 1] - firstOfChunk[k];

@@ -147,8 +147,9 @@ int launch_bgr2gray(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, 
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s);
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
-int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, const TmaMaps& mapsOri, const TmaMaps& mapsBlur,
-                    const TmaMaps& mapsBlurN, int B, cudaStream_t s);
+int launch_blur(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, int B, cudaStream_t s);
+int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, const TmaMaps& mapsBlurN, int B,
+                    cudaStream_t s);
 int launch_debug_sort(unsigned long long* d_recs, int n, cudaStream_t s);   // test hook (stdsort_warp.cuh)
 
 // matchers (match_kernels.cu)

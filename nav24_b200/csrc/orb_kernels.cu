@@ -1626,17 +1626,17 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     return 2;
 }
 
-int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, const TmaMaps& mapsOri, const TmaMaps& mapsBlur,
-                    const TmaMaps& mapsBlurN, int B, cudaStream_t s) {
-    int n = 0;
-    {
-        dim3 grid(g.blurTiles, B);
-        blur_kernel<<<grid, 128, 0, s>>>(g, p, mapsBlurSrc);
-        ++n;
-    }
+int launch_blur(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, int B, cudaStream_t s) {
+    dim3 grid(g.blurTiles, B);
+    blur_kernel<<<grid, 128, 0, s>>>(g, p, mapsBlurSrc);
+    return 1;
+}
+
+int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, const TmaMaps& mapsBlurN, int B,
+                    cudaStream_t s) {
     dim3 grid((g.kpPerFrame + kDescWarps * kDescSlots - 1) / (kDescWarps * kDescSlots), B);
     describe_kernel<<<grid, kDescWarps * 32, 0, s>>>(g, p, mapsOri, mapsBlur, mapsBlurN);
-    return n + 1;
+    return 1;
 }
 
 }  // namespace nav24
