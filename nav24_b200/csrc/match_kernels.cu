@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
     __shared__ int s_scan[33];
     __shared__ int s_hist[kHisto];
     __shared__ int s_ind[3];
-    __shared__ int s_nm, s_nA, s_poolUsed, s_big, s_changed, s_ovf;
+    __shared__ int s_nm, s_nA, s_poolUsed, s_big, s_changed, s_ovf, s_nq;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
     const int pr = a.pairOrder ? a.pairOrder[a.pairBase + blockIdx.x] : a.pairBase + (int)blockIdx.x;
     PairView v;
@@ -180,8 +180,16 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
     for (int j = tid; j < v.n2; j += nth) { dist2[j] = 0x7fffffff; m21[j] = -1; }
     for (int i = tid; i < v.n1; i += nth) { m12[i] = -1; bins[i] = -1; candCnt[i] = 0; }
     if (tid < kHisto) s_hist[tid] = 0;
-    if (tid == 0) { s_nA = 0; s_poolUsed = 0; s_big = 0; s_changed = 0; s_ovf = 0; }
+    if (tid == 0) { s_nA = 0; s_poolUsed = 0; s_big = 0; s_changed = 0; s_ovf = 0; s_nq = 0; }
     __syncthreads();
+    // the queries — octave-0 keypoints of frame 1 (:120-122) — are listed up front (any order: their candidate lists are
+    // independent), in the candidate pool, which is free until phase A is over; otherwise every warp of phase A would
+    // discover its queries one dependent global load at a time (a quarter of this kernel's stall samples)
+    for (int i = tid; i < v.n1; i += nth)
+        if (v.k1[i].octave == 0) {
+            const int q = atomicAdd(&s_nq, 1);
+            if (q < sm.pool) s_pool[q] = i;
+        }
     for (int j = tid; j < v.n2; j += nth) {
         int c = -1;
         if (v.k2[j].octave == 0) {
@@ -227,8 +235,11 @@ __global__ void __launch_bounds__(1024) match_window_kernel(const MatchArgs a, c
     // test as second best ((float)dist*ratio > TH_LOW >= best) is equivalent to "no candidate".
     // Entry = (j << 14) | (rotation bin << 9) | distance, so that the sequential phase touches no global memory.
     const float thLowF = (float)a.thLow;
-    for (int i1 = wid; i1 < v.n1; i1 += nw) {
-        if (v.k1[i1].octave > 0) continue;                       // :120-122
+    const int nq = s_nq;
+    const bool listed = nq <= sm.pool;                           // (else: walk all keypoints, as the reference does)
+    for (int qi = wid; qi < (listed ? nq : v.n1); qi += nw) {
+        const int i1 = listed ? s_pool[qi] : qi;
+        if (!listed && v.k1[i1].octave > 0) continue;            // :120-122
         const float ang1 = v.k1[i1].angle;
         int cnt = 0;
         for_each_candidate(a, v, cellStart, items, i1, [&](int j, int d) {

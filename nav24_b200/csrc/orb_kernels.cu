@@ -561,7 +561,11 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     const int ngx = sg.ngx, rc = sg.rc;             // stage A work items: (word column, chunk of rc rows), one round
     const int nItems = ngx * sg.nChunks;
     unsigned emptyCells = 0;                         // pass 1: cells without a keypoint at iniTh
-    const unsigned sqAddr = smem_u32(&s_q), qAddr = smem_u32(queue);
+    unsigned sqAddr = smem_u32(&s_q), qAddr = smem_u32(queue), tileAddr = smem_u32(tile);
+    // (opaque to the compiler: otherwise it re-derives these shared-window addresses — S2R + LEA — at every use in stage A)
+    asm volatile("mov.u32 %0, %0;" : "+r"(sqAddr));
+    asm volatile("mov.u32 %0, %0;" : "+r"(qAddr));
+    asm volatile("mov.u32 %0, %0;" : "+r"(tileAddr));
     RawRec* outL = p.raw + (long long)f * g.rawPerFrame + L.rawOff;
     const int xBase = 3 + sg.cj0 * wCell, yBase = 3 + sg.ci * L.hCell;      // :811-812, relative to (minBorderX, minBorderY)
 
@@ -608,7 +612,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
                 if (alive) {      /* (PTX: the C++ atomicAdd drags in the compiler's warp-aggregation path and */    \
                     unsigned pos;     /* generic-address set-up, 40 instructions per row instead of 16) */              \
                     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos) : "r"(sqAddr), "r"(__popc(alive)) : "memory"); \
-                    const unsigned e = (unsigned)(tp - tile);                                                        \
+                    const unsigned e = smem_u32(tp) - tileAddr;                                                      \
                     if (pos + 4 <= kFastQueueCap) {      /* else: s_q > cap -> the dense path below */                \
                         unsigned qa = qAddr + 2u * pos;                                                              \
                         if (alive & 0x80u) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "r"(e) : "memory"); qa += 2u; }        \
@@ -1090,10 +1094,47 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) quadtree_kernel(const 
     int* sAux = reinterpret_cast<int*>(sB + qs.nodeCap);
     unsigned* sBest = reinterpret_cast<unsigned*>(sAux + qs.nodeCap);
     const bool useSm = L.nodeCap <= qs.nodeCap;      // CTA-uniform
-    for (int c = tid >> 5; c < nC; c += nth >> 5) {
-        const uint2 ci = cinfo[c];
-        const int d = cdst[c];
-        for (int k = tid & 31; k < (int)ci.y; k += 32) gkeys[d + k] = raw[ci.x + k];
+    // A warp takes 32 consecutive cells, lane j the table entry of cell c0 + j.  Their keys are consecutive in the ordered
+    // array, so entry t of the group goes to gkeys[first + t] (coalesced) and comes from the cell whose inclusive count
+    // first exceeds t (binary search over the lanes); the trips are independent, two are in flight at a time.  (One warp
+    // per cell — table entry, then keys, then the next cell — was a chain of dependent L2 latencies: 17 % of this kernel's
+    // stall samples.)
+    {
+        const int lane = tid & 31;
+        for (int c0 = (tid >> 5) * 32; c0 < nC; c0 += nth) {
+            const int c = c0 + lane;
+            const uint2 ci = c < nC ? cinfo[c] : make_uint2(0u, 0u);
+            const int first = cdst[c0];
+            int incl = (int)ci.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int T = __shfl_sync(0xffffffffu, incl, 31);
+            const int srcOff = (int)ci.x - (incl - (int)ci.y);      // source index of entry t of this lane's cell = srcOff + t
+            for (int t0 = 0; t0 < T; t0 += 64) {
+                int src[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    int col = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int probe = __shfl_sync(0xffffffffu, incl, col + step - 1);
+                        if (probe <= t) col += step;
+                    }
+                    src[u] = __shfl_sync(0xffffffffu, srcOff, min(col, 31)) + t;
+                }
+                RawRec r[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (t0 + 32 * u + lane < T) r[u] = raw[src[u]];
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (t0 + 32 * u + lane < T) gkeys[first + t0 + 32 * u + lane] = r[u];
+            }
+        }
     }
     if (tid == 0) p.rawTotal[f * g.nlevels + l] = n;
     __syncthreads();
@@ -1329,71 +1370,105 @@ __device__ const PatternT kPatternT = make_pattern_t();
 // bytes inside the disc (0 outside), (y) their 0/1 mask.  m10 = sum dp4a(word, x), m01 = sum v * dp4a(word, y).
 // Built once per context on the host (capi.cu: build_orientation_table) from umax[] (OP_FtDtOrbSlam.cpp:484-499).
 //
-// A warp walks kDescSlots consecutive keypoint slots of one frame (warps never synchronise with each other: the first
-// multi-warp version of this kernel was slower because a CTA held its resources until its slowest warp finished; here
-// every warp has the same amount of work).  Both patches of a keypoint — 31 rows of the un-blurred level for the
-// moments, 37 rows of the blurred level for the 512 samples — arrive in shared memory as two TMA boxes (x start rounded
-// down to 16 bytes, hence the 48- and 64-byte box widths): no per-thread address arithmetic, no register staging, and
-// the gathers index a power-of-two row pitch.  The boxes are double-buffered: while keypoint k is computed the boxes
-// of keypoint k+1 are in flight and the LevelKp record of keypoint k+2 is being loaded.
+// A warp owns kDescSlots consecutive keypoint slots of one frame and works in two passes over its live keypoints, so that
+// everything that is ONE value per keypoint is computed by ONE LANE per keypoint, for all of the warp's keypoints at once,
+// instead of redundantly by 32 lanes keypoint after keypoint (the first version spent 28 % of its instructions that way):
+//   set-up  lane i < kDescSlots: level, liveness and record of slot i (the dead slots are the tail of every level's range)
+//   pass 1  per keypoint: the 31-row patch of the un-blurred level arrives as a TMA box; DP4A moments of the disc (279 aligned
+//           words, 9 per lane), two REDUX sums; lane i keeps (m01, m10) of keypoint i
+//   between lane i: fastAtan2, sincosf, the nav24_kp record and the angle of keypoint i
+//   pass 2  per keypoint: the 37-row patch of the blurred level arrives as a TMA box; (cos, sin) come from lane i by SHFL;
+//           512 rotated samples, lane j produces descriptor byte j
+// The boxes (x start rounded down to 16 bytes, hence the 48- and 80-byte box widths) land in a ring of kDescStages stages
+// per warp, each holding one descriptor box or two orientation boxes: while a keypoint is computed, the boxes of the next
+// kDescStages - 1 (pass 2) or 2 * kDescStages - 1 (pass 1, whose items are short) keypoints are in flight.  Warps never
+// synchronise with each other (a CTA is four independent warps).
 constexpr int kDescWarps = 4;                  // warps per CTA
 constexpr int kDescSlots = 16;                 // keypoint slots per warp
-constexpr int kDescOriOff = (kDescBoxW * kDescBoxH + 127) / 128 * 128;      // TMA destinations are 128-byte aligned
-constexpr int kDescStage = (kDescOriOff + kOriBoxW * kOriBoxH + 127) / 128 * 128;      // bytes per stage
+#ifndef NAV24_DESC_STAGES
+#define NAV24_DESC_STAGES 3
+#endif
+constexpr int kDescStages = NAV24_DESC_STAGES;
+constexpr int kDescStage = (kDescBoxW * kDescBoxH + 255) / 256 * 256;      // bytes per stage
+constexpr int kOriSlots = 2 * kDescStages;     // orientation boxes in the ring
+static_assert(2 * ((kOriBoxW * kOriBoxH + 127) / 128 * 128) <= kDescStage, "one stage holds two orientation boxes");
 
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                                    const __grid_constant__ TmaMaps mapsOri,
                                                                    const __grid_constant__ TmaMaps mapsBlur,
                                                                    const __grid_constant__ TmaMaps mapsBlurN) {
-    __shared__ __align__(128) uint8_t s_buf[kDescWarps][2][kDescStage];
-    __shared__ __align__(8) unsigned long long s_bar[kDescWarps][2];
+    extern __shared__ __align__(128) uint8_t s_desc[];      // [kDescWarps][kDescStages * kDescStage] box ring of every warp
+    __shared__ __align__(8) unsigned long long s_bar[kDescWarps][kOriSlots + kDescStages];      // orientation slots, then descriptor stages
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int f = blockIdx.y;
     const int slot0 = (blockIdx.x * kDescWarps + wid) * kDescSlots;
-    const int slotEnd = min(slot0 + kDescSlots, g.kpPerFrame);
-    if (slot0 >= slotEnd) return;
-    // lane j holds the slot range of level j: [kpOff, kpOff + count)
-    const int myOff = lane < g.nlevels ? g.lv[lane].kpOff : 0x7fffffff;
-    const int myCnt = lane < g.nlevels ? p.levelCount[f * g.nlevels + lane] : 0;
-    const LevelKp* lkp = p.lkp + (long long)f * g.kpPerFrame;
-    // next live slot >= s (and its level), or slotEnd: the dead slots are the tail of every level's range
-    auto next_live = [&](int s, int& l) {
-        while (s < slotEnd) {
-            const unsigned below = __ballot_sync(0xffffffffu, myOff <= s);      // levels that start at or before s
-            l = 31 - __clz(below);
-            const int off = __shfl_sync(0xffffffffu, myOff, l), cnt = __shfl_sync(0xffffffffu, myCnt, l);
-            if (s - off < cnt) return s;
-            s = l + 1 < g.nlevels ? __shfl_sync(0xffffffffu, myOff, l + 1) : slotEnd;      // skip to the next level
+    if (slot0 >= g.kpPerFrame) return;
+    // set-up: lane i looks at slot slot0 + i
+    LevelKp* lkp = p.lkp + (long long)f * g.kpPerFrame;
+    int myL = 0;
+    bool live = false;
+    unsigned myXY = 0;
+    {
+        const int s = slot0 + lane;
+        if (lane < kDescSlots && s < g.kpPerFrame) {
+            for (int l = 1; l < g.nlevels; ++l)
+                if (g.lv[l].kpOff <= s) myL = l;
+            live = s - g.lv[myL].kpOff < p.levelCount[f * g.nlevels + myL];
+            if (live) myXY = *reinterpret_cast<const unsigned*>(lkp + s);        // x | y << 16
         }
-        return slotEnd;
-    };
-    const unsigned bar0 = smem_u32(&s_bar[wid][0]);
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
+    if (liveMask == 0u) return;
+    const int nLive = __popc(liveMask);
+    uint8_t* const s_ring = s_desc + wid * (kDescStages * kDescStage);
+    const unsigned bar0 = smem_u32(&s_bar[wid][0]), buf0 = smem_u32(s_ring);
+    if (lane < kOriSlots + kDescStages) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * lane));
+    if (lane == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    // lane 0: both boxes of the keypoint at level l, level coordinates (cx, cy) -> stage st
-    // The box start must be 16-byte aligned in x (an unaligned start coordinate of a u8 tensor faults), so a 37-px patch
-    // needs 37 + slack columns, slack = (cx - 18) & 15: the narrow 48-byte box when slack <= 11 (3 keypoints of 4), the
-    // 80-byte box otherwise.  Both row pitches cost 3.1 shared-memory wavefronts per gather of the rotated pattern (a
-    // 64-byte pitch: 4.8); the narrow box takes 40 % fewer bytes through L2 and the shared-memory fill.
-    auto issue = [&](int l, int cx, int cy, int st) {
-        const unsigned bar = bar0 + 8 * st, dst = smem_u32(&s_buf[wid][st][0]);
-        const bool narrow = ((cx - 18) & 15) <= kDescBoxWN - 37;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                     "r"((unsigned)((narrow ? kDescBoxWN : kDescBoxW) * kDescBoxH + kOriBoxW * kOriBoxH))
-                     : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-            "l"(narrow ? &mapsBlurN.m[l] : &mapsBlur.m[l]), "r"((cx - 18) & ~15), "r"(cy - 18), "r"(f + p.frameBase), "r"(bar)
-            : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                dst + kDescOriOff),
-            "l"(&mapsOri.m[l]), "r"((cx - 15) & ~15), "r"(cy - 15), "r"(f + p.frameBase), "r"(bar)
-            : "memory");
+    // lane 0: the orientation box of a keypoint -> orientation slot i, or its descriptor box -> stage i.  The box start must
+    // be 16-byte aligned in x (an unaligned start coordinate of a u8 tensor faults), so a 37-px patch needs 37 + slack
+    // columns, slack = (cx - 18) & 15: the narrow 48-byte box when slack <= 11 (3 keypoints of 4), the 80-byte box
+    // otherwise.  Both row pitches cost 3.1 shared-memory wavefronts per gather of the rotated pattern (a 64-byte pitch: 4.8).
+    auto issue = [&](bool ori, int l, int cx, int cy, int i) {      // (called by lane 0 only)
+        if (ori) {
+            const unsigned bar = bar0 + 8 * i, dst = buf0 + (unsigned)i * (kDescStage / 2);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(kOriBoxW * kOriBoxH)) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                "l"(&mapsOri.m[l]), "r"((cx - 15) & ~15), "r"(cy - 15), "r"(f + p.frameBase), "r"(bar)
+                : "memory");
+        } else {
+            const unsigned bar = bar0 + 8 * (kOriSlots + i), dst = buf0 + (unsigned)i * kDescStage;
+            const bool narrow = ((cx - 18) & 15) <= kDescBoxWN - 37;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                         "r"((unsigned)((narrow ? kDescBoxWN : kDescBoxW) * kDescBoxH))
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                "l"(narrow ? &mapsBlurN.m[l] : &mapsBlur.m[l]), "r"((cx - 18) & ~15), "r"(cy - 18), "r"(f + p.frameBase), "r"(bar)
+                : "memory");
+        }
+    };
+    unsigned phase = 0;                          // bit i: parity of barrier i's next wait
+    auto wait = [&](int i) {
+        unsigned done = 0;
+        const unsigned bar = bar0 + 8 * i, par = (phase >> i) & 1u;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(par)
+                : "memory");
+        }
+        phase ^= 1u << i;
+    };
+    // the next keypoint of `todo` (in slot order) gets its box issued into ring position i
+    auto issue_next = [&](unsigned& todo, bool ori, int i) {
+        const int kn = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned xy = __shfl_sync(0xffffffffu, myXY, kn);
+        const int l = __shfl_sync(0xffffffffu, myL, kn);
+        if (lane == 0) issue(ori, l, (int)(xy & 0xffffu), (int)(xy >> 16), i);
     };
     // (keeping the lane's eight test pairs in registers across keypoints was measured slower: 96 registers per thread
     // cost more in occupancy than the 32 L1 wavefronts per keypoint cost in the load pipe)
@@ -1407,64 +1482,82 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
         wrow[k] = r - 15;
     }
 
-    int lCur = 0, lNext = 0, lNext2 = 0;
-    int sCur = next_live(slot0, lCur);
-    if (sCur >= slotEnd) return;
-    unsigned kpCur = *reinterpret_cast<const unsigned*>(lkp + sCur);                // x | y << 16
-    int sNext = next_live(sCur + 1, lNext);
-    unsigned kpNext = sNext < slotEnd ? *reinterpret_cast<const unsigned*>(lkp + sNext) : 0u;
-    if (lane == 0) issue(lCur, (int)(kpCur & 0xffffu), (int)(kpCur >> 16), 0);
-    unsigned phase = 0;                                                             // bit st: parity of stage st's next wait
-    for (int st = 0; sCur < slotEnd; st ^= 1) {
-        // prefetch: boxes of the next keypoint, record of the one after it
-        if (sNext < slotEnd && lane == 0) issue(lNext, (int)(kpNext & 0xffffu), (int)(kpNext >> 16), st ^ 1);
-        const int sNext2 = sNext < slotEnd ? next_live(sNext + 1, lNext2) : slotEnd;
-        const unsigned kpNext2 = sNext2 < slotEnd ? *reinterpret_cast<const unsigned*>(lkp + sNext2) : 0u;
-
-        const int l = lCur, cx = (int)(kpCur & 0xffffu), cy = (int)(kpCur >> 16);
-        const LevelGeom& L = g.lv[l];
-        const uint8_t* s_blur = &s_buf[wid][st][0];
-        const uint8_t* s_ori = s_blur + kDescOriOff;
-        // this lane's orientation weights while the boxes land
+    int myM10 = 0, myM01 = 0;
+    // ---- pass 1: moments ------------------------------------------------------------------------------------------
+    unsigned todo = liveMask;                   // keypoints whose box is not yet issued
+    int iss = 0;                                // boxes issued in this pass
+    for (; iss < min(nLive, kOriSlots - 1); ++iss) issue_next(todo, true, iss);
+    unsigned cur = liveMask;
+    for (int t = 0; t < nLive; ++t) {
+        const int k = __ffs(cur) - 1;           // the keypoint computed in this trip
+        cur &= cur - 1;
+        if (todo) {                             // (its ring position was released by keypoint t - 1)
+            issue_next(todo, true, iss % kOriSlots);
+            ++iss;
+        }
+        const int cx = (int)(__shfl_sync(0xffffffffu, myXY, k) & 0xffffu);
+        const int sl = t % kOriSlots;
+        // this lane's orientation weights while the box lands
         const int off = (cx - 15) & 15;                                            // 0..15
         const uint2* tab = reinterpret_cast<const uint2*>(p.oriTab) + (off & 3) * 279 + lane;
-        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ori) + (off >> 2);
+        const unsigned* ow = reinterpret_cast<const unsigned*>(s_ring + sl * (kDescStage / 2)) + (off >> 2);
         uint2 wt[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) wt[k] = __ldg(tab + min(k * 32, 278 - lane));
-        {
-            unsigned done = 0;
-            const unsigned bar = bar0 + 8 * st, par = (phase >> st) & 1u;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(bar), "r"(par)
-                    : "memory");
-            }
-            phase ^= 1u << st;
-        }
+        for (int j = 0; j < 9; ++j) wt[j] = __ldg(tab + min(j * 32, 278 - lane));
+        wait(sl);
         // IC_Angle: integer moments of the 31-px disc by DP4A over the aligned words of the patch (279 words, 9 per lane;
         // the lane's word positions and row numbers do not depend on the keypoint: wpos / wrow, set up once per warp)
         int m10 = 0, m01 = 0;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (k * 32 + lane < 279) {
-                const unsigned w = ow[wpos[k]];
-                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[k].x));      // u8 pixels x s8 offsets
-                m01 += wrow[k] * (int)__dp4a(w, wt[k].y, 0u);
+        for (int j = 0; j < 9; ++j) {
+            if (j * 32 + lane < 279) {
+                const unsigned w = ow[wpos[j]];
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(w), "r"(wt[j].x));      // u8 pixels x s8 offsets
+                m01 += wrow[j] * (int)__dp4a(w, wt[j].y, 0u);
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        }
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        m10 = __reduce_add_sync(0xffffffffu, m10);
+        m01 = __reduce_add_sync(0xffffffffu, m01);
+        if (lane == k) { myM10 = m10; myM01 = m01; }
+        __syncwarp();                               // every lane is done with the slot before it is refilled
+    }
+    // the first descriptor boxes fly while one lane per keypoint does the scalar work
+    todo = liveMask;
+    iss = 0;
+    for (; iss < min(nLive, kDescStages - 1); ++iss) issue_next(todo, false, iss);
+    // ---- between the passes: one lane per keypoint -------------------------------------------------------------
+    float myA = 1.f, myB = 0.f;                 // cos, sin of the keypoint's angle
+    int myDst = 0;
+    if (live) {
+        const float angle = fast_atan2_deg((float)myM01, (float)myM10);
         const float factorPI = (float)(3.14159265358979323846 / 180.f);
-        float b, a;
-        sincosf(__fmul_rn(angle, factorPI), &b, &a);
-
+        sincosf(__fmul_rn(angle, factorPI), &myB, &myA);
+        LevelKp* kp = lkp + slot0 + lane;
+        myDst = kp->dst;
+        kp->angle = angle;
+        const LevelGeom& L = g.lv[myL];
+        const int cx = (int)(myXY & 0xffffu), cy = (int)(myXY >> 16);
+        nav24_kp o;
+        o.x = myL ? __fmul_rn((float)cx, L.scale) : (float)cx;
+        o.y = myL ? __fmul_rn((float)cy, L.scale) : (float)cy;
+        o.size = L.patch; o.angle = angle; o.response = (float)kp->score; o.octave = myL; o.class_id = -1;
+        p.outKp[(long long)f * g.outCap + myDst] = o;
+    }
+    // ---- pass 2: descriptors ---------------------------------------------------------------------------------------
+    cur = liveMask;
+    for (int t = 0; t < nLive; ++t) {
+        const int k = __ffs(cur) - 1;
+        cur &= cur - 1;
+        if (todo) {
+            issue_next(todo, false, iss % kDescStages);
+            ++iss;
+        }
+        const int cx = (int)(__shfl_sync(0xffffffffu, myXY, k) & 0xffffu);
+        const float a = __shfl_sync(0xffffffffu, myA, k), b = __shfl_sync(0xffffffffu, myB, k);
+        const int dst = __shfl_sync(0xffffffffu, myDst, k);
+        const int st = t % kDescStages;
+        const uint8_t* s_blur = s_ring + st * kDescStage;
+        wait(kOriSlots + st);
         // computeOrbDescriptor: the 512 sample points lie within +-18 px of the keypoint (pattern radius 18.38).
         // cvRound = round-half-even of an f32 in (-2^22, 2^22): adding 1.5 * 2^23 leaves the integer in the low mantissa
         // bits (float bits = 0x4B400000 + n), one full-rate FADD instead of a quarter-rate F2I per coordinate (1024 per
@@ -1486,20 +1579,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(pcA + r1 * bp + q1));
             val |= (unsigned)(t0 < t1) << j;
         }
-        LevelKp* kp = p.lkp + (long long)f * g.kpPerFrame + sCur;
-        const int dst = kp->dst;
         p.outDesc[((long long)f * g.outCap + dst) * 32 + lane] = (uint8_t)val;
-        if (lane == 0) {
-            kp->angle = angle;
-            nav24_kp o;
-            o.x = l ? __fmul_rn((float)cx, L.scale) : (float)cx;
-            o.y = l ? __fmul_rn((float)cy, L.scale) : (float)cy;
-            o.size = L.patch; o.angle = angle; o.response = (float)kp->score; o.octave = l; o.class_id = -1;
-            p.outKp[(long long)f * g.outCap + dst] = o;
-        }
         __syncwarp();                               // every lane is done with stage st before it is refilled
-        sCur = sNext; lCur = lNext; kpCur = kpNext;
-        sNext = sNext2; lNext = lNext2; kpNext = kpNext2;
     }
 }
 
@@ -1635,7 +1716,9 @@ int launch_blur(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc
 int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, const TmaMaps& mapsBlurN, int B,
                     cudaStream_t s) {
     dim3 grid((g.kpPerFrame + kDescWarps * kDescSlots - 1) / (kDescWarps * kDescSlots), B);
-    describe_kernel<<<grid, kDescWarps * 32, 0, s>>>(g, p, mapsOri, mapsBlur, mapsBlurN);
+    constexpr int smem = kDescWarps * kDescStages * kDescStage;
+    cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    describe_kernel<<<grid, kDescWarps * 32, smem, s>>>(g, p, mapsOri, mapsBlur, mapsBlurN);
     return 1;
 }
 
