@@ -11,7 +11,7 @@ namespace nav24 {
 constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;           // EDGE_THRESHOLD (OP_FtDtOrbSlam.cpp:14)
 constexpr int kMinBorder = 16;      // EDGE_THRESHOLD-3 (:735)
-constexpr int kBlurTileRows = 35;                    // rows per warp tile of blur_kernel (multiple of 7)
+constexpr int kBlurTileRows = 36;                    // rows per warp tile of blur_kernel (multiple of 6: the row-pair ring)
 constexpr int kBlurCtaRows = 4 * kBlurTileRows;     // rows per CTA tile (four warp tiles stacked)
 constexpr int kBlurBoxW = 160, kBlurBoxH = kBlurCtaRows + 6;   // TMA box: 128 px + 16-byte aligned halos, 3 halo rows each side
 constexpr int kMaxCellTile = 76;    // wCell+6 <= 75 whenever nCols >= 1 (cell pitch < 70)

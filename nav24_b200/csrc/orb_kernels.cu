@@ -1203,7 +1203,8 @@ __device__ __forceinline__ int reflect101(int v, int n) {
 // halo columns / rows of the tile in shared memory (uniform branches, edge tiles only), so the main loop has a single
 // branch-free body.  One WARP owns kBlurTileRows rows of the tile, lane i the pixels [4i, 4i+4) of every row: per row
 // three words from shared memory (immediate offsets), the four horizontal 7-tap sums with two DP4A each
-// (coefficients (18,34,48,56 | 48,34,18,0)), the last seven rows of sums in a register ring, one 32-bit store.
+// (coefficients (18,34,48,56 | 48,34,18,0)), the vertical pass on pairs of rows kept in a register ring (see below), one
+// 32-bit store.
 // All levels and frames in one launch; the CTA tiles of a frame are numbered level by level (blurTileBase).
 __global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                    const __grid_constant__ TmaMaps maps) {
@@ -1283,42 +1284,52 @@ __global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ Frame
     asm("mov.u32 %0, 32768;" : "=r"(half));      // kept in a register: IMAD has one immediate slot
     // word 0 of the lane's window (pixels x4-4 .. x4-1) in the row that enters the ring first (image row y0 - 3)
     const uint8_t* rp = tile + (y0 - rowBase) * P + 12 + lane * 4;
-    unsigned hr[7][4];
-    // one row enters the 7-row window: horizontal sums of tile row *rp into ring slot (s + 6) % 7
-    auto hstep = [&](int s) {
+    // Vertical pass on PAIRS of rows: the horizontal sums fit 16 bits (<= 255 * 256), so the sums of two consecutive rows
+    // of one pixel share a register (one PRMT when the lower row arrives) and weigh in with ONE DP2A:
+    //   out(y) = DP2A(pair(y-3, y-2), (18, 34)) + DP2A(pair(y-1, y), (48, 56)) + DP2A(pair(y+1, y+2), (48, 34)) + 18 * row(y+3)
+    // i.e. 1 PRMT + 3 DP2A + 1 IMAD per pixel instead of 3 IADD + 4 IMAD.  Every pair of consecutive rows is used (by
+    // the outputs of its own parity): ring of six pairs, pair j = rows (j, j+1) of the strip in slot j % 6, plus the last
+    // two rows of sums (alternating, so that "the previous row" needs no register moves).
+    unsigned pk[6][4], ob[2][4];
+    // horizontal sums of tile row *rp
+    auto hrow = [&](unsigned* o) {
         const unsigned w0 = *reinterpret_cast<const unsigned*>(rp), w1 = *reinterpret_cast<const unsigned*>(rp + 4),
                        w2 = *reinterpret_cast<const unsigned*>(rp + 8);
         rp += P;
-        unsigned* o = hr[(s + 6) % 7];
         const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
         o[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
         o[1] = __dp4a(__byte_perm(w0, w1, 0x5432), K1, __dp4a(__byte_perm(w1, w2, 0x5432), K2, 0u));
         o[2] = __dp4a(__byte_perm(w0, w1, 0x6543), K1, __dp4a(__byte_perm(w1, w2, 0x6543), K2, 0u));
         o[3] = __dp4a(w1, K1, __dp4a(w2, K2, 0u));
     };
-    // the output row whose window ends with the row that just entered slot (s + 6) % 7
-    auto vstep = [&](int s) {
+    auto pack = [&](int slot, const unsigned* lo, const unsigned* hi) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[slot][i] = __byte_perm(lo[i], hi[i], 0x5410);
+    };
+    // the output row whose window ends with row `o`; m = (index of that row inside the strip) % 6
+    auto emit = [&](int m, const unsigned* o) {
+        const unsigned K01 = 0x2212u, K23 = 0x3830u, K45 = 0x2230u;      // (18,34), (48,56), (48,34)
         unsigned v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            v[i] = 18u * (hr[s % 7][i] + hr[(s + 6) % 7][i]) + (34u * (hr[(s + 1) % 7][i] + hr[(s + 5) % 7][i]) +
-                   (48u * (hr[(s + 2) % 7][i] + hr[(s + 4) % 7][i]) + (56u * hr[(s + 3) % 7][i] + half)));
+            v[i] = __dp2a_lo(pk[m % 6][i], K01, __dp2a_lo(pk[(m + 2) % 6][i], K23, __dp2a_lo(pk[(m + 4) % 6][i], K45, 18u * o[i] + half)));
         const unsigned word = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
         if (active) *reinterpret_cast<unsigned*>(dp) = word;
         dp += dPitch;
     };
-    // six rows fill the window, then every row emits; full groups of seven rows run without any per-row test
+    // six rows fill the window, then every row emits; full groups of six rows run without any per-row test
+    hrow(ob[0]);
 #pragma unroll
-    for (int s = 0; s < 6; ++s) hstep(s);
+    for (int j = 1; j < 6; ++j) { hrow(ob[j & 1]); pack(j - 1, ob[(j - 1) & 1], ob[j & 1]); }
     const int nrows = yEnd - y0;
     int done = 0;
-    for (; done + 7 <= nrows; done += 7) {
+    for (; done + 6 <= nrows; done += 6) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) { hstep((k + 6) % 7); vstep((k + 6) % 7); }
+        for (int m = 0; m < 6; ++m) { hrow(ob[m & 1]); emit(m, ob[m & 1]); pack((m + 5) % 6, ob[(m + 1) & 1], ob[m & 1]); }
     }
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
-        if (done + k < nrows) { hstep((k + 6) % 7); vstep((k + 6) % 7); }      // uniform: the bottom tile of a level
+    for (int m = 0; m < 6; ++m)
+        if (done + m < nrows) { hrow(ob[m & 1]); emit(m, ob[m & 1]); pack((m + 5) % 6, ob[(m + 1) & 1], ob[m & 1]); }      // uniform: the bottom tile of a level
 }
 
 // ------------------------------------------------------------------------------------------
