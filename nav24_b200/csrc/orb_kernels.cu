@@ -811,7 +811,8 @@ template <int NT, bool SM>
 __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& p, const int l, const int f, const int n,
                                              const int sortSmemCap, unsigned long long* s_sort, int* s_scan, int* s_K, int* s_nexp,
                                              const RawRec* __restrict__ keys, unsigned short* __restrict__ nodeOfKey, QNode* cur, QNode* nxt,
-                                             int* childCnt, int* aux, unsigned* best) {
+                                             int* childCnt, int* aux, unsigned* best, const RawRec* __restrict__ raw,
+                                             const uint2* __restrict__ cinfo, const int* __restrict__ cdst, const int nC, RawRec* keysOut) {
     const int tid = threadIdx.x, nth = NT;
     const LevelGeom& L = g.lv[l];
     const long long fn = (long long)f * g.nodesPerFrame + L.nodeOff;
@@ -823,11 +824,57 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
     const float hX = L.hX;
     for (int r = tid; r < nIni; r += nth) childCnt[r] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nth) {
-        int r = (int)__fdiv_rn((float)keys[i].x, hX);
-        if (r >= nIni || r < 0) { atomicOr(p.err, ERR_ROOT_RANGE); r = nIni - 1; }
-        nodeOfKey[i] = (unsigned short)r;
-        atomicAdd(&childCnt[r], 1);
+    // The per-cell lists of the FAST kernel go into the reference order (cells row-major, row-major inside a cell: keysOut =
+    // `keys`, read back only after the barrier below) and every key is counted into its root on the way.
+    // A warp takes 32 consecutive cells, lane j the table entry of cell c0 + j.  Their keys are consecutive in the ordered
+    // array, so entry t of the group goes to keys[first + t] (coalesced) and comes from the cell whose inclusive count
+    // first exceeds t (binary search over the lanes); the trips are independent, four are in flight at a time.  (One warp
+    // per cell — table entry, then keys, then the next cell — was a chain of dependent L2 latencies: 17 % of this kernel's
+    // stall samples.)
+    {
+        const int lane = tid & 31;
+        for (int c0 = (tid >> 5) * 32; c0 < nC; c0 += nth) {
+            const int c = c0 + lane;
+            const uint2 ci = c < nC ? cinfo[c] : make_uint2(0u, 0u);
+            const int first = cdst[c0];
+            int incl = (int)ci.y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int T = __shfl_sync(0xffffffffu, incl, 31);
+            const int srcOff = (int)ci.x - (incl - (int)ci.y);      // source index of entry t of this lane's cell = srcOff + t
+            for (int t0 = 0; t0 < T; t0 += 128) {
+                int src[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    int col = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int probe = __shfl_sync(0xffffffffu, incl, col + step - 1);
+                        if (probe <= t) col += step;
+                    }
+                    src[u] = __shfl_sync(0xffffffffu, srcOff, min(col, 31)) + t;
+                }
+                RawRec rr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (t0 + 32 * u + lane < T) rr[u] = raw[src[u]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u + lane;
+                    if (t < T) {
+                        keysOut[first + t] = rr[u];
+                        int r = (int)__fdiv_rn((float)rr[u].x, hX);
+                        if (r >= nIni || r < 0) { atomicOr(p.err, ERR_ROOT_RANGE); r = nIni - 1; }
+                        nodeOfKey[first + t] = (unsigned short)r;
+                        atomicAdd(&childCnt[r], 1);
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
     int size = 0;
@@ -1094,48 +1141,6 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) quadtree_kernel(const 
     int* sAux = reinterpret_cast<int*>(sB + qs.nodeCap);
     unsigned* sBest = reinterpret_cast<unsigned*>(sAux + qs.nodeCap);
     const bool useSm = L.nodeCap <= qs.nodeCap;      // CTA-uniform
-    // A warp takes 32 consecutive cells, lane j the table entry of cell c0 + j.  Their keys are consecutive in the ordered
-    // array, so entry t of the group goes to gkeys[first + t] (coalesced) and comes from the cell whose inclusive count
-    // first exceeds t (binary search over the lanes); the trips are independent, two are in flight at a time.  (One warp
-    // per cell — table entry, then keys, then the next cell — was a chain of dependent L2 latencies: 17 % of this kernel's
-    // stall samples.)
-    {
-        const int lane = tid & 31;
-        for (int c0 = (tid >> 5) * 32; c0 < nC; c0 += nth) {
-            const int c = c0 + lane;
-            const uint2 ci = c < nC ? cinfo[c] : make_uint2(0u, 0u);
-            const int first = cdst[c0];
-            int incl = (int)ci.y;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int T = __shfl_sync(0xffffffffu, incl, 31);
-            const int srcOff = (int)ci.x - (incl - (int)ci.y);      // source index of entry t of this lane's cell = srcOff + t
-            for (int t0 = 0; t0 < T; t0 += 64) {
-                int src[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int t = t0 + 32 * u + lane;
-                    int col = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int probe = __shfl_sync(0xffffffffu, incl, col + step - 1);
-                        if (probe <= t) col += step;
-                    }
-                    src[u] = __shfl_sync(0xffffffffu, srcOff, min(col, 31)) + t;
-                }
-                RawRec r[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (t0 + 32 * u + lane < T) r[u] = raw[src[u]];
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (t0 + 32 * u + lane < T) gkeys[first + t0 + 32 * u + lane] = r[u];
-            }
-        }
-    }
     if (tid == 0) p.rawTotal[f * g.nlevels + l] = n;
     __syncthreads();
     if (n == 0) {
@@ -1144,10 +1149,10 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) quadtree_kernel(const 
     }
     unsigned short* nok = reinterpret_cast<unsigned short*>(p.nodeOfKey + fr);
     if (useSm)
-        quadtree_run<NT, true>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, sA, sB, sChild, sAux, sBest);
+        quadtree_run<NT, true>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, sA, sB, sChild, sAux, sBest, raw, cinfo, cdst, nC, gkeys);
     else
         quadtree_run<NT, false>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, p.nodesA + fn, p.nodesB + fn,
-                                p.childCnt + 4 * fn, p.nodeAux + fn, reinterpret_cast<unsigned*>(p.best + fn));
+                                p.childCnt + 4 * fn, p.nodeAux + fn, reinterpret_cast<unsigned*>(p.best + fn), raw, cinfo, cdst, nC, gkeys);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1395,9 +1400,15 @@ __device__ const PatternT kPatternT = make_pattern_t();
 // kDescStages - 1 (pass 2) or 2 * kDescStages - 1 (pass 1, whose items are short) keypoints are in flight.  Warps never
 // synchronise with each other (a CTA is four independent warps).
 constexpr int kDescWarps = 4;                  // warps per CTA
-constexpr int kDescSlots = 16;                 // keypoint slots per warp
+// Measured on KITTI batches (this kernel, ms / 1024 frames; slots x stages): 16x2 1.40, 16x3 1.21, 16x4 1.34, 32x3 1.45,
+// 8x3 1.18, 8x2 1.13, 10x2 1.11, 12x2 1.11 — warps in flight (8 CTAs of 4 warps per SM with a 6 KB ring each) matter more
+// than ring depth: the kernel waits on box arrivals and L2 (67 % busy), not on issue slots.
+#ifndef NAV24_DESC_SLOTS
+#define NAV24_DESC_SLOTS 10
+#endif
+constexpr int kDescSlots = NAV24_DESC_SLOTS;   // keypoint slots per warp
 #ifndef NAV24_DESC_STAGES
-#define NAV24_DESC_STAGES 3
+#define NAV24_DESC_STAGES 2
 #endif
 constexpr int kDescStages = NAV24_DESC_STAGES;
 constexpr int kDescStage = (kDescBoxW * kDescBoxH + 255) / 256 * 256;      // bytes per stage
