@@ -105,7 +105,7 @@ struct nav24_orb {
     int mapsB = 0;            // frame count the level>=1 maps were encoded for
     const void* mapsPyr = nullptr;
     DevBuf bL0Tight, bL0, bPyr, bBlur, bCell, bCellDst, bRawCount, bRaw, bKeys, bNodeOfKey, bNodesA, bNodesB, bChild, bAux, bBest,
-        bSort, bLkp, bLevelCount, bRawTotal, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs, bOriTab, bSegs, bOutUd, bUdTmp;
+        bSort, bLkp, bLevelCount, bRawTotal, bFrameDone, bOutKp, bOutDesc, bNOut, bMono, bErr, bTabs, bOriTab, bSegs, bOutUd, bUdTmp;
     // matcher scratch
     DevBuf mK1, mK2, mU1, mU2, mD1, mD2, mN1, mN2, mCellOf, mCellStart, mCellFill, mCellItems, mCand, mCandCnt, mDist2,
         mM21, mBins, mMatches, mNMatches, mPairs, mPairOrder, mI0, mI1, mF0, mF1, mPass;
@@ -240,6 +240,21 @@ int build_geometry(nav24_orb* ctx, int w, int h, FrameGeom& g) {
     g.totalCells = cellBase;
     g.totalSegs = 0;
     for (int l = 0; l < nl; ++l) g.totalSegs += g.lv[l].segsPerRow * g.lv[l].nRows;
+    // FAST launch groups (launch_fast): the cut below the tallest cell rows that lets the most segments run with one more
+    // resident CTA per SM than a single launch sized for the tallest level would (228 KB per SM, 1 KB reserved per CTA)
+    {
+        auto ctas = [&](int lo, int hi) { const int b = fast_smem_bytes(g, lo, hi, nullptr); return b ? (228 * 1024) / (b + 1024) : 0; };
+        const int all = ctas(0, 1 << 30);
+        g.fastCutH = 1 << 30; g.segsLow = g.totalSegs;
+        int bestSegs = 0;
+        for (int l = 0; l < nl; ++l) {
+            const int cut = g.lv[l].boxH;
+            if (ctas(0, cut) <= all) continue;
+            int segs = 0;
+            for (int k = 0; k < nl; ++k) if (g.lv[k].boxH <= cut) segs += g.lv[k].segsPerRow * g.lv[k].nRows;
+            if (segs > bestSegs && segs < g.totalSegs) { bestSegs = segs; g.fastCutH = cut; g.segsLow = segs; }
+        }
+    }
     g.blurTiles = stripBase;
     g.rawPerFrame = rawOff;
     g.nodesPerFrame = nodeOff;
@@ -270,8 +285,10 @@ void build_resize_table(int ssize, int dsize, std::vector<int>& ofs, std::vector
 // (OP_FtDtOrbSlam.cpp:751-768) evaluated once on the host.
 void build_fast_segments(const FrameGeom& g, std::vector<FastSeg>& segs) {
     segs.clear();
+    for (int pass = 0; pass < 2; ++pass)      // the levels of the low group first (g.fastCutH)
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& L = g.lv[l];
+        if ((L.boxH <= g.fastCutH) != (pass == 0)) continue;
         for (int ci = 0; ci < L.nRows; ++ci)
             for (int sj = 0; sj < L.segsPerRow; ++sj) {
                 FastSeg s{};
@@ -430,6 +447,8 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         CK(ctx->bLkp.ensure(b * g.kpPerFrame * sizeof(LevelKp)));
         CK(ctx->bLevelCount.ensure(b * g.nlevels * sizeof(int)));
         CK(ctx->bRawTotal.ensure(b * g.nlevels * sizeof(int)));
+        CK(ctx->bFrameDone.ensure(b * sizeof(int)));
+        CK(cudaMemset(ctx->bFrameDone.ptr, 0, ctx->bFrameDone.bytes));      // quadtree_kernel leaves the counters at zero
         CK(ctx->bOutKp.ensure(b * g.outCap * sizeof(nav24_kp)));
         CK(ctx->bOutDesc.ensure(b * g.outCap * 32));
         CK(ctx->bOutUd.ensure(b * g.outCap * 2 * sizeof(float)));
@@ -467,7 +486,7 @@ int ensure_workspace(nav24_orb* ctx, int w, int h, int B) {
         p.nodesA = (QNode*)ctx->bNodesA.ptr; p.nodesB = (QNode*)ctx->bNodesB.ptr; p.childCnt = (int*)ctx->bChild.ptr;
         p.nodeAux = (int*)ctx->bAux.ptr; p.best = (unsigned long long*)ctx->bBest.ptr;
         p.sortRec = (unsigned long long*)ctx->bSort.ptr; p.lkp = (LevelKp*)ctx->bLkp.ptr;
-        p.levelCount = (int*)ctx->bLevelCount.ptr; p.rawTotal = (int*)ctx->bRawTotal.ptr;
+        p.levelCount = (int*)ctx->bLevelCount.ptr; p.rawTotal = (int*)ctx->bRawTotal.ptr; p.frameDone = (int*)ctx->bFrameDone.ptr;
         p.outKp = (nav24_kp*)ctx->bOutKp.ptr; p.outDesc = (uint8_t*)ctx->bOutDesc.ptr; p.outUd = (float*)ctx->bOutUd.ptr;
         p.nOut = (int*)ctx->bNOut.ptr; p.monoOut = (int*)ctx->bMono.ptr; p.err = (int*)ctx->bErr.ptr;
         p.oriTab = (const unsigned*)ctx->bOriTab.ptr;
@@ -484,7 +503,7 @@ DevPtrs chunk_ptrs(const nav24_orb* ctx, int f0) {
     const long long f = f0;
     q.l0 += f * q.l0Frame; q.pyr += f * g.pyrFrameBytes; q.blur += f * g.blurFrameBytes;
     q.cellInfo += f * g.totalCells; q.cellDst += f * g.totalCells;
-    q.rawCount += f * g.nlevels; q.levelCount += f * g.nlevels; q.rawTotal += f * g.nlevels;
+    q.rawCount += f * g.nlevels; q.levelCount += f * g.nlevels; q.rawTotal += f * g.nlevels; q.frameDone += f;
     q.raw += f * g.rawPerFrame; q.keys += f * g.rawPerFrame; q.nodeOfKey += f * g.rawPerFrame;
     q.nodesA += f * g.nodesPerFrame; q.nodesB += f * g.nodesPerFrame; q.childCnt += 4 * f * g.nodesPerFrame;
     q.nodeAux += f * g.nodesPerFrame; q.best += f * g.nodesPerFrame; q.sortRec += f * g.nodesPerFrame;
@@ -746,7 +765,7 @@ void nav24_orb_destroy(nav24_orb* ctx) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->bL0Tight, &ctx->bL0, &ctx->bPyr, &ctx->bBlur, &ctx->bCell, &ctx->bCellDst, &ctx->bRawCount, &ctx->bRaw, &ctx->bKeys,
                       &ctx->bNodeOfKey, &ctx->bNodesA, &ctx->bNodesB, &ctx->bChild, &ctx->bAux, &ctx->bBest, &ctx->bSort,
-                      &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
+                      &ctx->bLkp, &ctx->bLevelCount, &ctx->bRawTotal, &ctx->bFrameDone, &ctx->bOutKp, &ctx->bOutDesc, &ctx->bNOut, &ctx->bMono,
                       &ctx->bErr, &ctx->bTabs, &ctx->bOriTab, &ctx->bSegs, &ctx->bOutUd, &ctx->bUdTmp, &ctx->mK1, &ctx->mK2, &ctx->mU1, &ctx->mU2, &ctx->mD1, &ctx->mD2, &ctx->mN1,
                       &ctx->mN2, &ctx->mCellOf, &ctx->mCellStart, &ctx->mCellFill, &ctx->mCellItems, &ctx->mCand, &ctx->mCandCnt,
                       &ctx->mDist2, &ctx->mM21, &ctx->mBins, &ctx->mMatches, &ctx->mNMatches, &ctx->mPairs, &ctx->mPairOrder, &ctx->mI0, &ctx->mI1,

@@ -59,6 +59,8 @@ struct FrameGeom {
     int nlevels;
     int totalCells;
     int totalSegs;           // FAST segments per frame (grid.x of fast_band_kernel)
+    int fastCutH, segsLow;   // the segments of the levels with boxH <= fastCutH come first in the table (segsLow of them) and are
+                             // launched with a smaller shared-memory footprint (launch_fast); segsLow == totalSegs: one launch
     int rawPerFrame;         // records
     int nodesPerFrame;
     int kpPerFrame;          // level-keypoint slab size (sum of kpCap)
@@ -115,6 +117,7 @@ struct DevPtrs {
     LevelKp* lkp;            // [B][kpPerFrame]
     int* levelCount;         // [B][nlevels] keypoints per level after the quadtree
     int* rawTotal;           // [B][nlevels] raw keys per level
+    int* frameDone;          // [B] levels of the frame whose quadtree CTA has finished (zero between launches)
     float* outUd;            // [B][outCap][2] undistorted keypoint coordinates (camera model != pinhole)
     nav24_kp* outKp;         // [B][outCap]
     uint8_t* outDesc;        // [B][outCap][32]
@@ -146,6 +149,7 @@ int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, in
 int launch_bgr2gray(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s);
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s);
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
+int fast_smem_bytes(const FrameGeom& g, int minBoxH, int maxBoxH, FastSmem* out);      // levels with minBoxH < boxH <= maxBoxH
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);
 int launch_blur(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsBlurSrc, int B, cudaStream_t s);
 int launch_describe(const FrameGeom& g, const DevPtrs& p, const TmaMaps& mapsOri, const TmaMaps& mapsBlur, const TmaMaps& mapsBlurN, int B,

@@ -9,6 +9,33 @@
 #include "orb_internal.cuh"
 #include "stdsort_warp.cuh"
 
+// minimum-blocks argument of the launch bounds of the image kernels (0 = none: ptxas picks the register count for the plain
+// thread bound); -DNAV24_*_MINB=n for A/B builds
+#ifndef NAV24_FAST_MINB
+#define NAV24_FAST_MINB 0
+#endif
+#ifndef NAV24_BLUR_MINB
+#define NAV24_BLUR_MINB 0
+#endif
+#ifndef NAV24_RS_MINB
+#define NAV24_RS_MINB 1      // resize: 62 registers instead of 40 (the loads of a source row are issued further ahead): 0.79 -> 0.75 ms
+#endif
+#if NAV24_FAST_MINB > 0
+#define NAV24_FAST_LB __launch_bounds__(kFastThreads, NAV24_FAST_MINB)
+#else
+#define NAV24_FAST_LB __launch_bounds__(kFastThreads)
+#endif
+#if NAV24_BLUR_MINB > 0
+#define NAV24_BLUR_LB __launch_bounds__(128, NAV24_BLUR_MINB)
+#else
+#define NAV24_BLUR_LB __launch_bounds__(128)
+#endif
+#if NAV24_RS_MINB > 0
+#define NAV24_RS_LB __launch_bounds__(128, NAV24_RS_MINB)
+#else
+#define NAV24_RS_LB __launch_bounds__(128)
+#endif
+
 namespace nav24 {
 
 namespace {
@@ -124,15 +151,15 @@ __global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t* __restrict
 //     left by 16, >> 2, pack, one 32-bit store.
 // ------------------------------------------------------------------------------------------
 template <int BOXW>
-__global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ CUtensorMap srcMap, int frameBase,
+__global__ void NAV24_RS_LB resize_kernel(const __grid_constant__ CUtensorMap srcMap, int frameBase,
                                                      uint8_t* __restrict__ dst, int dPitch, long long dFrame, int dw, int dh,
-                                                     ResizeTab t) {
+                                                     ResizeTab t, int xBase) {
     extern __shared__ __align__(128) uint8_t s_rs[];       // [boxH][BOXW] source tile
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint2 s_yt[4][kResizeMaxRows];              // per warp strip: (source row inside the tile, b0 | b1 << 16) per destination row
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int rows = t.rows;                               // <= kResizeMaxRows (one lane per row of the warp's strip)
-    const int x0c = blockIdx.x * 128, y0c = blockIdx.y * 4 * rows;
+    const int x0c = xBase + blockIdx.x * 128, y0c = blockIdx.y * 4 * rows;      // (xBase: the remainder strip of a wide level)
     const int tileX0 = __ldg(t.xofs + x0c) & ~15, tileY0 = __ldg(t.yofs + y0c);
     const unsigned barAddr = smem_u32(&bar);
     if (threadIdx.x == 0) {
@@ -270,7 +297,7 @@ stateBA:
 // (true for the reference's 1.2 pyramid); the host checks every pixel group of a level (ResizeTab::wide) and launches
 // resize_kernel for levels that do not qualify.
 template <int BOXW>
-__global__ void __launch_bounds__(128) resize8_kernel(const __grid_constant__ CUtensorMap srcMap, int frameBase,
+__global__ void NAV24_RS_LB resize8_kernel(const __grid_constant__ CUtensorMap srcMap, int frameBase,
                                                       uint8_t* __restrict__ dst, int dPitch, long long dFrame, int dw, int dh,
                                                       ResizeTab t) {
     extern __shared__ __align__(128) uint8_t s_rs[];       // [2][boxH][BOXW] source tiles of the two 128-column halves
@@ -485,9 +512,9 @@ __device__ __forceinline__ int mask_range_count(const unsigned* rowp, int x0, in
 
 // Dynamic shared memory: [tile | score map | keypoint bit mask | queue u16], sizes from FastSmem.
 // Queue and winner entries are the byte offset of the pixel inside the tile (row * kFastPitch + column).
-__global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+__global__ void NAV24_FAST_LB fast_band_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                                  const __grid_constant__ TmaMaps maps, const FastSmem sm,
-                                                                 int iniTh, int minTh) {
+                                                                 int iniTh, int minTh, int segBase) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
     uint8_t* tile = s_dyn;
     uint8_t* smap = s_dyn + sm.offMap;
@@ -503,7 +530,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_band_kernel(const __grid_co
     const int lane = tid & 31, wid = tid >> 5;
     FastSeg sg;                                                      // 2 x 16 B, the same for all threads
     {
-        const uint4* sp = reinterpret_cast<const uint4*>(p.segs + blockIdx.x);
+        const uint4* sp = reinterpret_cast<const uint4*>(p.segs + segBase + blockIdx.x);
         uint4* dp = reinterpret_cast<uint4*>(&sg);
         dp[0] = __ldg(sp); dp[1] = __ldg(sp + 1);
     }
@@ -1102,7 +1129,9 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
 }
 
 // Shared-memory table sizes of quadtree_kernel (nodeCap 0: the node tables stay in global memory)
-struct QtSmem { int sortCap, nodeCap; };
+struct QtSmem { int sortCap, nodeCap, orderInside; };
+
+__device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p, const int f, int* s_scan);      // K7, below
 
 template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency; one CTA
                        // per SM is enough there, so it may use 64 registers: the default bound of 32 spilled 616 bytes of loads)
@@ -1143,38 +1172,56 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) quadtree_kernel(const 
     const bool useSm = L.nodeCap <= qs.nodeCap;      // CTA-uniform
     if (tid == 0) p.rawTotal[f * g.nlevels + l] = n;
     __syncthreads();
+    unsigned short* nok = reinterpret_cast<unsigned short*>(p.nodeOfKey + fr);
     if (n == 0) {
         if (tid == 0) p.levelCount[f * g.nlevels + l] = 0;
-        return;
-    }
-    unsigned short* nok = reinterpret_cast<unsigned short*>(p.nodeOfKey + fr);
-    if (useSm)
+    } else if (useSm) {
         quadtree_run<NT, true>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, sA, sB, sChild, sAux, sBest, raw, cinfo, cdst, nC, gkeys);
-    else
+    } else {
         quadtree_run<NT, false>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, p.nodesA + fn, p.nodesB + fn,
                                 p.childCnt + 4 * fn, p.nodeAux + fn, reinterpret_cast<unsigned*>(p.best + fn), raw, cinfo, cdst, nC, gkeys);
+    }
+    // small batches: the CTA that finishes last among the levels of frame f puts the frame's keypoints into the output order
+    if (!qs.orderInside) return;
+    __threadfence();                             // this level's keypoints and count are visible before the counter moves
+    __syncthreads();
+    if (tid == 0) {
+        const int done = atomicAdd(p.frameDone + f, 1);
+        s_K = done == g.nlevels - 1;
+        if (s_K) p.frameDone[f] = 0;             // ready for the next launch (nobody else touches it any more)
+    }
+    __syncthreads();
+    if (s_K) {
+        __threadfence();
+        order_frame(g, p, f, s_scan);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// K7  output order.  One CTA per frame.  Reproduces the two-ended placement of detect()
+// K7  output order of one frame, by one CTA.  Reproduces the two-ended placement of detect()
 // (OP_FtDtOrbSlam.cpp:877-921): keypoints with 0 <= x*scale <= 1000 fill the output from the back,
 // the others from the front; monoIndex = number of the latter.
+// Small batches (single-camera latency): runs at the end of quadtree_kernel in the CTA that finishes LAST among the levels
+// of its frame (a counter per frame, release / acquire by __threadfence around the atomic) — no separate launch, and the
+// step, a chain of block scans, overlaps the quadtree CTAs still running (single 4K frame: 0.288 -> 0.267 ms).  Batches
+// that fill the GPU run it as order_kernel, one CTA per frame: there the tail inside the quadtree CTAs costs more than the
+// launch (0.107 vs 0.07 ms per 1024 KITTI frames).  The level tables may have been written by other CTAs of the same
+// launch, so they are read with ld.global.cg (L2), never through L1.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) order_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
-    __shared__ int s_scan[33];
-    const int tid = threadIdx.x, f = blockIdx.x;
+__device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p, const int f, int* s_scan) {
+    const int tid = threadIdx.x, nth = blockDim.x;
     int n = 0;
-    for (int l = 0; l < g.nlevels; ++l) n += p.levelCount[f * g.nlevels + l];
+    for (int l = 0; l < g.nlevels; ++l) n += __ldcg(p.levelCount + f * g.nlevels + l);
     int nSt = 0, nMo = 0;
     for (int l = 0; l < g.nlevels; ++l) {
-        const int cnt = p.levelCount[f * g.nlevels + l];
+        const int cnt = __ldcg(p.levelCount + f * g.nlevels + l);
         LevelKp* lkp = p.lkp + (long long)f * g.kpPerFrame + g.lv[l].kpOff;
         const float sc = g.lv[l].scale;
-        for (int base = 0; base < cnt; base += 256) {
+        for (int base = 0; base < cnt; base += nth) {
             const int i = base + tid;
             bool st = false, mo = false;
             if (i < cnt) {
-                const float x = (float)lkp[i].x;
+                const float x = (float)(__ldcg(reinterpret_cast<const unsigned*>(lkp + i)) & 0xffffu);      // LevelKp::x
                 const float xs = l ? __fmul_rn(x, sc) : x;
                 st = xs >= 0.f && xs <= 1000.f;
                 mo = !st;
@@ -1190,6 +1237,11 @@ __global__ void __launch_bounds__(256) order_kernel(const __grid_constant__ Fram
         if (n > g.outCap) { atomicOr(p.err, ERR_KP_OVERFLOW); n = 0; nMo = 0; }
         p.nOut[f] = n; p.monoOut[f] = nMo;
     }
+}
+
+__global__ void __launch_bounds__(256) order_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
+    __shared__ int s_scan[33];
+    order_frame(g, p, blockIdx.x, s_scan);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1211,7 +1263,7 @@ __device__ __forceinline__ int reflect101(int v, int n) {
 // (coefficients (18,34,48,56 | 48,34,18,0)), the vertical pass on pairs of rows kept in a register ring (see below), one
 // 32-bit store.
 // All levels and frames in one launch; the CTA tiles of a frame are numbered level by level (blurTileBase).
-__global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+__global__ void NAV24_BLUR_LB blur_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                    const __grid_constant__ TmaMaps maps) {
     __shared__ __align__(128) uint8_t tile[kBlurBoxW * kBlurBoxH];
     __shared__ __align__(8) unsigned long long bar;
@@ -1302,6 +1354,8 @@ __global__ void __launch_bounds__(128) blur_kernel(const __grid_constant__ Frame
                        w2 = *reinterpret_cast<const unsigned*>(rp + 8);
         rp += P;
         const unsigned K1 = 0x38302212u, K2 = 0x00122230u;      // (18,34,48,56) and (48,34,18,0), little endian
+        // (weighing the three ALIGNED words with per-pixel coefficient words instead — 10 DP4A, no PRMT — measured slower:
+        // the ten constants do not fit the instruction and cost a uniform move each)
         o[0] = __dp4a(__byte_perm(w0, w1, 0x4321), K1, __dp4a(__byte_perm(w1, w2, 0x4321), K2, 0u));
         o[1] = __dp4a(__byte_perm(w0, w1, 0x5432), K1, __dp4a(__byte_perm(w1, w2, 0x5432), K2, 0u));
         o[2] = __dp4a(__byte_perm(w0, w1, 0x6543), K1, __dp4a(__byte_perm(w1, w2, 0x6543), K2, 0u));
@@ -1415,7 +1469,9 @@ constexpr int kDescStage = (kDescBoxW * kDescBoxH + 255) / 256 * 256;      // by
 constexpr int kOriSlots = 2 * kDescStages;     // orientation boxes in the ring
 static_assert(2 * ((kOriBoxW * kOriBoxH + 127) / 128 * 128) <= kDescStage, "one stage holds two orientation boxes");
 
-__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
+// (no register bound: with the 64 registers ptxas picks for a plain 128-thread bound the kernel is 9 % slower than with the
+// 72 it takes when left alone — the loads of a keypoint's test pairs are batched further ahead)
+__global__ void __launch_bounds__(kDescWarps * 32, 1) describe_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p,
                                                                    const __grid_constant__ TmaMaps mapsOri,
                                                                    const __grid_constant__ TmaMaps mapsBlur,
                                                                    const __grid_constant__ TmaMaps mapsBlurN) {
@@ -1634,41 +1690,79 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
         const ResizeTab& T = tabs[l];
         const size_t tile = (size_t)((T.boxW * T.boxH + 127) / 128 * 128);
         if (T.wide) {      // eight pixels per thread: 256-column CTAs, two source boxes
-            dim3 grid((D.w + 255) / 256, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
+            // a last column of <= 128 px would leave half of every warp of its CTAs idle: it goes to the four-pixel kernel
+            // (128-column CTAs) instead — 16 % of the lanes of the 1.2 pyramid of a 1241-px frame were such idle halves
+            const int rem = D.w % 256;
+#ifndef NAV24_RS_SPLIT
+#define NAV24_RS_SPLIT 1
+#endif
+            // (batches only: a single frame pays more for the extra launches than for the idle lanes — 0.047 -> 0.071 ms)
+            const bool split = NAV24_RS_SPLIT && B >= 16 && rem > 0 && rem <= 128 && T.boxW == 192 && D.w > 256;
+            const int cols8 = split ? D.w / 256 : (D.w + 255) / 256;
+            dim3 grid(cols8, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
             resize8_kernel<192><<<grid, 128, 2 * tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch,
-                                                                                        g.pyrFrameBytes, D.w, D.h, T);
+                                                                                        g.pyrFrameBytes, split ? cols8 * 256 : D.w, D.h, T);
+            if (split) {
+                dim3 gridR(1, grid.y, B);
+                resize_kernel<192><<<gridR, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T,
+                                                            cols8 * 256);
+                ++n;
+            }
         } else {
             dim3 grid((D.w + 127) / 128, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
             if (T.boxW == 192)
-                resize_kernel<192><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
+                resize_kernel<192><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T, 0);
             else
-                resize_kernel<256><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T);
+                resize_kernel<256><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T, 0);
         }
         ++n;
     }
     return n;
 }
 
-int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
-    cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
+// shared-memory layout of fast_band_kernel for the levels with minBoxH < boxH <= maxBoxH; returns the bytes (0: no such level)
+int fast_smem_bytes(const FrameGeom& g, int minBoxH, int maxBoxH, FastSmem* out) {
     FastSmem sm{};
     int tileBytes = 0, mwords = 0, wcap = 0;
     const int qcap = kFastQueueCap;
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& L = g.lv[l];
+        if (L.boxH <= minBoxH || L.boxH > maxBoxH) continue;
         tileBytes = max(tileBytes, L.boxW * L.boxH + 64);
         mwords = max(mwords, ((L.segCols * L.wCell + 31) / 32) * L.hCell);
         wcap = max(wcap, L.segCols * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2));      // strict 3x3 maxima inside a cell: one per 2x2 block
     }
+    if (tileBytes == 0) return 0;
     tileBytes = (tileBytes + 127) / 128 * 128;
     sm.offMap = tileBytes;
     sm.offMask = 2 * tileBytes;                                               // cleared together with the score map
     sm.offQueue = sm.offMask + (mwords * 4 + 15) / 16 * 16;
     sm.total = sm.offQueue + (max(qcap, wcap) * 2 + 15) / 16 * 16 + 16;      // (the dense path lists its keypoints in the queue)
-    cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(sm.total, 48 * 1024));
-    dim3 grid(g.totalSegs, B);
-    fast_band_kernel<<<grid, kFastThreads, sm.total, s>>>(g, p, maps, sm, iniTh, minTh);
-    return 1;
+    if (out) *out = sm;
+    return sm.total;
+}
+
+// The tile and the score map are sized by the tallest cell row of the launch, and one level with tall cells (KITTI: 47-px
+// cells at level 6, 39 elsewhere) would cost every CTA of the frame a resident CTA per SM (6 instead of 7).  The segment
+// table therefore lists the levels with boxH <= g.fastCutH first (build_geometry picks the cut) and they are launched
+// apart from the tall ones, each group with its own layout.
+int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
+    cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
+    int n = 0;
+    const bool grouped = g.segsLow < g.totalSegs && B >= 16;      // (a small batch does not fill the SMs: one launch)
+    const int cutH = grouped ? g.fastCutH : 1 << 30, segsLow = grouped ? g.segsLow : g.totalSegs;
+    const int lo[2] = {0, cutH}, hi[2] = {cutH, 1 << 30}, seg0[2] = {0, segsLow}, nSeg[2] = {segsLow, g.totalSegs - segsLow};
+    int maxTotal = 0;
+    FastSmem sm[2];
+    for (int k = 0; k < 2; ++k) maxTotal = max(maxTotal, nSeg[k] > 0 ? fast_smem_bytes(g, lo[k], hi[k], &sm[k]) : 0);
+    cudaFuncSetAttribute(fast_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max(maxTotal, 48 * 1024));
+    for (int k = 0; k < 2; ++k) {
+        if (nSeg[k] <= 0) continue;
+        dim3 grid(nSeg[k], B);
+        fast_band_kernel<<<grid, kFastThreads, sm[k].total, s>>>(g, p, maps, sm[k], iniTh, minTh, seg0[k]);
+        ++n;
+    }
+    return n;
 }
 
 // test hook: std::sort of n records (key = high 32 bits) by one warp, in shared memory
@@ -1723,8 +1817,10 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     dim3 grid(g.nlevels, B);
     // 256 threads per (level, frame) when the batch fills the GPU (128: 5 % faster alone, slower in the chunked host
     // pipeline); a small batch (single-camera latency) has few CTAs, so each gets 1024 threads for its parallel passes
+    qs.orderInside = nCta < 2 * 148;
     if (big) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, qs);
     else quadtree_kernel<256><<<grid, 256, smem, s>>>(g, p, qs);
+    if (qs.orderInside) return 1;
     order_kernel<<<B, 256, 0, s>>>(g, p);
     return 2;
 }
