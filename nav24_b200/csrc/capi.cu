@@ -1199,8 +1199,12 @@ int nav24_orb_detect_match_device(nav24_orb* ctx, const uint8_t* d_gray, int n_f
         MatchPlan mp{n_pairs, pairs_ab, grid, window, nnratio, th_low, check_ori};
         // Device-resident frames need no copy overlap, and cutting the batch only shortens the latency-bound launches
         // (quadtree, matcher) without making them cheaper: measured 3.24 ms/step as one chunk vs 3.47 ms in chunks of 64.
+        // A large batch is still cut once, into two halves on two streams: the tails of one half's kernels are filled by the
+        // other half (1024 KITTI frames: 5.99 -> 5.92 ms; three chunks 5.95, four and more slower).  NAV24_RESIDENT_CHUNK
+        // overrides (a value >= the batch: one chunk).
+        const int autoChunk = n_frames >= 512 ? ((n_frames + 1) / 2 + 1) & ~1 : n_frames;      // even: stereo pairs stay inside a chunk
         return run_chunked(ctx, n_frames, w, h, nullptr, stride, frame_stride, n_pairs > 0 ? &mp : nullptr, nullptr, nullptr, 0,
-                           nullptr, nullptr, nullptr, 0, nullptr, ctx->residentChunk > 0 ? ctx->residentChunk : n_frames);
+                           nullptr, nullptr, nullptr, 0, nullptr, ctx->residentChunk > 0 ? ctx->residentChunk : autoChunk);
     });
 }
 

@@ -1135,7 +1135,10 @@ __device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p
 
 template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency; one CTA
                        // per SM is enough there, so it may use 64 registers: the default bound of 32 spilled 616 bytes of loads)
-__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 6) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
+#ifndef NAV24_QT_MINB
+#define NAV24_QT_MINB 5
+#endif
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NAV24_QT_MINB) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
     extern __shared__ __align__(16) unsigned long long s_sort[];
     __shared__ int s_scan[33];
     __shared__ int s_K, s_nexp;
