@@ -186,6 +186,31 @@ def test_batch_equals_single(ctxs):
         assert int((desc[f, :n[f]] != do).any(axis=1).sum()) <= DESC_TOL * len(ko)
 
 
+@pytest.mark.parametrize("H,W,nf", [(480, 752, 1000), (243, 427, 500), (376, 1241, 2000)])
+def test_batch_launch_paths_equal_single_frame_paths(ctxs, H, W, nf):
+    """Batches of >= 16 frames take launch paths a single frame never sees: FAST launched per tile-height group, the
+    <= 128-px remainder column of a wide pyramid level through the four-pixel resize kernel, the output order as its own
+    kernel.  Every frame of such a batch must equal the same frame detected alone (which takes the other paths), and
+    sampled frames must equal the oracle, level by level."""
+    ctx = _ctx(ctxs, nf)
+    frames = np.stack([synth(H, W, 300 + i, lowtex=(i % 5 == 4)) for i in range(18)])
+    n, mono, kps, desc = ctx.detect_batch(frames)
+    lv = {f: [ctx.level(f, l) for l in range(8)] for f in (0, 17)}
+    raw = {f: [ctx.raw_keys(f, l) for l in range(8)] for f in (0, 17)}
+    for f in range(len(frames)):
+        m1, k1, d1 = ctx.detect(frames[f])
+        assert mono[f] == m1 and n[f] == len(k1)
+        assert kps[f, :n[f]].tobytes() == k1.tobytes() and np.array_equal(desc[f, :n[f]], d1)
+    o = oo.OrbOracle(nf)
+    for f in (0, 17):
+        mo, ko, do = o.detect(frames[f])
+        assert mono[f] == mo and kps[f, :n[f]].tobytes() == ko.tobytes()
+        assert int((desc[f, :n[f]] != do).any(axis=1).sum()) <= DESC_TOL * len(ko)
+        for l in range(8):
+            assert np.array_equal(lv[f][l], o.level(l)), f"pyramid level {l} of frame {f}"
+            assert np.array_equal(raw[f][l], o.raw(l)), f"raw FAST keys level {l} of frame {f}"
+
+
 def test_window_matcher_parity(ctxs):
     ctx = _ctx(ctxs, 1000)
     for (H, W, step) in [(480, 752, (2, 1)), (376, 1241, (17, 0)), (480, 640, (3, 1))]:
