@@ -99,7 +99,9 @@ def test_roofline_inputs_come_from_the_newest_ncu_summary():
     import bench
     path, frames, rows = bench.newest_ncu_summary()
     assert re.match(r"r\d+_v\d+_ncu_full_summary\.md$", os.path.basename(path)) and frames > 0
-    assert any("fast_band" in k for k in rows) and sum(len(v) for k, v in rows.items() if "resize_kernel" in k) == 7
+    # one step = every pyramid level once: 7 eight-pixel launches (resize8) plus the four-pixel launches of the remainder columns
+    assert any("fast_band" in k for k in rows) and sum(len(v) for k, v in rows.items() if "resize8" in k) == 7
+    assert 7 <= sum(len(v) for k, v in rows.items() if "resize" in k) <= 14
     pix = bench.level_pixels(376, 1241)
     assert pix == 1444097
     traffic, inst_px, src = bench.pyrfast_from_summary(pix)
