@@ -22,7 +22,10 @@ constexpr int kDescBoxWN = 48;                  // narrow box of the descriptor 
 constexpr int kFastThreads = 256;   // threads per CTA of fast_band_kernel
 constexpr int kFastMaxSegCells = 8; // cells of one FAST segment (TMA boxes are <= 256 px wide, cells >= 35 px)
 constexpr int kFastQueueCap = 3072; // stage A survivors one CTA queues (typ. 700 of 8400 pixels); beyond: the dense path
-constexpr int kFastPitch = 256;     // row pitch of the FAST tile in shared memory = TMA box width, the same for every level, so
+#ifndef NAV24_FAST_PITCH
+#define NAV24_FAST_PITCH 256
+#endif
+constexpr int kFastPitch = NAV24_FAST_PITCH;     // row pitch of the FAST tile in shared memory = TMA box width (multiple of 16, <= 256), the same for every level, so
                                     // that every tap of the kernel is an immediate offset
 
 // device error bits (ctx->d_err)

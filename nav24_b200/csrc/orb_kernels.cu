@@ -670,7 +670,8 @@ __global__ void NAV24_FAST_LB fast_band_kernel(const __grid_constant__ FrameGeom
         // interior count as 0
         auto nms = [&](int e) {
             const uint8_t* q = smap + e;
-            const int xx = (e & (P - 1)) - c_lo;
+            const int er = (int)__umulhi((unsigned)e, 0xFFFFFFFFu / (unsigned)P + 1u);      // e / P: tile row (e < 65536)
+            const int xx = (e - er * P) - c_lo;
             const int cl = xx - (int)__umulhi((unsigned)xx, L.magicW) * wCell;      // column inside the cell's interior
             const int s = q[0];
             int m = max((int)q[-P], (int)q[P]);
@@ -679,8 +680,7 @@ __global__ void NAV24_FAST_LB fast_band_kernel(const __grid_constant__ FrameGeom
             if (cl > 0) m = max(m, ml);
             if (cl < wCell - 1) m = max(m, mr);
             if (s > m) {
-                static_assert(kFastPitch == 256, "row = offset >> 8");
-                const int bi = ((e >> 8) - 3) * (wpr << 5) + xx;
+                const int bi = (er - 3) * (wpr << 5) + xx;
                 atomicOr(&kmask[bi >> 5], 1u << (bi & 31));
                 return true;
             }

@@ -312,6 +312,50 @@ def test_device_resident_match_frames(ctxs):
         assert nm[p] == (ref >= 0).sum() and nm[p] > 50
 
 
+def test_large_resident_batch_runs_as_two_halves(monkeypatch, cuda_required):
+    """Device-resident batches of >= 512 frames are cut into two halves on two streams (capi.cu, detect_match_device).
+    The results must equal the same batch run as one chunk, pairs that span the halves included, and sampled frames / pairs
+    must equal the oracle."""
+    H, W, nf, B = 260, 340, 300, 514
+    base = sequence(H, W, 77, 8, step=(4, 1))
+    fr = np.ascontiguousarray(np.stack([base[(f * 5) % 8] if f % 3 else synth(H, W, 400 + f % 11) for f in range(B)]))
+    pitch = (W + 127) // 128 * 128
+    buf = np.zeros((B, H, pitch), np.uint8)
+    buf[:, :, :W] = fr
+    pairs = [(2 * i, 2 * i + 1) for i in range(B // 2)] + [(256, 257), (255, 258), (0, 513), (256, 255)]
+    grid = capi.grid_for(W, H)
+    res = {}
+    for name, env in (("halves", None), ("one", "100000")):
+        if env:
+            monkeypatch.setenv("NAV24_RESIDENT_CHUNK", env)
+        ctx = capi.OrbContext(nf)
+        try:
+            dptr = capi.C.c_void_p()
+            assert ctx.L.nav24_device_alloc(buf.nbytes, capi.C.byref(dptr)) == 0
+            assert ctx.L.nav24_memcpy_h2d(dptr, buf.ctypes.data_as(capi.C.c_void_p), buf.nbytes) == 0
+            for _ in range(2):      # twice: the second call runs ahead of the first one's tail on the second stream
+                ctx.detect_match_device(dptr.value, B, W, H, pitch, pitch * H, pairs, grid)
+            ctx.sync()
+            res[name] = ctx.fetch(B) + ctx.match_fetch(len(pairs))
+            ctx.L.nav24_device_free(dptr)
+        finally:
+            ctx.close()
+    (n, mono, kps, desc, m, nm), (n2, mono2, kps2, desc2, m2, nm2) = res["halves"], res["one"]
+    assert np.array_equal(n, n2) and np.array_equal(mono, mono2) and np.array_equal(nm, nm2)
+    for f in range(B):
+        assert kps[f, :n[f]].tobytes() == kps2[f, :n[f]].tobytes() and np.array_equal(desc[f, :n[f]], desc2[f, :n[f]])
+    for q, (a, b) in enumerate(pairs):
+        assert np.array_equal(m[q, :n[a]], m2[q, :n[a]])
+    o = oo.OrbOracle(nf)
+    for f in (0, 255, 256, 257, 513):
+        mo, ko, do = o.detect(fr[f])
+        assert mono[f] == mo and kps[f, :n[f]].tobytes() == ko.tobytes()
+        assert int((desc[f, :n[f]] != do).any(axis=1).sum()) <= DESC_TOL * max(1, len(ko))
+    for q in (128, B // 2, B // 2 + 1, B // 2 + 2, B // 2 + 3):
+        a, b = pairs[q]
+        assert np.array_equal(m[q, :n[a]], _oracle_matches_on(kps, desc, n, a, b, oo.grid_for(W, H)))
+
+
 @pytest.mark.parametrize("norm", [0, 1])
 def test_bf_knn2_parity(ctxs, norm):
     ctx = _ctx(ctxs, 1000)
