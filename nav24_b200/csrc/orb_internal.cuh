@@ -143,7 +143,10 @@ struct ResizeTab {           // per level >= 1: source offsets and 11-bit coeffi
 };
 
 constexpr int kResizeMaxRows = 32;     // destination rows of one warp strip of resize_kernel (one lane per row's constants)
-constexpr int kResizeCtaRows = 64;     // target destination rows per CTA (4 warp strips)
+#ifndef NAV24_RESIZE_CTA_ROWS
+#define NAV24_RESIZE_CTA_ROWS 64
+#endif
+constexpr int kResizeCtaRows = NAV24_RESIZE_CTA_ROWS;     // target destination rows per CTA (4 warp strips)
 
 // launchers (orb_kernels.cu); each returns the number of kernels launched
 // tight (pitch = w) host-order frames -> 16-byte aligned pitch (TMA needs it); returns 1

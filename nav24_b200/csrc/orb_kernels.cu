@@ -1144,7 +1144,9 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NAV24_QT_MINB) quadtree_k
     __shared__ int s_K, s_nexp;
 
     const int tid = threadIdx.x, nth = NT;
-    const int l = blockIdx.x, f = blockIdx.y;
+    // grid = (frames, levels): CTAs are handed out level by level, i.e. the long ones first (level 0 has 13 x the keys of level
+    // 7), so that the kernel does not end on a few level-0 CTAs that started late
+    const int l = blockIdx.y, f = blockIdx.x;
     const LevelGeom& L = g.lv[l];
     const long long fr = (long long)f * g.rawPerFrame + L.rawOff;
     const long long fn = (long long)f * g.nodesPerFrame + L.nodeOff;
@@ -1817,7 +1819,7 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     }
     cudaFuncSetAttribute(quadtree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(quadtree_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    dim3 grid(g.nlevels, B);
+    dim3 grid(B, g.nlevels);
     // 256 threads per (level, frame) when the batch fills the GPU (128: 5 % faster alone, slower in the chunked host
     // pipeline); a small batch (single-camera latency) has few CTAs, so each gets 1024 threads for its parallel passes
     qs.orderInside = nCta < 2 * 148;
