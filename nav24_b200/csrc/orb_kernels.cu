@@ -839,7 +839,8 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
                                              const int sortSmemCap, unsigned long long* s_sort, int* s_scan, int* s_K, int* s_nexp,
                                              const RawRec* __restrict__ keys, unsigned short* __restrict__ nodeOfKey, QNode* cur, QNode* nxt,
                                              int* childCnt, int* aux, unsigned* best, const RawRec* __restrict__ raw,
-                                             const uint2* __restrict__ cinfo, const int* __restrict__ cdst, const int nC, RawRec* keysOut) {
+                                             const uint2* __restrict__ cinfo, const int* __restrict__ cdst, const int nC, RawRec* keysOut,
+                                             const uint2* s_ci, const int* s_dst) {
     const int tid = threadIdx.x, nth = NT;
     const LevelGeom& L = g.lv[l];
     const long long fn = (long long)f * g.nodesPerFrame + L.nodeOff;
@@ -853,12 +854,44 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
     __syncthreads();
     // The per-cell lists of the FAST kernel go into the reference order (cells row-major, row-major inside a cell: keysOut =
     // `keys`, read back only after the barrier below) and every key is counted into its root on the way.
-    // A warp takes 32 consecutive cells, lane j the table entry of cell c0 + j.  Their keys are consecutive in the ordered
+    // Levels whose cell table does not fit the CTA's shared memory (4K frames): a warp takes 32 consecutive cells, lane j the
+    // table entry of cell c0 + j.  Their keys are consecutive in the ordered
     // array, so entry t of the group goes to keys[first + t] (coalesced) and comes from the cell whose inclusive count
     // first exceeds t (binary search over the lanes); the trips are independent, four are in flight at a time.  (One warp
     // per cell — table entry, then keys, then the next cell — was a chain of dependent L2 latencies: 17 % of this kernel's
     // stall samples.)
-    {
+    if (s_ci) {
+        // the cell table (source offset, ordered offset) is in shared memory: a thread per key finds its cell by binary search
+        // over the ordered offsets — the last cell whose offset is <= i — so that the only global round trip of the
+        // gather is the key itself, four per thread in flight
+        for (int i0 = tid; i0 < n; i0 += 4 * nth) {
+            int src[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(i0 + u * nth, n - 1);
+                int lo = 0, hi = nC;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_dst[mid] <= i) lo = mid; else hi = mid;
+                }
+                src[u] = (int)s_ci[lo].x + (i - s_dst[lo]);
+            }
+            RawRec rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rr[u] = raw[src[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nth;
+                if (i < n) {
+                    keysOut[i] = rr[u];
+                    int r = (int)__fdiv_rn((float)rr[u].x, hX);
+                    if (r >= nIni || r < 0) { atomicOr(p.err, ERR_ROOT_RANGE); r = nIni - 1; }
+                    nodeOfKey[i] = (unsigned short)r;
+                    atomicAdd(&childCnt[r], 1);
+                }
+            }
+        }
+    } else {
         const int lane = tid & 31;
         for (int c0 = (tid >> 5) * 32; c0 < nC; c0 += nth) {
             const int c = c0 + lane;
@@ -1157,13 +1190,20 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NAV24_QT_MINB) quadtree_k
 
     // (a) bring the per-cell lists into the reference order: cells row-major, row-major inside a cell
     const int nC = L.nCols * L.nRows;
+    // the cell table goes to shared memory (in the sort scratch, which is idle until the "largest first" phase) when it fits
+    const bool cellsInSm = (size_t)nC * 12 <= quadtree_sort_bytes(qs.sortCap);
+    uint2* s_ci = reinterpret_cast<uint2*>(s_sort);
+    int* s_dst = reinterpret_cast<int*>(s_ci + nC);
     int n = 0;
     for (int base = 0; base < nC; base += nth) {
         const int c = base + tid;
-        const int cnt = c < nC ? (int)cinfo[c].y : 0;
+        const uint2 ci = c < nC ? cinfo[c] : make_uint2(0u, 0u);
         int tot;
-        const int ex = block_excl_scan(cnt, &tot, s_scan);
-        if (c < nC) cdst[c] = n + ex;
+        const int ex = block_excl_scan((int)ci.y, &tot, s_scan);
+        if (c < nC) {
+            if (cellsInSm) { s_ci[c] = ci; s_dst[c] = n + ex; }
+            else cdst[c] = n + ex;
+        }
         n += tot;
     }
     __syncthreads();
@@ -1181,10 +1221,12 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NAV24_QT_MINB) quadtree_k
     if (n == 0) {
         if (tid == 0) p.levelCount[f * g.nlevels + l] = 0;
     } else if (useSm) {
-        quadtree_run<NT, true>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, sA, sB, sChild, sAux, sBest, raw, cinfo, cdst, nC, gkeys);
+        quadtree_run<NT, true>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, sA, sB, sChild, sAux, sBest, raw, cinfo, cdst, nC, gkeys,
+                               cellsInSm ? s_ci : nullptr, s_dst);
     } else {
         quadtree_run<NT, false>(g, p, l, f, n, qs.sortCap, s_sort, s_scan, &s_K, &s_nexp, gkeys, nok, p.nodesA + fn, p.nodesB + fn,
-                                p.childCnt + 4 * fn, p.nodeAux + fn, reinterpret_cast<unsigned*>(p.best + fn), raw, cinfo, cdst, nC, gkeys);
+                                p.childCnt + 4 * fn, p.nodeAux + fn, reinterpret_cast<unsigned*>(p.best + fn), raw, cinfo, cdst, nC, gkeys,
+                                cellsInSm ? s_ci : nullptr, s_dst);
     }
     // small batches: the CTA that finishes last among the levels of frame f puts the frame's keypoints into the output order
     if (!qs.orderInside) return;
