@@ -49,6 +49,8 @@ __device__ __forceinline__ long long level_pitch(const FrameGeom& g, const DevPt
 
 // exclusive block scan of one int per thread; returns the exclusive prefix, *total = block sum.
 // All threads of the block must call it. blockDim.x must be a multiple of 32, <= 1024.
+// Fewest instructions (warp 0 alone scans the warp sums), three barriers: the form for the issue-bound FAST kernel
+// (the one-barrier form below made it 1.5 % slower).
 __device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /* >= 33 ints */) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int incl = v;
@@ -74,6 +76,33 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /*
     __syncthreads();
     *total = s_warp[32];
     return s_warp[wid] + incl - v;
+}
+
+// The same scan with ONE barrier per call, for the kernels that live on barrier latency (quadtree, order: 0.624 -> 0.606 ms): every warp leaves its sum in shared memory, and after the barrier every warp scans the (<= 32)
+// warp sums itself.  The sums alternate between two buffers, so a warp that is already in the next call cannot overwrite
+// what a slower warp still reads (it cannot be two calls ahead: the next call's barrier is in between).
+struct BlockScan { int* buf; int par; };      // buf: 2 x 32 ints of shared memory; par = 0 at kernel start
+__device__ __forceinline__ int block_excl_scan(int v, int* total, BlockScan& bs) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int* w = bs.buf + 32 * bs.par;
+    bs.par ^= 1;
+    if (lane == 31) w[wid] = incl;
+    __syncthreads();
+    const int ws = lane < nw ? w[lane] : 0;
+    int wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+    }
+    *total = __shfl_sync(0xffffffffu, wi, nw - 1);
+    return __shfl_sync(0xffffffffu, wi - ws, wid) + incl - v;
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -836,7 +865,7 @@ __device__ __forceinline__ int quadrant_of(const QNode& n, int x, int y) {
 // latency, not by bandwidth — got 23 % slower instead of faster.
 template <int NT, bool SM>
 __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& p, const int l, const int f, const int n,
-                                             const int sortSmemCap, unsigned long long* s_sort, int* s_scan, int* s_K, int* s_nexp,
+                                             const int sortSmemCap, unsigned long long* s_sort, BlockScan& s_scan, int* s_K, int* s_nexp,
                                              const RawRec* __restrict__ keys, unsigned short* __restrict__ nodeOfKey, QNode* cur, QNode* nxt,
                                              int* childCnt, int* aux, unsigned* best, const RawRec* __restrict__ raw,
                                              const uint2* __restrict__ cinfo, const int* __restrict__ cdst, const int nC, RawRec* keysOut,
@@ -996,9 +1025,10 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
                     const int4 cc = *reinterpret_cast<const int4*>(childCnt + nd * 4);
                     ne = (cc.x > 0) + (cc.y > 0) + (cc.z > 0) + (cc.w > 0);
                 }
-                int totNe, totUn;
-                const int exNe = block_excl_scan(ne, &totNe, s_scan);
-                const int exUn = block_excl_scan(valid && !split, &totUn, s_scan);
+                // (one scan for both counts: per call they stay below 4 x 1024 and 1024, so they share a word)
+                int tot2;
+                const int ex2 = block_excl_scan(ne | ((int)(valid && !split) << 16), &tot2, s_scan);
+                const int exNe = ex2 & 0xffff, exUn = ex2 >> 16, totNe = tot2 & 0xffff, totUn = tot2 >> 16;
                 if (valid) aux[nd] = split ? (C + exNe) : -(U + exUn) - 1;
                 C += totNe; U += totUn;
             }
@@ -1164,7 +1194,7 @@ __device__ __forceinline__ void quadtree_run(const FrameGeom& g, const DevPtrs& 
 // Shared-memory table sizes of quadtree_kernel (nodeCap 0: the node tables stay in global memory)
 struct QtSmem { int sortCap, nodeCap, orderInside; };
 
-__device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p, const int f, int* s_scan);      // K7, below
+__device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p, const int f, BlockScan& s_scan);      // K7, below
 
 template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 1024 for small batches (single-camera latency; one CTA
                        // per SM is enough there, so it may use 64 registers: the default bound of 32 spilled 616 bytes of loads)
@@ -1173,7 +1203,8 @@ template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 102
 #endif
 __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NAV24_QT_MINB) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
     extern __shared__ __align__(16) unsigned long long s_sort[];
-    __shared__ int s_scan[33];
+    __shared__ int s_scanBuf[64];
+    BlockScan s_scan{s_scanBuf, 0};
     __shared__ int s_K, s_nexp;
 
     const int tid = threadIdx.x, nth = NT;
@@ -1255,7 +1286,7 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NAV24_QT_MINB) quadtree_k
 // launch (0.107 vs 0.07 ms per 1024 KITTI frames).  The level tables may have been written by other CTAs of the same
 // launch, so they are read with ld.global.cg (L2), never through L1.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p, const int f, int* s_scan) {
+__device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p, const int f, BlockScan& s_scan) {
     const int tid = threadIdx.x, nth = blockDim.x;
     int n = 0;
     for (int l = 0; l < g.nlevels; ++l) n += __ldcg(p.levelCount + f * g.nlevels + l);
@@ -1273,9 +1304,9 @@ __device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p
                 st = xs >= 0.f && xs <= 1000.f;
                 mo = !st;
             }
-            int tS, tM;
-            const int eS = block_excl_scan(st, &tS, s_scan);
-            const int eM = block_excl_scan(mo, &tM, s_scan);
+            int t2;      // (one scan for both counts: each stays below 1024 per call, so they share a word)
+            const int e2 = block_excl_scan((int)st | ((int)mo << 16), &t2, s_scan);
+            const int eS = e2 & 0xffff, eM = e2 >> 16, tS = t2 & 0xffff, tM = t2 >> 16;
             if (i < cnt) lkp[i].dst = st ? n - 1 - (nSt + eS) : nMo + eM;
             nSt += tS; nMo += tM;
         }
@@ -1287,7 +1318,8 @@ __device__ __forceinline__ void order_frame(const FrameGeom& g, const DevPtrs& p
 }
 
 __global__ void __launch_bounds__(256) order_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p) {
-    __shared__ int s_scan[33];
+    __shared__ int s_scanBuf[64];
+    BlockScan s_scan{s_scanBuf, 0};
     order_frame(g, p, blockIdx.x, s_scan);
 }
 
