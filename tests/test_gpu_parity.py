@@ -211,6 +211,36 @@ def test_batch_launch_paths_equal_single_frame_paths(ctxs, H, W, nf):
             assert np.array_equal(raw[f][l], o.raw(l)), f"raw FAST keys level {l} of frame {f}"
 
 
+@pytest.mark.parametrize("H,W", [(240, 512), (300, 641), (260, 769), (333, 897), (250, 1025), (301, 1153), (256, 1281), (270, 1409),
+                                 (480, 307), (600, 460)])
+def test_batch_launch_paths_geometry_sweep(cuda_required, H, W):
+    """Level widths around the 128 / 256-column boundaries of the resize kernels and cell heights that put the levels into
+    different FAST launch groups: a batch of 16 (batch launch paths) must equal the single-frame call (single-launch paths)
+    byte for byte, pyramid levels and raw FAST keys included; one frame per shape is also checked against the oracle."""
+    nf = 700
+    ctx = capi.OrbContext(nf)
+    try:
+        img = synth(H, W, 500 + W, lowtex=(W % 2 == 0))
+        frames = np.stack([img] * 16)
+        n, mono, kps, desc = ctx.detect_batch(frames)
+        lv = [ctx.level(15, l) for l in range(8)]
+        raw = [ctx.raw_keys(15, l) for l in range(8)]
+        assert (n == n[0]).all() and (mono == mono[0]).all()
+        for f in range(1, 16):
+            assert kps[f, :n[f]].tobytes() == kps[0, :n[0]].tobytes() and np.array_equal(desc[f, :n[f]], desc[0, :n[0]])
+        m1, k1, d1 = ctx.detect(img)
+        assert mono[0] == m1 and kps[0, :n[0]].tobytes() == k1.tobytes() and np.array_equal(desc[0, :n[0]], d1)
+        for l in range(8):
+            assert np.array_equal(lv[l], ctx.level(0, l)), f"pyramid level {l}"
+            assert np.array_equal(raw[l], ctx.raw_keys(0, l)), f"raw FAST keys level {l}"
+        o = oo.OrbOracle(nf)
+        mo, ko, do = o.detect(img)
+        assert m1 == mo and k1.tobytes() == ko.tobytes()
+        assert int((d1 != do).any(axis=1).sum()) <= DESC_TOL * max(1, len(ko))
+    finally:
+        ctx.close()
+
+
 def test_window_matcher_parity(ctxs):
     ctx = _ctx(ctxs, 1000)
     for (H, W, step) in [(480, 752, (2, 1)), (376, 1241, (17, 0)), (480, 640, (3, 1))]:
