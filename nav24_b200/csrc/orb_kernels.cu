@@ -1201,7 +1201,7 @@ template <int NT>      // threads per CTA: 256 when the batch fills the GPU, 102
 #ifndef NAV24_QT_MINB
 #define NAV24_QT_MINB 5
 #endif
-__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : NAV24_QT_MINB) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
+__global__ void __launch_bounds__(NT, NT >= 512 ? 1 : NAV24_QT_MINB) quadtree_kernel(const __grid_constant__ FrameGeom g, const DevPtrs p, const QtSmem qs) {
     extern __shared__ __align__(16) unsigned long long s_sort[];
     __shared__ int s_scanBuf[64];
     BlockScan s_scan{s_scanBuf, 0};
@@ -1893,11 +1893,16 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     }
     cudaFuncSetAttribute(quadtree_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(quadtree_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(quadtree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid(B, g.nlevels);
     // 256 threads per (level, frame) when the batch fills the GPU (128: 5 % faster alone, slower in the chunked host
     // pipeline); a small batch (single-camera latency) has few CTAs, so each gets 1024 threads for its parallel passes
     qs.orderInside = nCta < 2 * 148;
-    if (big) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, qs);
+    // (small batches of megapixel-sized frames, a few thousand keys at level 0: 512 threads — the barriers are cheaper and the
+    // parallel passes are one trip either way: single KITTI frame 0.065 -> 0.062 ms, EuRoC 0.055 -> 0.051; 4K frames with
+    // 47 k keys at level 0 need the 1024: 0.264 vs 0.322 ms)
+    if (big && (long long)g.lv[0].w * g.lv[0].h < 1500000) quadtree_kernel<512><<<grid, 512, smem, s>>>(g, p, qs);
+    else if (big) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, qs);
     else quadtree_kernel<256><<<grid, 256, smem, s>>>(g, p, qs);
     if (qs.orderInside) return 1;
     order_kernel<<<B, 256, 0, s>>>(g, p);
