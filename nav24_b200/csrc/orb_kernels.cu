@@ -17,6 +17,12 @@
 #ifndef NAV24_BLUR_MINB
 #define NAV24_BLUR_MINB 0
 #endif
+#ifndef NAV24_RS_SPLIT
+#define NAV24_RS_SPLIT 1
+#endif
+#ifndef NAV24_PDL
+#define NAV24_PDL 1
+#endif
 #ifndef NAV24_RS_MINB
 #define NAV24_RS_MINB 1      // resize: 62 registers instead of 40 (the loads of a source row are issued further ahead): 0.79 -> 0.75 ms
 #endif
@@ -191,12 +197,16 @@ __global__ void NAV24_RS_LB resize_kernel(const __grid_constant__ CUtensorMap sr
     const int x0c = xBase + blockIdx.x * 128, y0c = blockIdx.y * 4 * rows;      // (xBase: the remainder strip of a wide level)
     const int tileX0 = __ldg(t.xofs + x0c) & ~15, tileY0 = __ldg(t.yofs + y0c);
     const unsigned barAddr = smem_u32(&bar);
+    // programmatic dependent launch (single-frame chains, launch_pyramid): the next level's CTAs may become resident now;
+    // what they do before their own griddepcontrol.wait touches only the per-geometry tables, never a pyramid level
+    asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");      // the source level is complete (no-op without the launch attribute)
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"((unsigned)(BOXW * t.boxH)) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -342,12 +352,14 @@ __global__ void NAV24_RS_LB resize8_kernel(const __grid_constant__ CUtensorMap s
     const unsigned barAddr = smem_u32(&bar);
     const unsigned tileBytes = (unsigned)(BOXW * t.boxH);
     const unsigned tileStride = (tileBytes + 127u) & ~127u;      // TMA destinations are 128-byte aligned
+    asm volatile("griddepcontrol.launch_dependents;");       // (see resize_kernel)
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(twoBoxes ? 2u * tileBytes : tileBytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -1758,6 +1770,19 @@ int launch_bgr2gray(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, 
     return 1;
 }
 
+// kernel launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the
+// stream is still running and orders itself behind it with griddepcontrol.wait (works under stream capture too)
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k, KArgs(std::forward<Args>(args))...);
+}
+
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s) {
     int n = 0;
     // (function attributes are per device and this library serves several devices and host threads: set on every call)
@@ -1768,19 +1793,19 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
         const LevelGeom& D = g.lv[l];
         const ResizeTab& T = tabs[l];
         const size_t tile = (size_t)((T.boxW * T.boxH + 127) / 128 * 128);
+        // a few frames: the chain of seven dependent launches is launch latency — levels 2.. start early (PDL) and wait for
+        // their source level inside the kernel
+        const bool pdl = NAV24_PDL && B <= 4 && l >= 2;
         if (T.wide) {      // eight pixels per thread: 256-column CTAs, two source boxes
             // a last column of <= 128 px would leave half of every warp of its CTAs idle: it goes to the four-pixel kernel
             // (128-column CTAs) instead — 16 % of the lanes of the 1.2 pyramid of a 1241-px frame were such idle halves
             const int rem = D.w % 256;
-#ifndef NAV24_RS_SPLIT
-#define NAV24_RS_SPLIT 1
-#endif
             // (batches only: a single frame pays more for the extra launches than for the idle lanes — 0.047 -> 0.071 ms)
             const bool split = NAV24_RS_SPLIT && B >= 16 && rem > 0 && rem <= 128 && T.boxW == 192 && D.w > 256;
             const int cols8 = split ? D.w / 256 : (D.w + 255) / 256;
             dim3 grid(cols8, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
-            resize8_kernel<192><<<grid, 128, 2 * tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch,
-                                                                                        g.pyrFrameBytes, split ? cols8 * 256 : D.w, D.h, T);
+            launch_k(resize8_kernel<192>, grid, dim3(128), 2 * tile, s, pdl, mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch,
+                     g.pyrFrameBytes, split ? cols8 * 256 : D.w, D.h, T);
             if (split) {
                 dim3 gridR(1, grid.y, B);
                 resize_kernel<192><<<gridR, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T,
@@ -1790,9 +1815,9 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
         } else {
             dim3 grid((D.w + 127) / 128, (D.h + 4 * T.rows - 1) / (4 * T.rows), B);
             if (T.boxW == 192)
-                resize_kernel<192><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T, 0);
+                launch_k(resize_kernel<192>, grid, dim3(128), tile, s, pdl, mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T, 0);
             else
-                resize_kernel<256><<<grid, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T, 0);
+                launch_k(resize_kernel<256>, grid, dim3(128), tile, s, pdl, mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T, 0);
         }
         ++n;
     }
