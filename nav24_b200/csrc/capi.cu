@@ -570,6 +570,7 @@ int run_pipeline(nav24_orb* ctx, int f0, int C, cudaStream_t s, bool stages, int
         ctx->evCalls++;
         CK(cudaEventRecord(ctx->ev[0], s));
     }
+    launch_fast_prepare(g, q, C, s);
     ctx->launches += launch_pyramid(g, q, ctx->tabs.data(), ctx->mapsRs, C, s);
     if (stages) CK(cudaEventRecord(ctx->ev[1], s));
     ctx->launches += launch_fast(g, q, ctx->maps, C, ctx->prm.ini_th_fast, ctx->prm.min_th_fast, s);

@@ -154,6 +154,7 @@ int launch_repack(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, in
 // tight interleaved BGR host-order frames -> grey at the aligned pitch (cv::cvtColor COLOR_BGR2GRAY fixed point); returns 1
 int launch_bgr2gray(const uint8_t* src, int w, int h, uint8_t* dst, int dPitch, int B, cudaStream_t s);
 int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, const TmaMaps& mapsSrc, int B, cudaStream_t s);
+void launch_fast_prepare(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);      // before launch_pyramid
 int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s);
 int fast_smem_bytes(const FrameGeom& g, int minBoxH, int maxBoxH, FastSmem* out);      // levels with minBoxH < boxH <= maxBoxH
 int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s);

@@ -569,6 +569,7 @@ __global__ void NAV24_FAST_LB fast_band_kernel(const __grid_constant__ FrameGeom
 
     const int tid = threadIdx.x, f = blockIdx.y;
     const int lane = tid & 31, wid = tid >> 5;
+    asm volatile("griddepcontrol.launch_dependents;");
     FastSeg sg;                                                      // 2 x 16 B, the same for all threads
     {
         const uint4* sp = reinterpret_cast<const uint4*>(p.segs + segBase + blockIdx.x);
@@ -581,6 +582,7 @@ __global__ void NAV24_FAST_LB fast_band_kernel(const __grid_constant__ FrameGeom
     const int nv = sg.nv, ih = sg.ih, iw = sg.iw;
     if (nv == 0) {
         if (tid < sg.nc) info[tid] = make_uint2(0u, 0u);
+        if (tid == 0) asm volatile("griddepcontrol.wait;" ::: "memory");      // (every CTA orders itself behind the previous grid: completion stays transitive)
         return;
     }
     const int wCell = L.wCell;
@@ -596,6 +598,9 @@ __global__ void NAV24_FAST_LB fast_band_kernel(const __grid_constant__ FrameGeom
     }
     __syncthreads();
     if (tid == 0) {
+        // (programmatic dependent launch, launch_fast: everything above reads the segment table and writes this segment's own
+        // cell entries only; the pyramid level is complete once this returns)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const unsigned bytes = (unsigned)(P * boxH);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
         asm volatile(
@@ -1220,6 +1225,9 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 1 : NAV24_QT_MINB) quadtree_ke
     __shared__ int s_K, s_nexp;
 
     const int tid = threadIdx.x, nth = NT;
+    // (programmatic dependent launch: resident early, ordered behind the FAST kernel here)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // grid = (frames, levels): CTAs are handed out level by level, i.e. the long ones first (level 0 has 13 x the keys of level
     // 7), so that the kernel does not end on a few level-0 CTAs that started late
     const int l = blockIdx.y, f = blockIdx.x;
@@ -1793,9 +1801,10 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
         const LevelGeom& D = g.lv[l];
         const ResizeTab& T = tabs[l];
         const size_t tile = (size_t)((T.boxW * T.boxH + 127) / 128 * 128);
-        // a few frames: the chain of seven dependent launches is launch latency — levels 2.. start early (PDL) and wait for
-        // their source level inside the kernel
-        const bool pdl = NAV24_PDL && B <= 4 && l >= 2;
+        // programmatic dependent launch: levels 2.. may become resident while the previous level is still running and wait for
+        // it inside the kernel (a single frame: the chain of seven launches is launch latency, 0.047 -> 0.037 ms; 1024 frames:
+        // the tail of every launch is filled earlier, 0.74 -> 0.72 ms)
+        const bool pdl = NAV24_PDL && l >= 2;
         if (T.wide) {      // eight pixels per thread: 256-column CTAs, two source boxes
             // a last column of <= 128 px would leave half of every warp of its CTAs idle: it goes to the four-pixel kernel
             // (128-column CTAs) instead — 16 % of the lanes of the 1.2 pyramid of a 1241-px frame were such idle halves
@@ -1808,8 +1817,8 @@ int launch_pyramid(const FrameGeom& g, const DevPtrs& p, const ResizeTab* tabs, 
                      g.pyrFrameBytes, split ? cols8 * 256 : D.w, D.h, T);
             if (split) {
                 dim3 gridR(1, grid.y, B);
-                resize_kernel<192><<<gridR, 128, tile, s>>>(mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch, g.pyrFrameBytes, D.w, D.h, T,
-                                                            cols8 * 256);
+                launch_k(resize_kernel<192>, gridR, dim3(128), tile, s, NAV24_PDL != 0, mapsSrc.m[l], p.frameBase, p.pyr + D.off, D.pitch,
+                         g.pyrFrameBytes, D.w, D.h, T, cols8 * 256);
                 ++n;
             }
         } else {
@@ -1850,8 +1859,13 @@ int fast_smem_bytes(const FrameGeom& g, int minBoxH, int maxBoxH, FastSmem* out)
 // cells at level 6, 39 elsewhere) would cost every CTA of the frame a resident CTA per SM (6 instead of 7).  The segment
 // table therefore lists the levels with boxH <= g.fastCutH first (build_geometry picks the cut) and they are launched
 // apart from the tall ones, each group with its own layout.
-int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
+// (the raw-list counters are cleared by launch_fast_prepare BEFORE the pyramid launches, so that the FAST kernel follows the
+// last resize kernel directly and can be launched as its programmatic dependent)
+void launch_fast_prepare(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s) {
     cudaMemsetAsync(p.rawCount, 0, sizeof(int) * (size_t)B * g.nlevels, s);
+}
+
+int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B, int iniTh, int minTh, cudaStream_t s) {
     int n = 0;
     const bool grouped = g.segsLow < g.totalSegs && B >= 16;      // (a small batch does not fill the SMs: one launch)
     const int cutH = grouped ? g.fastCutH : 1 << 30, segsLow = grouped ? g.segsLow : g.totalSegs;
@@ -1863,7 +1877,7 @@ int launch_fast(const FrameGeom& g, const DevPtrs& p, const TmaMaps& maps, int B
     for (int k = 0; k < 2; ++k) {
         if (nSeg[k] <= 0) continue;
         dim3 grid(nSeg[k], B);
-        fast_band_kernel<<<grid, kFastThreads, sm[k].total, s>>>(g, p, maps, sm[k], iniTh, minTh, seg0[k]);
+        launch_k(fast_band_kernel, grid, dim3(kFastThreads), (size_t)sm[k].total, s, NAV24_PDL != 0, g, p, maps, sm[k], iniTh, minTh, seg0[k]);
         ++n;
     }
     return n;
@@ -1926,9 +1940,9 @@ int launch_quadtree(const FrameGeom& g, const DevPtrs& p, int B, cudaStream_t s)
     // (small batches of megapixel-sized frames, a few thousand keys at level 0: 512 threads — the barriers are cheaper and the
     // parallel passes are one trip either way: single KITTI frame 0.065 -> 0.062 ms, EuRoC 0.055 -> 0.051; 4K frames with
     // 47 k keys at level 0 need the 1024: 0.264 vs 0.322 ms)
-    if (big && (long long)g.lv[0].w * g.lv[0].h < 1500000) quadtree_kernel<512><<<grid, 512, smem, s>>>(g, p, qs);
-    else if (big) quadtree_kernel<1024><<<grid, 1024, smem, s>>>(g, p, qs);
-    else quadtree_kernel<256><<<grid, 256, smem, s>>>(g, p, qs);
+    if (big && (long long)g.lv[0].w * g.lv[0].h < 1500000) launch_k(quadtree_kernel<512>, grid, dim3(512), smem, s, NAV24_PDL != 0, g, p, qs);
+    else if (big) launch_k(quadtree_kernel<1024>, grid, dim3(1024), smem, s, NAV24_PDL != 0, g, p, qs);
+    else launch_k(quadtree_kernel<256>, grid, dim3(256), smem, s, NAV24_PDL != 0, g, p, qs);
     if (qs.orderInside) return 1;
     order_kernel<<<B, 256, 0, s>>>(g, p);
     return 2;
