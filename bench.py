@@ -749,7 +749,7 @@ def main():
         "matches_per_pair": float(nm.mean()),
         "config": {"workload": WORKLOAD,
                    "pairs_per_step_per_gpu": P, "frames_per_step_per_gpu": F, "parallelism": f"sequences sharded x{world}, no collective",
-                   "pipeline": "fused detect+match; resident: one launch set per step; host buffers: chunks of <= 64 frames (short first and last chunks), H2D / three compute streams / D2H overlapped, one host synchronisation per call",
+                   "pipeline": "fused detect+match; resident: one launch set per half of the step's frames, the halves on two streams (batches >= 512 frames), resize / FAST / quadtree launched as programmatic dependents; host buffers: chunks of <= 64 frames (short first and last chunks), H2D / three compute streams / D2H overlapped, one host synchronisation per call",
                    "e2e_contexts": n_ctx, "host_numa_node": numa, "host_numa_nodes": numa_nodes, "host_cores": len(all_cpus),
                    "l2": f"two input sets alternate; per-step working set {(F * (pix * 2 + H * PITCH)) / 1e6:.0f} MB > 126 MB L2"},
         "stage_ms_per_step": {"pyramid": float(stage[0]) / max(calls, 1), "fast": float(stage[1]) / max(calls, 1),
