@@ -345,6 +345,29 @@ def pyrfast_from_summary(pix_per_frame):
     return dram / frames, inst / frames / pix_per_frame, os.path.relpath(path, ROOT)
 
 
+def pyrfast_warp_inst_per_frame():
+    """Warp-level instructions pyramid + FAST issue per frame (newest ncu summary), or None: the numerator of the issue-slot
+    roofline, the one that actually bounds the group."""
+    s = newest_ncu_summary()
+    if not s:
+        return None
+    _, frames, rows = s
+    inst = sum(num(r.get("inst", "0")) * 1e6 for name, rr in rows.items() if "resize" in name or "fast_band" in name for r in rr)
+    return inst / frames if inst > 0 else None
+
+
+def issue_roofline(pf_ms, frames, clocks, sms=148):
+    wi = pyrfast_warp_inst_per_frame()
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    if wi is None or pf_ms <= 0:
+        return None
+    achieved = wi * frames / (pf_ms * 1e-3) / 1e9
+    peak = sms * 4 * mhz * 1e6 / 1e9
+    return {"achieved": achieved, "peak": peak, "unit": "G warp-instructions/s", "frac": achieved / peak,
+            "how": "warp instructions of the resize + FAST launches per frame (newest ncu --set full summary) x frames per step / "
+                   "the group's CUDA-event time; peak = 148 SMs x 4 schedulers x SM clock under load"}
+
+
 def copy_ceiling(torch, barrier, world, h2d_bytes, d2h_bytes, chunks=16, seconds=1.0):
     """Pure-copy ceiling of the host<->device path of THIS box with all ranks copying at once: pinned H2D of one step's
     frames in `chunks` pieces on one stream, pinned D2H of one step's results on another, no kernels.  Returns the
@@ -734,6 +757,8 @@ def main():
                 # roofline is the one BASELINE.json's metric asks the group to be reported against
                 "limiter": "instruction issue (integer ALU / LSU pipes), DRAM < 25 % busy — see profiles/",
                 "inst_per_px": inst_px,
+                # the roofline that does bound the group: warp instructions issued (ncu summary) / (SMs x 4 schedulers x clock)
+                "issue": issue_roofline(pf_ms, F, clocks),
                 "traffic": traffic_frame * F if traffic_frame is not None else None, "traffic_source": src,
                 "traffic_over_algorithmic": (traffic_frame / alg_bytes_frame) if traffic_frame is not None else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_frame * F,
