@@ -648,7 +648,9 @@ __global__ void NAV24_FAST_LB fast_band_kernel(const __grid_constant__ FrameGeom
         const unsigned kk = (unsigned)(0x7f - min(th, 127)) * 0x01010101u;
         const bool reject = th < 128;
         for (int it = tid; it < nItems; it += NT) {
-            const int chunk = (int)__umulhi((unsigned)it, sg.magicG), gx = it - chunk * ngx;
+            // it / ngx by multiply-high; a divisor of 1 has no 32-bit magic (2^32): a last segment that is ONE cell whose
+            // interior is 1..4 px of one word (e.g. a 1149-px-wide level: 31 cells of 37, the last 7 px wide)
+            const int chunk = ngx == 1 ? it : (int)__umulhi((unsigned)it, sg.magicG), gx = it - chunk * ngx;
             const int wc = gx0 + gx, cb = 4 * wc;                      // tile column of byte 0
             const int first = max(c_lo - cb, 0), last = min(c_hi - cb, 4);      // interior bytes [first, last)
             unsigned vmask = (0x80808080u >> (8 * (4 - last))) & (0x80808080u << (8 * first));

@@ -112,6 +112,15 @@ def test_tile_edge_geometries(ctxs, H, W):
     _compare_detect(_ctx(ctxs, 400), synth(H, W, 5000 + H + W, lowtex=(H + W) % 3 == 0), 400)
 
 
+@pytest.mark.parametrize("H,W,low", [(300, 1149, True), (343, 1335, True), (310, 1151, True), (300, 1149, False), (290, 1150, False)])
+def test_last_fast_segment_of_one_narrow_cell(ctxs, H, W, low):
+    """Widths whose last FAST segment of level 0 is ONE cell with a 1- or 2-px interior (31 cells of 37 px over 1117 px: the last
+    cell is 7 px wide; found by tools/gpu_fuzz.py): the segment has a single word column, whose index / column split had
+    no 32-bit magic divisor, so only the first row of that cell was scanned.  Raw FAST keys of every level against the oracle."""
+    img = synth(H, W, 700 + W, lowtex=low)
+    _compare_detect(_ctx(ctxs, 2000), img, 2000)
+
+
 @pytest.mark.parametrize("scale,nlevels,ini,mn", [(1.1, 6, 20, 7), (1.5, 5, 30, 10), (1.33, 4, 12, 5), (1.8, 3, 20, 7)])
 def test_other_pyramid_parameters(scale, nlevels, ini, mn, cuda_required):
     """Scale factor, level count and FAST thresholds other than the defaults (OP_FtDt.cpp:31-48 reads them from YAML):
