@@ -226,13 +226,17 @@ __global__ void NAV24_RS_LB resize_kernel(const __grid_constant__ CUtensorMap sr
                                      __ldg(reinterpret_cast<const unsigned*>(t.yab) + yl));      // b0 | b1 << 16, both in [0, 2048]
     }
     // per-thread horizontal constants
+    // (lanes beyond the level mirror the LAST ACTIVE lane: the host sizes the source box for the windows of the active
+    // pixel groups; a lane clamped to column dw - 1 itself would start its window up to 3 source steps further right and
+    // read past the last tile row — an out-of-range shared-memory access at e.g. scale 1.6, level width 116)
     const bool active = x4 < dw;
-    const int s0 = __ldg(t.xofs + min(x4, dw - 1));
+    const int x4c = min(x4, (dw - 1) & ~3);
+    const int s0 = __ldg(t.xofs + x4c);
     const unsigned shift = (unsigned)(s0 & 3) * 8u;
     unsigned sel[4], ab[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int x = min(x4 + k, dw - 1);
+        const int x = min(x4c + k, dw - 1);
         const int d = __ldg(t.xofs + x) - s0;              // 0..5
         sel[k] = (unsigned)d | ((unsigned)(d + 1) << 4);
         ab[k] = __ldg(reinterpret_cast<const unsigned*>(t.xab) + x);      // (a0, a1) as two u16 (both in [0, 2048])
@@ -384,13 +388,14 @@ __global__ void NAV24_RS_LB resize8_kernel(const __grid_constant__ CUtensorMap s
     }
     // per-thread horizontal constants (columns beyond the level are clamped: their results are never stored)
     const bool active = x8 < dw;
-    const int s0 = __ldg(t.xofs + min(x8, dw - 1));
+    const int x8c = min(x8, (dw - 1) & ~7);                // (lanes beyond the level mirror the last active lane, see resize_kernel)
+    const int s0 = __ldg(t.xofs + x8c);
     const int tileX0 = __ldg(t.xofs + min(xh, dw - 1)) & ~15;
     const unsigned shift = (unsigned)(s0 & 3) * 8u;
     unsigned sel[8], ab[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int x = min(x8 + k, dw - 1);
+        const int x = min(x8c + k, dw - 1);
         int d = __ldg(t.xofs + x) - s0;                    // pixels 0..3: 0..6 inside the word pair (0, 1); 4..7: 4..10 -> 0..6 inside (1, 2)
         d = k < 4 ? min(d, 6) : min(max(d - 4, 0), 6);
         sel[k] = (unsigned)d | ((unsigned)(d + 1) << 4);

@@ -140,6 +140,27 @@ def test_other_pyramid_parameters(scale, nlevels, ini, mn, cuda_required):
         ctx.close()
 
 
+@pytest.mark.parametrize("H,W,scale,nl", [(909, 762, 1.6, 5), (300, 475, 1.6, 4), (360, 371, 1.5, 4), (400, 697, 1.33, 6)])
+def test_resize_lanes_beyond_a_narrow_level(cuda_required, H, W, scale, nl):
+    """Level widths that are not a multiple of the pixels a thread owns, at large scale factors (found by tools/gpu_fuzz2.py:
+    scale 1.6, 762 px -> ... -> 116 px): the lanes beyond the level used to place their source window up to three source steps
+    right of the last active lane's, past the last row of the shared-memory tile (an illegal address that killed the
+    context).  Every level against the oracle."""
+    img = np.random.default_rng(H * W).integers(0, 256, (H, W), dtype=np.uint8)
+    ctx = capi.OrbContext(100, scale_factor=scale, n_levels=nl, ini_th_fast=30, min_th_fast=30, raw_keys_per_kpx=250)
+    try:
+        o = oo.OrbOracle(100, scale, nl, 30, 30)
+        mono_o, k_o, d_o = o.detect(img)
+        mono_g, k_g, d_g = ctx.detect(img)
+        for l in range(nl):
+            assert np.array_equal(ctx.level(0, l), o.level(l)), f"pyramid level {l}"
+            assert np.array_equal(ctx.raw_keys(0, l), o.raw(l)), f"raw FAST keys level {l}"
+        assert mono_g == mono_o and k_g.tobytes() == k_o.tobytes()
+        assert int((d_g != d_o).any(axis=1).sum()) <= DESC_TOL * max(1, len(k_o))
+    finally:
+        ctx.close()
+
+
 def test_detect_strided_input_and_reuse(ctxs):
     ctx = _ctx(ctxs, 1000)
     big = synth(500, 800, 3)
