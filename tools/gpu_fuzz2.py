@@ -42,10 +42,13 @@ def image(H, W, kind, seed):
 
 
 while time.time() - t0 < budget:
-    W = int(rng.integers(200, 1700)); H = int(rng.integers(max(160, W // 4), min(1000, int(1.9 * W))))
+    if os.environ.get("FUZZ_BIG"):      # 2K .. 4K frames, feature counts up to the x5 mode of a 4K camera
+        W = int(rng.integers(1500, 4100)); H = int(rng.integers(max(700, W // 4), min(2300, int(1.5 * W))))
+    else:
+        W = int(rng.integers(200, 1700)); H = int(rng.integers(max(160, W // 4), min(1000, int(1.9 * W))))
     scale = float(rng.choice([1.1, 1.15, 1.2, 1.25, 1.33, 1.5, 1.6])); nl = int(rng.integers(3, 9))
     ini = int(rng.choice([10, 15, 20, 30, 45])); mn = int(rng.integers(3, ini + 1))
-    nf = int(rng.choice([100, 400, 1000, 2000, 5000, 9000])); kind = int(rng.integers(0, 5)); seed = int(rng.integers(0, 1 << 30))
+    nf = int(rng.choice([2000, 8000, 20000, 40000] if os.environ.get("FUZZ_BIG") else [100, 400, 1000, 2000, 5000, 9000])); kind = int(rng.integers(0, 5)); seed = int(rng.integers(0, 1 << 30))
     img = image(H, W, kind, seed)
     case = dict(H=H, W=W, scale=scale, nl=nl, ini=ini, mn=mn, nf=nf, kind=kind, seed=seed)
     if os.environ.get("FUZZ_TRACE"):
