@@ -17,6 +17,9 @@ DETECT_CASES = [  # H, W, nFeatures, seed, lowtex
     (480, 752, 1000, 24, False), (480, 752, 5000, 25, False), (480, 752, 200, 26, True),
     (376, 1241, 2000, 24, False), (376, 1241, 2000, 31, True), (376, 1241, 10000, 32, False),
     (480, 640, 1000, 7, True), (260, 340, 300, 5, True), (300, 900, 700, 9, False),
+    # widths whose last FAST cell of level 0 is 7 / 8 px wide (a 1- / 2-px interior): the geometry behind the first bug the
+    # randomised GPU runs found — pins the ORACLE's treatment of such cells to the reference's own cell loop
+    (300, 1149, 2000, 1849, True), (343, 1335, 2000, 2035, True), (310, 1151, 2000, 1851, True), (300, 1149, 2000, 1850, False),
 ]
 
 
