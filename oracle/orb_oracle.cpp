@@ -5,12 +5,16 @@
 // cpu_baseline / --impl reference legs as the checker and the timed CPU baseline.  Nothing in
 // nav24_b200/ may link or call this file.
 //
-// Parity status: the reference holds no golden vectors / known-answer tests for this path
-//  and cannot be compiled here (needs OpenCV C++, Eigen, glog, g2o), so the
-// oracle is pinned against (i) cv2 4.13.0 primitives (resize / FAST / GaussianBlur / fastAtan2 /
-// BFMatcher) called from oracle/orb_ref_cv2.py and (ii) golden fixtures generated by that
-// cv2-driven restatement (tests/golden/, tools/gen_golden.py).  "parity unpinned by the
-// reference's own tests; pinned to OpenCV 4.13.0 behaviour".
+// Parity status: PINNED.  The reference holds no golden vectors / known-answer tests for this path
+//  and its own build system cannot run here (OpenCV C++, Eigen, glog, g2o are
+// absent), so the oracle is pinned against
+//   (i)   live cv2 4.13.0 for every OpenCV primitive (resize / FAST / GaussianBlur / fastAtan2 /
+//         BFMatcher / cvtColor / undistortPoints; tests/test_oracle_vs_cv2.py, frozen in tests/golden/),
+//   (ii)  the reference's OWN translation units compiled unchanged from /root/reference into
+//         oracle/_ref (oracle/Makefile.ref, container stand-ins in oracle/ref_shim): extractor,
+//         quadtree, matcher, grid, frame classes (tests/test_ref_build.py) and the two-view scoring
+//         (TwoViewReconstruction::CheckHomography / CheckFundamental / FindHomography /
+//         FindFundamental, tests/test_two_view.py) — oracle == reference build, bit for bit.
 //
 // Build: g++ -O3 -march=x86-64-v3 -ffp-contract=off -shared -fPIC (see oracle/Makefile).
 // -ffp-contract=off matters: the reference is built without FMA contraction.
@@ -20,6 +24,7 @@
 //   operators/objAssoc/OP_FtAssocOrbSlam.cpp    (windowed matcher)
 //   operators/objAssoc/OP_FtAssoc.cpp           (brute-force kNN-2 + ratio)
 //   sensorData/observation/FeatureGrid.cpp      (10-px grid, candidate order)
+//   operators/mapInit/OP_2ViewReconstruction.cpp (CheckHomography / CheckFundamental)
 // OpenCV primitives follow SURVEY.md Appendix A (verified bit-exact vs cv2 4.13.0 by tests).
 
 #include <algorithm>

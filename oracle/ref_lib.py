@@ -21,8 +21,9 @@ def build(force=False):
     have_ref = os.path.exists(os.path.join(REF_ROOT, "core", "operators", "objDetection", "OP_FtDtOrbSlam.cpp"))
     if have_ref:
         oo.build()
-        src = [os.path.join(_HERE, f) for f in ("ref_driver.cpp", "ref_link_stubs.cpp", "Makefile.ref",
-                                                "ref_shim/opencv2/core.hpp", "_build/liborb_oracle.so")]
+        src = [os.path.join(_HERE, f) for f in ("ref_driver.cpp", "ref_driver_2v.cpp", "ref_link_stubs.cpp", "Makefile.ref",
+                                                "ref_shim/opencv2/core.hpp", "ref_shim/opencv2/core_algebra.hpp",
+                                                "_build/liborb_oracle.so")]
         stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
         if force or stale:
             subprocess.check_call(["make", "-C", _HERE, "-f", "Makefile.ref", "-B", "REF=" + REF_ROOT], stdout=subprocess.DEVNULL)
@@ -64,6 +65,20 @@ def lib():
         L.ref_grid_query.restype = C.c_int
         L.ref_grid_query.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float,
                                      C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        u8p = C.c_void_p
+        L.ref_2v_create.restype = C.c_void_p
+        L.ref_2v_create.argtypes = [C.c_void_p, C.c_float, C.c_int]
+        L.ref_2v_destroy.argtypes = [C.c_void_p]
+        L.ref_2v_reconstruct.restype = C.c_int
+        L.ref_2v_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, i32p]
+        L.ref_2v_get_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_2v_check_h.restype = C.c_float
+        L.ref_2v_check_h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, u8p]
+        L.ref_2v_check_f.restype = C.c_float
+        L.ref_2v_check_f.argtypes = [C.c_void_p, C.c_void_p, C.c_float, u8p]
+        L.ref_2v_hypotheses.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_2v_find_h.argtypes = [C.c_void_p, u8p, C.c_void_p, C.c_void_p]
+        L.ref_2v_find_f.argtypes = [C.c_void_p, u8p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -144,3 +159,70 @@ def grid_query(k2, ud2, W, H, x, y, r, min_level, max_level, bounds=None):
     out = np.zeros(max(1, len(k2)), np.int32)
     n = lib().ref_grid_query(_p(k2), _p(ud2), len(k2), W, H, _p(b), x, y, r, min_level, max_level, _p(out), len(out))
     return out[:n].copy()
+
+
+class RefTwoView:
+    """NAV24::OP::TwoViewReconstruction itself (core/operators/mapInit/OP_2ViewReconstruction.cpp), SURVEY 8(f)-4.
+    `reconstruct` runs the public entry point (match list, RANSAC sets, FindHomography / FindFundamental in two threads,
+    model selection); afterwards the private scoring members can be called on the match list it built."""
+
+    def __init__(self, K=None, sigma=1.0, iterations=200):
+        self.L = lib()
+        K = np.ascontiguousarray(K if K is not None else [[458.0, 0, 367.0], [0, 457.0, 248.0], [0, 0, 1]], np.float32)
+        self.iterations = iterations
+        self.sigma = float(sigma)
+        self.n = 0
+        self.h = C.c_void_p(self.L.ref_2v_create(_p(K), self.sigma, iterations))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_2v_destroy(self.h)
+            self.h = None
+
+    def reconstruct(self, xy1, xy2, matches12):
+        """Reconstruct(vKeys1, vKeys2, vMatches12, ...): matches12[i] = index into xy2 or -1.  Needs >= 8 matches (the
+        reference draws 8 of them per RANSAC set without checking).  Returns its bool."""
+        xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+        m = np.ascontiguousarray(matches12, np.int32)
+        assert len(m) == len(xy1) and (m >= 0).sum() >= 8
+        n = C.c_int(0)
+        ok = self.L.ref_2v_reconstruct(self.h, _p(xy1), len(xy1), _p(xy2), len(xy2), _p(m), C.byref(n))
+        self.n = n.value
+        return bool(ok)
+
+    def matches(self):
+        """(xy1, xy2, sets): the matched points in mvMatches12 order and the 8-point sets of every iteration."""
+        a = np.zeros((self.n, 2), np.float32); b = np.zeros((self.n, 2), np.float32)
+        s = np.zeros((self.iterations, 8), np.int32)
+        self.L.ref_2v_get_matches(self.h, _p(a), _p(b), _p(s))
+        return a, b, s
+
+    def check_homography(self, H21, H12, sigma=None):
+        H21 = np.ascontiguousarray(H21, np.float32).reshape(9); H12 = np.ascontiguousarray(H12, np.float32).reshape(9)
+        inl = np.zeros(max(1, self.n), np.uint8)
+        s = self.L.ref_2v_check_h(self.h, _p(H21), _p(H12), self.sigma if sigma is None else sigma, _p(inl))
+        return np.float32(s), inl[:self.n]
+
+    def check_fundamental(self, F21, sigma=None):
+        F21 = np.ascontiguousarray(F21, np.float32).reshape(9)
+        inl = np.zeros(max(1, self.n), np.uint8)
+        s = self.L.ref_2v_check_f(self.h, _p(F21), self.sigma if sigma is None else sigma, _p(inl))
+        return np.float32(s), inl[:self.n]
+
+    def hypotheses(self):
+        """(H21, H12, F21), iterations x 9 each: T2inv*Hn*T1, its inverse and T2t*Fn*T1 of every RANSAC iteration, from the
+        reference's own Normalize / ComputeH21 / ComputeF21."""
+        H21 = np.zeros((self.iterations, 9), np.float32); H12 = np.zeros_like(H21); F21 = np.zeros_like(H21)
+        self.L.ref_2v_hypotheses(self.h, _p(H21), _p(H12), _p(F21))
+        return H21, H12, F21
+
+    def find_homography(self):
+        """FindHomography: (score, inliers, H21) its selection loop keeps."""
+        inl = np.zeros(max(1, self.n), np.uint8); sc = np.zeros(1, np.float32); H = np.zeros(9, np.float32)
+        self.L.ref_2v_find_h(self.h, _p(inl), _p(sc), _p(H))
+        return sc[0], inl[:self.n], H
+
+    def find_fundamental(self):
+        inl = np.zeros(max(1, self.n), np.uint8); sc = np.zeros(1, np.float32); F = np.zeros(9, np.float32)
+        self.L.ref_2v_find_f(self.h, _p(inl), _p(sc), _p(F))
+        return sc[0], inl[:self.n], F

@@ -13,6 +13,8 @@
 #include <iostream>
 #include <list>
 #include <map>
+#include <sstream>
+#include <utility>
 #include <string>
 #include <cmath>
 #include <cstdint>
@@ -24,6 +26,7 @@
 #define CV_8U 0
 #define CV_8UC1 0
 #define CV_32F 5
+#define CV_64F 6
 
 typedef unsigned char uchar;
 
@@ -77,8 +80,11 @@ class DescriptorMatcher;
 
 enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16, INTER_LINEAR = 1 };
 
-// 8-bit single-channel matrix: reference-counted storage, views share it (cv::Mat semantics the reference relies on:
-// mvImagePyramid[level] = temp(Rect(...)) keeps temp's buffer alive, OP_FtDtOrbSlam.cpp:943)
+// Matrix container: reference-counted storage, views share it (cv::Mat semantics the reference relies on:
+// mvImagePyramid[level] = temp(Rect(...)) keeps temp's buffer alive, OP_FtDtOrbSlam.cpp:943).  CV_8UC1 for the ORB path;
+// CV_32F (with the small dense algebra of core_algebra.hpp) for core/operators/mapInit/OP_2ViewReconstruction.cpp.
+struct Scalar { double v[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : v{a, b, c, d} {} };
+class MatExpr;
 class Mat {
 public:
     int rows = 0, cols = 0;
@@ -87,39 +93,65 @@ public:
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(Size s, int type) { create(s.height, s.width, type); }
-    void create(int r, int c, int /*type*/) {
-        if (data && r == rows && c == cols) return;
-        rows = r; cols = c; step = (size_t)c;
-        buf_ = std::shared_ptr<uchar>(new uchar[(size_t)r * c + 64](), std::default_delete<uchar[]>());
+    Mat(int r, int c, int type, const Scalar& s) { create(r, c, type); fill(s.v[0]); }
+    Mat(const Mat&) = default;
+    Mat& operator=(const Mat&) = default;
+    inline Mat& operator=(const MatExpr& e);      // writes INTO a view of matching size (A.row(0) = ...), else takes the result
+    void create(int r, int c, int type) {
+        if (data && r == rows && c == cols && type == type_) return;
+        rows = r; cols = c; type_ = type; step = (size_t)c * elemSize();
+        buf_ = std::shared_ptr<uchar>(new uchar[(size_t)r * step + 64](), std::default_delete<uchar[]>());
         data = buf_.get();
     }
     void release() { buf_.reset(); data = nullptr; rows = cols = 0; step = 0; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    int type() const { return CV_8UC1; }
-    size_t step1() const { return step; }
-    Mat view(int y, int x, int h, int w) const { Mat m; m.buf_ = buf_; m.data = data + (size_t)y * step + x; m.rows = h; m.cols = w; m.step = step; return m; }
+    int type() const { return type_; }
+    size_t elemSize() const { return type_ == CV_32F ? 4 : type_ == CV_64F ? 8 : 1; }
+    size_t step1() const { return step / elemSize(); }
+    size_t total() const { return (size_t)rows * cols; }
+    bool isContinuous() const { return step == (size_t)cols * elemSize() || rows <= 1; }
+    Mat view(int y, int x, int h, int w) const { Mat m; m.buf_ = buf_; m.type_ = type_; m.data = data + (size_t)y * step + (size_t)x * elemSize(); m.rows = h; m.cols = w; m.step = step; return m; }
     Mat operator()(const Rect& r) const { return view(r.y, r.x, r.height, r.width); }
     Mat rowRange(int a, int b) const { return view(a, 0, b - a, cols); }
     Mat colRange(int a, int b) const { return view(0, a, rows, b - a); }
     Mat row(int i) const { return view(i, 0, 1, cols); }
+    Mat col(int i) const { return view(0, i, rows, 1); }
+    Mat reshape(int /*cn = 0: unchanged*/, int r) const {      // continuous data only (vt.row(8).reshape(0, 3))
+        assert(isContinuous() && r > 0 && total() % (size_t)r == 0);
+        Mat m = *this; m.rows = r; m.cols = (int)(total() / (size_t)r); m.step = (size_t)m.cols * elemSize(); return m;
+    }
     Mat clone() const {
         Mat m;
         if (empty()) return m;
-        m.create(rows, cols, CV_8UC1);
-        for (int y = 0; y < rows; ++y) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols);
+        m.create(rows, cols, type_);
+        copy_rows(m);
         return m;
     }
-    void copyTo(Mat& m) const { m.create(rows, cols, CV_8UC1); copy_rows(m); }
+    void copyTo(Mat& m) const { m.create(rows, cols, type_); copy_rows(m); }
     void copyTo(Mat&& m) const { copy_rows(m); }      // a view of matching size (descriptors.row(i))
     template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <class T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }      // vectors: w.at<float>(2)
+    template <class T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
     template <class T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
     template <class T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
-    static Mat zeros(int r, int c, int type) { Mat m; m.create(r, c, type); for (int y = 0; y < r; ++y) memset(m.ptr(y), 0, (size_t)c); return m; }
+    static Mat zeros(int r, int c, int type) { Mat m; m.create(r, c, type); for (int y = 0; y < r; ++y) memset(m.ptr(y), 0, (size_t)c * m.elemSize()); return m; }
+    // CV_32F algebra (core_algebra.hpp)
+    static inline Mat eye(int r, int c, int type);
+    static inline Mat diag(const Mat& d);
+    inline MatExpr t() const;
+    inline MatExpr inv() const;
+    inline double dot(const Mat& m) const;
+    void fill(double v) {
+        for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) {
+            if (type_ == CV_32F) at<float>(y, x) = (float)v; else if (type_ == CV_64F) at<double>(y, x) = v; else at<uchar>(y, x) = (uchar)v;
+        }
+    }
 private:
-    void copy_rows(Mat& m) const { for (int y = 0; y < rows && y < m.rows; ++y) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)(cols < m.cols ? cols : m.cols)); }
+    void copy_rows(Mat& m) const { for (int y = 0; y < rows && y < m.rows; ++y) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)(cols < m.cols ? cols : m.cols) * elemSize()); }
+    int type_ = CV_8UC1;
     std::shared_ptr<uchar> buf_;
 };
 
@@ -163,6 +195,8 @@ inline void FAST(const Mat& img, std::vector<KeyPoint>& kps, int threshold, bool
 }
 
 }  // namespace cv
+
+#include "core_algebra.hpp"
 
 using cv::cvRound;
 using cv::cvFloor;

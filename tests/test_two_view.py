@@ -1,11 +1,15 @@
 """two-view RANSAC scoring (TwoViewReconstruction::CheckHomography / CheckFundamental,
 core/operators/mapInit/OP_2ViewReconstruction.cpp:447-610) for all hypotheses in one launch.
 
-Oracle: oracle/orb_oracle.cpp restates both functions in plain IEEE float (-ffp-contract=off).  PARITY UNPINNED by the
-reference build: OP_2ViewReconstruction.cpp needs cv::SVDecomp, cv::Mat algebra and DBoW2's DUtils::Random, none of
-which exist in this image, so oracle/_ref cannot contain it; a float64 numpy evaluation of the same formulas bounds the
-oracle instead (CPU test below).  The CUDA path must equal the oracle BIT FOR BIT: scores are sequential float sums in
-match order and the kernel keeps that order."""
+Oracle: oracle/orb_oracle.cpp restates both functions in plain IEEE float (-ffp-contract=off).  It is pinned to the
+REFERENCE'S OWN TwoViewReconstruction, compiled unchanged into oracle/_ref (oracle/Makefile.ref, ref_driver_2v.cpp):
+CheckHomography / CheckFundamental are plain float code that read their matrices with at<float>(), so scores and inlier
+flags must agree bit for bit on any hypothesis — perturbed ground truth or the reference's own ComputeH21 / ComputeF21
+output — and the iteration FindHomography / FindFundamental keep must be the one the `currentScore > score` loop over
+those scores keeps.  (cv::SVD and the cv::Mat algebra of that build are this repo's stand-ins, so the 8-point solvers'
+last bits are NOT pinned to OpenCV; the solvers stay on the host and are not part of the product.)  A float64 numpy
+evaluation of the same formulas bounds the oracle as well.  The CUDA path must equal the oracle AND the reference build
+BIT FOR BIT: scores are sequential float sums in match order and the kernel keeps that order."""
 import numpy as np
 import pytest
 
@@ -70,6 +74,118 @@ def test_oracle_against_float64():
     x1, x2, H21, H12, F21 = scene(2, planar=True)
     s, inl = oo.check_homography(H21[17], H12[17], x1, x2)
     assert inl.sum() > 0.5 * len(x1)
+
+
+def keep_loop(sc):
+    """The reference's `if (currentScore > score)` selection (OP_2ViewReconstruction.cpp:307, :358): first strict maximum
+    above 0; NaN scores are never kept."""
+    b, best = -1, np.float32(0)
+    for i, v in enumerate(sc):
+        if v > best:
+            b, best = i, v
+    return b
+
+
+def ref_session(seed, n, planar, unmatched=0.0, sigma=1.0):
+    """The reference's TwoViewReconstruction after Reconstruct() on a scene: (session, xy1, xy2 in match order)."""
+    from oracle import ref_lib as rl
+    x1, x2, H21, H12, F21 = scene(seed, n, planar)
+    rng = np.random.default_rng(seed + 100)
+    # the second view holds extra, shuffled keypoints; some of the first view's stay unmatched (-1)
+    perm = rng.permutation(n + 7)
+    k2 = np.zeros((n + 7, 2), np.float32)
+    k2[perm[:n]] = x2
+    k2[perm[n:]] = rng.uniform(0, 480, (7, 2))
+    m12 = perm[:n].astype(np.int32)
+    m12[rng.random(n) < unmatched] = -1
+    t = rl.RefTwoView(sigma=sigma)
+    t.reconstruct(x1, k2, m12)
+    a, b, sets = t.matches()
+    keep = m12 >= 0
+    assert t.n == keep.sum() and np.array_equal(a, x1[keep]) and np.array_equal(b, x2[keep])
+    assert all(len(set(r)) == 8 for r in sets.tolist()) and sets.min() >= 0 and sets.max() < t.n
+    return t, a, b, (H21, H12, F21)
+
+
+ref_required = pytest.mark.skipif("not __import__('oracle.ref_lib', fromlist=['x']).available()",
+                                  reason="oracle/_ref is not built and /root/reference is not here")
+
+
+@ref_required
+@pytest.mark.parametrize("seed,n,planar,unmatched,sigma", [(1, 400, False, 0.0, 1.0), (2, 400, True, 0.2, 1.0), (3, 8, False, 0.0, 1.0),
+                                                           (4, 2500, False, 0.1, 1.0), (5, 300, True, 0.0, 2.5), (6, 64, False, 0.5, 0.7)])
+def test_oracle_equals_reference_build(seed, n, planar, unmatched, sigma):
+    """oracle == the reference's own CheckHomography / CheckFundamental, bit for bit, on perturbed ground-truth hypotheses
+    and on the hypotheses of the reference's own 8-point solvers; FindHomography / FindFundamental keep the iteration the
+    selection loop over the oracle's scores keeps."""
+    t, a, b, (H21, H12, F21) = ref_session(seed, n, planar, unmatched, sigma)
+    Hs, His, Fs = t.hypotheses()
+    for tag, (hh, hi, ff) in (("perturbed", (H21, H12, F21)), ("solver", (Hs, His, Fs))):
+        sh = np.zeros(200, np.float32); sf = np.zeros(200, np.float32)
+        for h in range(200):
+            sr, ir = t.check_homography(hh[h], hi[h])
+            sh[h], io = oo.check_homography(hh[h], hi[h], a, b, sigma=sigma)
+            assert sr.tobytes() == sh[h].tobytes() and np.array_equal(ir, io), f"{tag} homography {h}"
+            sr, ir = t.check_fundamental(ff[h])
+            sf[h], io = oo.check_fundamental(ff[h], a, b, sigma=sigma)
+            assert sr.tobytes() == sf[h].tobytes() and np.array_equal(ir, io), f"{tag} fundamental {h}"
+    # sh / sf now hold the solver hypotheses' scores: the reference's RANSAC loops must keep the same iteration
+    for find, sc, hyp, check in ((t.find_homography, sh, Hs, lambda i: oo.check_homography(Hs[i], His[i], a, b, sigma=sigma)),
+                                 (t.find_fundamental, sf, Fs, lambda i: oo.check_fundamental(Fs[i], a, b, sigma=sigma))):
+        score, inl, M = find()
+        i = keep_loop(sc)
+        if i < 0:
+            assert score == 0 and not inl.any()
+        else:
+            assert score.tobytes() == sc[i].tobytes() and np.array_equal(M, hyp[i]) and np.array_equal(inl, check(i)[1])
+
+
+@ref_required
+def test_oracle_equals_reference_build_degenerate():
+    """All-zero and non-finite hypotheses: 0/0 makes every chi-square NaN, `NaN > th` is false, so both sides count every
+    match as an inlier of a NaN score — and the selection loop never keeps it."""
+    t, a, b, _ = ref_session(7, 60, False)
+    Z = np.zeros(9, np.float32)
+    for M in (Z, np.full(9, np.inf, np.float32), np.full(9, np.nan, np.float32)):
+        sr, ir = t.check_homography(M, M); so, io = oo.check_homography(M, M, a, b)
+        assert np.isnan(sr) and np.isnan(so) and np.array_equal(ir, io)
+        sr, ir = t.check_fundamental(M); so, io = oo.check_fundamental(M, a, b)
+        assert np.isnan(sr) and np.isnan(so) and np.array_equal(ir, io)
+    assert keep_loop(np.array([np.nan, 1.0, np.nan, 0.5], np.float32)) == 1
+    # a hypothesis that explains nothing: finite, score 0, no inliers
+    H = np.array([1, 0, 1e4, 0, 1, 1e4, 0, 0, 1], np.float32); Hi = np.array([1, 0, -1e4, 0, 1, -1e4, 0, 0, 1], np.float32)
+    sr, ir = t.check_homography(H, Hi); so, io = oo.check_homography(H, Hi, a, b)
+    assert sr == 0 and so == 0 and not ir.any() and not io.any()
+
+
+@ref_required
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,planar,unmatched,sigma", [(11, 400, False, 0.1, 1.0), (12, 1500, True, 0.0, 1.0), (13, 8, False, 0.0, 1.0),
+                                                           (14, 777, False, 0.3, 2.0)])
+def test_cuda_equals_reference_two_view(seed, n, planar, unmatched, sigma, cuda_required):
+    """CUDA == the reference build with no restatement in between: the device scores every hypothesis of the reference's
+    own solvers; scores, inlier masks and the kept iteration equal CheckHomography / CheckFundamental / FindHomography /
+    FindFundamental of the reference's TwoViewReconstruction (the library travels to the GPU box prebuilt)."""
+    from nav24_b200 import capi
+    t, a, b, _ = ref_session(seed, n, planar, unmatched, sigma)
+    Hs, His, Fs = t.hypotheses()
+    ctx = capi.OrbContext(1000)
+    try:
+        r = ctx.two_view_score(a, b, Hs, His, Fs, sigma=sigma)
+        for h in range(200):
+            sr, ir = t.check_homography(Hs[h], His[h])
+            assert r["score_h"][h].tobytes() == sr.tobytes() and np.array_equal(r["inliers_h"][h], ir), f"homography {h}"
+            sr, ir = t.check_fundamental(Fs[h])
+            assert r["score_f"][h].tobytes() == sr.tobytes() and np.array_equal(r["inliers_f"][h], ir), f"fundamental {h}"
+        for find, best, sc, inl, hyp in ((t.find_homography, r["best_h"], r["score_h"], r["inliers_h"], Hs),
+                                         (t.find_fundamental, r["best_f"], r["score_f"], r["inliers_f"], Fs)):
+            score, mask, M = find()
+            if best < 0:
+                assert score == 0 and not mask.any()
+            else:
+                assert score.tobytes() == sc[best].tobytes() and np.array_equal(mask, inl[best]) and np.array_equal(M, hyp[best])
+    finally:
+        ctx.close()
 
 
 @pytest.mark.gpu
