@@ -26,12 +26,26 @@ def build(force=False):
                                                 "_build/liborb_oracle.so")]
         stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
         if force or stale:
-            subprocess.check_call(["make", "-C", _HERE, "-f", "Makefile.ref", "-B", "REF=" + REF_ROOT], stdout=subprocess.DEVNULL)
+            subprocess.check_call(["make", "-C", _HERE, "-f", "Makefile.ref", "-B", "REF=" + REF_ROOT, "_ref/libnav24_ref.so"],
+                                  stdout=subprocess.DEVNULL)
     return _SO if os.path.exists(_SO) else None
 
 
 def available():
     return build() is not None
+
+
+BINDING_BIN = os.path.join(_HERE, "_ref", "test_ref_binding")
+
+
+def build_binding_test():
+    """tests/cpp/test_ref_binding.cpp: the nav24-side binding (nav24_b200/host/ref_binding) compiled against the reference's
+    own headers, linked to the reference's own classes and to libnav24orb.so.  Built where the reference tree exists;
+    elsewhere the prebuilt binary is used.  Returns its path or None."""
+    if build() is not None and os.path.exists(os.path.join(REF_ROOT, "core", "operators", "objDetection", "OP_FtDt.hpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-f", "Makefile.ref", "REF=" + REF_ROOT, "_ref/test_ref_binding"],
+                              stdout=subprocess.DEVNULL)
+    return BINDING_BIN if os.path.exists(BINDING_BIN) else None
 
 
 _lib = None
