@@ -42,7 +42,8 @@ def build_binding_test():
     """tests/cpp/test_ref_binding.cpp: the nav24-side binding (nav24_b200/host/ref_binding) compiled against the reference's
     own headers, linked to the reference's own classes and to libnav24orb.so.  Built where the reference tree exists;
     elsewhere the prebuilt binary is used.  Returns its path or None."""
-    if build() is not None and os.path.exists(os.path.join(REF_ROOT, "core", "operators", "objDetection", "OP_FtDt.hpp")):
+    product = os.path.join(os.path.dirname(_HERE), "nav24_b200", "libnav24orb.so")      # linked, never loaded by this module
+    if build() is not None and os.path.exists(product) and os.path.exists(os.path.join(REF_ROOT, "core", "operators", "objDetection", "OP_FtDt.hpp")):
         subprocess.check_call(["make", "-C", _HERE, "-f", "Makefile.ref", "REF=" + REF_ROOT, "_ref/test_ref_binding"],
                               stdout=subprocess.DEVNULL)
     return BINDING_BIN if os.path.exists(BINDING_BIN) else None

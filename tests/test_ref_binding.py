@@ -46,7 +46,8 @@ def test_binding_compiles_against_reference_headers_and_refuses_without_gpu(tmp_
 @needs_binary
 @pytest.mark.gpu
 @pytest.mark.parametrize("H,W,nf,scale,n", [(480, 752, 1000, None, 4), (376, 1241, 2000, None, 4), (376, 1241, 2000, 5.0, 3),
-                                            (480, 640, 1000, 0.2, 3)])
+                                            (480, 640, 1000, 0.2, 3),
+                                            (480, 752, 1000, None, 100)])      # BASELINE.json configs[0]: a 100-frame EuRoC-shaped mono sequence, match(first, t)
 def test_binding_equals_reference_classes(tmp_path, cuda_required, H, W, nf, scale, n):
     write_input(tmp_path / "in.raw", sequence(H, W, 23, n, step=(5, 2)), nf)
     args = [ref_lib.BINDING_BIN, str(tmp_path / "in.raw")] + ([str(scale)] if scale else [])
