@@ -141,6 +141,41 @@ def test_oracle_equals_reference_build(seed, n, planar, unmatched, sigma):
 
 
 @ref_required
+def test_reference_build_solvers_are_sane():
+    """The stand-in cv::SVD / cv::Mat algebra of the reference build (oracle/ref_shim/opencv2/core_algebra.hpp) is not part
+    of what is pinned, but the hypotheses it produces must be real ones: on exact correspondences of a plane the
+    reference's FindHomography explains every match, on exact correspondences of a 3-D scene its FindFundamental does,
+    and H21 * H12 of every iteration is the identity."""
+    from oracle import ref_lib as rl
+    rng = np.random.default_rng(3)
+    K = np.array([[458.0, 0, 367.0], [0, 457.0, 248.0], [0, 0, 1]])
+    ang = 0.05
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]); tv = np.array([0.3, 0.02, 0.05])
+    for planar in (True, False):
+        n = 300
+        X = np.c_[rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), (np.full(n, 5.0) if planar else rng.uniform(3, 9, n))]
+        x1 = (K @ X.T).T; x1 = (x1[:, :2] / x1[:, 2:]).astype(np.float32)
+        x2 = (K @ (R @ X.T + tv[:, None])).T; x2 = (x2[:, :2] / x2[:, 2:]).astype(np.float32)
+        t = rl.RefTwoView()
+        t.reconstruct(x1, x2, np.arange(n, dtype=np.int32))
+        Hs, His, Fs = t.hypotheses()
+        if planar:
+            score, inl, H = t.find_homography()
+            assert inl.all() and score > 0.95 * 2 * 5.991 * n
+            P = np.einsum("nij,njk->nik", Hs.reshape(-1, 3, 3).astype(np.float64), His.reshape(-1, 3, 3).astype(np.float64))
+            assert np.abs(P - np.eye(3)).max() < 1e-3
+            p = (H.reshape(3, 3).astype(np.float64) @ np.c_[x1, np.ones(n)].T).T
+            assert np.abs(p[:, :2] / p[:, 2:] - x2).max() < 0.05                 # pixels
+        else:
+            score, inl, F = t.find_fundamental()
+            assert inl.all() and score > 0.95 * 2 * 5.991 * n
+            F = F.reshape(3, 3).astype(np.float64)
+            assert abs(np.linalg.det(F / np.abs(F).max())) < 1e-6                # rank 2 (:440-444)
+            e = np.einsum("ni,ij,nj->n", np.c_[x2, np.ones(n)], F, np.c_[x1, np.ones(n)])
+            assert np.abs(e).max() / np.abs(F).max() < 0.5
+
+
+@ref_required
 def test_oracle_equals_reference_build_degenerate():
     """All-zero and non-finite hypotheses: 0/0 makes every chi-square NaN, `NaN > th` is false, so both sides count every
     match as an inlier of a NaN score — and the selection loop never keeps it."""
