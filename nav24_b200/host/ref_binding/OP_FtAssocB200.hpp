@@ -7,6 +7,7 @@
 #ifndef NAV24_OP_FTASSOCB200_HPP
 #define NAV24_OP_FTASSOCB200_HPP
 
+#include <algorithm>
 #include <cassert>
 #include <cstring>
 #include <memory>
@@ -47,27 +48,30 @@ public:
         return vnMatches12;
     }
 
-    // the reference's bodies (OP_FtAssocOrbSlam.cpp:225-260): both only call matchV
+    // The two wrappers keep FtAssocOrbSlam's contracts (OP_FtAssocOrbSlam.cpp:225-260); both are matchV plus bookkeeping.
+    // match(f1, f2, tracks): every accepted pair goes to the track container; returns the number of pairs (0 when matchV
+    // had nothing to say).
     int match(const FramePtr& pFrame1, const FramePtr& pFrame2, OB::FtTracksPtr& pTracks) override {
-        std::vector<int> vMatches12 = this->matchV(pFrame1, pFrame2);
-        auto vpObs1 = pFrame1->getObservations();
-        auto vpObs2 = pFrame2->getObservations();
-        if (vMatches12.empty()) return 0;
-        assert(vMatches12.size() == vpObs1.size());
-        int cnt = 0;
-        for (size_t i = 0; i < vMatches12.size(); i++) {
-            const int idx2 = vMatches12[i];
-            if (idx2 >= 0) { pTracks->addMatch(vpObs1[i], vpObs2[(size_t)idx2]); cnt++; }
+        const std::vector<int> m12 = matchV(pFrame1, pFrame2);
+        if (m12.empty()) return 0;
+        const auto& obs1 = pFrame1->getObservations();
+        const auto& obs2 = pFrame2->getObservations();
+        assert(m12.size() == obs1.size());
+        int nPairs = 0;
+        for (size_t i1 = 0; i1 < m12.size(); ++i1) {
+            if (m12[i1] < 0) continue;
+            pTracks->addMatch(obs1[i1], obs2[(size_t)m12[i1]]);
+            ++nPairs;
         }
-        return cnt;
+        return nPairs;
     }
 
+    // match(f1, f2): the result is left on frame 2 as a MatchedObs that refers (weakly) to frame 1.
     void match(const FramePtr& pFrame1, const FramePtr& pFrame2) override {
-        std::vector<int> matches12 = this->matchV(pFrame1, pFrame2);
-        int nMatches = 0;
-        for (const auto& m : matches12) if (m >= 0) nMatches++;
-        auto pMatchedObs = std::make_shared<OB::MatchedObs>(pFrame1, matches12, nMatches);
-        if (auto p = std::dynamic_pointer_cast<FrameImgMono>(pFrame2)) p->setMatches(pMatchedObs);
+        const std::vector<int> m12 = matchV(pFrame1, pFrame2);
+        const int nPairs = (int)std::count_if(m12.begin(), m12.end(), [](int v) { return v >= 0; });
+        if (auto pImgFrame2 = std::dynamic_pointer_cast<FrameImgMono>(pFrame2))
+            pImgFrame2->setMatches(std::make_shared<OB::MatchedObs>(pFrame1, m12, nPairs));
     }
 
 protected:
