@@ -6,55 +6,14 @@
 // FindFundamental (:266-365).  What it does NOT pin: the 8-point solvers' last bits; cv::SVD / cv::Mat algebra are this
 // repo's stand-ins (oracle/ref_shim/opencv2/core_algebra.hpp), so the hypothesis matrices are test INPUTS produced by
 // the reference's ComputeH21 / ComputeF21 over that algebra, not OpenCV-exact values.
-// The members involved are private; they are reached through explicit template instantiation (which may name private
-// members), so the reference header is included as it is.  Nothing in the product links, loads or imports this file.
+// The members involved are private; they are reached through explicit template instantiation (ref_access_2v.hpp), so the
+// reference header is included as it is.  Nothing in the product links, loads or imports this file.
 #include <cstdint>
 #include <cstring>
 #include <memory>
 #include <vector>
 
-#include "OP_2ViewReconstruction.hpp"
-
-using NAV24::OP::TwoViewReconstruction;
-
-namespace {
-
-template <class Tag, typename Tag::type M> struct Rob { friend typename Tag::type get(Tag) { return M; } };
-#define ROB(tag, ...) struct tag { typedef __VA_ARGS__; friend type get(tag); }
-
-typedef std::vector<bool> VB;
-typedef std::vector<cv::KeyPoint> VK;
-typedef std::vector<cv::Point2f> VP;
-typedef std::vector<std::pair<int, int>> VM;
-typedef std::vector<std::vector<size_t>> VS;
-
-ROB(CheckH, float (TwoViewReconstruction::*type)(const cv::Mat&, const cv::Mat&, VB&, float));
-ROB(CheckF, float (TwoViewReconstruction::*type)(const cv::Mat&, VB&, float));
-ROB(FindH, void (TwoViewReconstruction::*type)(VB&, float&, cv::Mat&));
-ROB(FindF, void (TwoViewReconstruction::*type)(VB&, float&, cv::Mat&));
-ROB(CompH, cv::Mat (TwoViewReconstruction::*type)(const VP&, const VP&));
-ROB(CompF, cv::Mat (TwoViewReconstruction::*type)(const VP&, const VP&));
-ROB(Norm, void (TwoViewReconstruction::*type)(const VK&, VP&, cv::Mat&));
-ROB(Keys1, VK TwoViewReconstruction::*type);
-ROB(Keys2, VK TwoViewReconstruction::*type);
-ROB(Matches, VM TwoViewReconstruction::*type);
-ROB(Sets, VS TwoViewReconstruction::*type);
-ROB(MaxIt, int TwoViewReconstruction::*type);
-ROB(Sigma, float TwoViewReconstruction::*type);
-}  // namespace
-template struct Rob<CheckH, &TwoViewReconstruction::CheckHomography>;
-template struct Rob<CheckF, &TwoViewReconstruction::CheckFundamental>;
-template struct Rob<FindH, &TwoViewReconstruction::FindHomography>;
-template struct Rob<FindF, &TwoViewReconstruction::FindFundamental>;
-template struct Rob<CompH, &TwoViewReconstruction::ComputeH21>;
-template struct Rob<CompF, &TwoViewReconstruction::ComputeF21>;
-template struct Rob<Norm, &TwoViewReconstruction::Normalize>;
-template struct Rob<Keys1, &TwoViewReconstruction::mvKeys1>;
-template struct Rob<Keys2, &TwoViewReconstruction::mvKeys2>;
-template struct Rob<Matches, &TwoViewReconstruction::mvMatches12>;
-template struct Rob<Sets, &TwoViewReconstruction::mvSets>;
-template struct Rob<MaxIt, &TwoViewReconstruction::mMaxIterations>;
-template struct Rob<Sigma, &TwoViewReconstruction::mSigma>;
+#include "ref_access_2v.hpp"
 
 namespace {
 

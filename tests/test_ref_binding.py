@@ -61,3 +61,51 @@ def test_binding_equals_reference_classes(tmp_path, cuda_required, H, W, nf, sca
     assert d["match_mismatches"] == 0 and d["match_mismatches_vs_all_reference"] == 0 and d["stored_matchedobs_mismatches"] == 0
     assert d["edge_cases_ok"] is True
     assert d["keypoints"] > 0.8 * n * d["num_features"] and d["matches"] > 20 * (n - 1)
+
+
+def write_two_view_input(path, seed, n, planar, unmatched):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_two_view import scene
+    x1, x2, _, _, _ = scene(seed, n, planar)
+    rng = np.random.default_rng(seed + 7)
+    perm = rng.permutation(n + 5)
+    k2 = np.zeros((n + 5, 2), np.float32)
+    k2[perm[:n]] = x2
+    k2[perm[n:]] = rng.uniform(0, 480, (5, 2))
+    m12 = perm[:n].astype(np.int32)
+    m12[rng.random(n) < unmatched] = -1
+    with open(path, "wb") as f:
+        f.write(np.array([n, n + 5], np.int32).tobytes()); f.write(x1.tobytes()); f.write(k2.tobytes()); f.write(m12.tobytes())
+    return int((m12 >= 0).sum())
+
+
+@needs_binary
+def test_two_view_binding_refuses_without_gpu(tmp_path):
+    try:
+        import torch
+        has = torch.cuda.is_available()
+    except Exception:
+        has = False
+    if has:
+        pytest.skip("CUDA device present; covered by the gpu test")
+    write_two_view_input(tmp_path / "tv.raw", 1, 100, False, 0.0)
+    r = subprocess.run([ref_lib.BINDING_BIN, "--two-view", str(tmp_path / "tv.raw")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr[-300:])
+
+
+@needs_binary
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,planar,unmatched", [(31, 400, False, 0.1), (32, 1200, True, 0.0), (33, 9, False, 0.0), (34, 250, True, 0.4)])
+def test_two_view_binding_equals_reference_class(tmp_path, cuda_required, seed, n, planar, unmatched):
+    """TwoViewScoringB200.hpp in the reference's own types: all 2 x 200 hypotheses of the reference's own solvers scored on
+    the device == its CheckHomography / CheckFundamental, and the (score, inliers, matrix) handed back in place of
+    FindHomography / FindFundamental == what those return, in one process."""
+    nm = write_two_view_input(tmp_path / "tv.raw", seed, n, planar, unmatched)
+    r = subprocess.run([ref_lib.BINDING_BIN, "--two-view", str(tmp_path / "tv.raw")], capture_output=True, text=True, timeout=300)
+    assert r.stdout.strip(), r.stderr[-500:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0, d
+    assert d["matches"] == nm and d["iterations"] == 200
+    assert d["score_mismatches"] == 0 and d["inlier_mismatches"] == 0 and d["kept_result_mismatches"] == 0
+    assert d["best_f"] >= 0 and d["score_f"] > 0
