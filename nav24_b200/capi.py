@@ -118,6 +118,8 @@ def lib():
                                             C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, vp]
     L.nav24_two_view_score.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp,
                                        vp, vp, ip, ip]
+    L.nav24_two_view_score_kept.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp,
+                                       vp, vp, ip, ip]
     L.nav24_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.nav24_host_free.argtypes = [vp]
     L.nav24_device_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -399,6 +401,25 @@ class OrbContext:
         self._check(self.L.nav24_two_view_score(self.h, _p(xy1), _p(xy2), n, _p(H21), _p(H12), _p(F21), nh, sigma, th_h, th_f,
                                                 th_score, _p(sh), _p(sf), _p(ih), _p(i_f), C.byref(bh), C.byref(bf)))
         return {"score_h": sh, "score_f": sf, "inliers_h": ih, "inliers_f": i_f, "best_h": bh.value, "best_f": bf.value}
+
+    def two_view_score_kept(self, xy1, xy2, H21=None, H12=None, F21=None, sigma=1.0, th_h=5.991, th_f=3.841, th_score=5.991):
+        """What FindHomography / FindFundamental hand back: all scores, the kept iteration and only ITS inlier mask.
+        Returns dict(score_h, score_f, kept_inliers_h, kept_inliers_f, best_h, best_f)."""
+        xy1 = np.ascontiguousarray(xy1, np.float32).reshape(-1, 2); xy2 = np.ascontiguousarray(xy2, np.float32).reshape(-1, 2)
+        n = len(xy1)
+        H21 = None if H21 is None else np.ascontiguousarray(H21, np.float32).reshape(-1, 9)
+        H12 = None if H12 is None else np.ascontiguousarray(H12, np.float32).reshape(-1, 9)
+        F21 = None if F21 is None else np.ascontiguousarray(F21, np.float32).reshape(-1, 9)
+        nh = len(H21) if H21 is not None else len(F21)
+        sh = np.zeros(nh, np.float32) if H21 is not None else None
+        sf = np.zeros(nh, np.float32) if F21 is not None else None
+        kh = np.full(max(n, 1), 255, np.uint8) if H21 is not None else None      # (255: the call must overwrite every entry)
+        kf = np.full(max(n, 1), 255, np.uint8) if F21 is not None else None
+        bh, bf = C.c_int(-1), C.c_int(-1)
+        self._check(self.L.nav24_two_view_score_kept(self.h, _p(xy1), _p(xy2), n, _p(H21), _p(H12), _p(F21), nh, sigma, th_h, th_f,
+                                                     th_score, _p(sh), _p(sf), _p(kh), _p(kf), C.byref(bh), C.byref(bf)))
+        return {"score_h": sh, "score_f": sf, "kept_inliers_h": None if kh is None else kh[:n], "kept_inliers_f": None if kf is None else kf[:n],
+                "best_h": bh.value, "best_f": bf.value}
 
     def debug_sort(self, keys):
         keys = np.ascontiguousarray(keys, np.uint32)

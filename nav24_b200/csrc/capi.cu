@@ -1672,9 +1672,11 @@ int nav24_ingest_detect(nav24_ingest* ring, int first_slot, int n_frames, nav24_
 // ---- two-view RANSAC scoring -------------------------------------------------------------------------
 extern "C" {
 
-int nav24_two_view_score(nav24_orb* ctx, const float* xy1, const float* xy2, int n_matches, const float* H21, const float* H12,
-                         const float* F21, int n_hyp, float sigma, float th_h, float th_f, float th_score, float* score_h,
-                         float* score_f, uint8_t* inliers_h, uint8_t* inliers_f, int* best_h, int* best_f) {
+// Shared body of nav24_two_view_score / nav24_two_view_score_kept.  all_h / all_f: n_hyp x n_matches masks of every iteration
+// (may be NULL); kept_h / kept_f: n_matches bytes, the mask of the kept iteration only (may be NULL).
+static int two_view_run(nav24_orb* ctx, const float* xy1, const float* xy2, int n_matches, const float* H21, const float* H12,
+                        const float* F21, int n_hyp, float sigma, float th_h, float th_f, float th_score, float* score_h,
+                        float* score_f, uint8_t* all_h, uint8_t* all_f, uint8_t* kept_h, uint8_t* kept_f, int* best_h, int* best_f) {
     return guarded(ctx, [&]() -> int {
         if (!ctx) return NAV24_E_BADARG;
         if (n_matches < 0 || n_hyp < 0 || !(sigma > 0.f) || (n_matches > 0 && (!xy1 || !xy2)) || (H21 && !H12) || (H21 && !score_h) ||
@@ -1682,6 +1684,8 @@ int nav24_two_view_score(nav24_orb* ctx, const float* xy1, const float* xy2, int
             return ctx->fail(NAV24_E_BADARG, "bad two-view scoring argument");
         if (best_h) *best_h = -1;
         if (best_f) *best_f = -1;
+        if (kept_h && n_matches > 0) memset(kept_h, 0, (size_t)n_matches);
+        if (kept_f && n_matches > 0) memset(kept_f, 0, (size_t)n_matches);
         if (n_hyp == 0) return NAV24_OK;
         cudaSetDevice(ctx->device);
         const size_t nb = (size_t)std::max(n_matches, 1), hb = (size_t)n_hyp;
@@ -1703,26 +1707,47 @@ int nav24_two_view_score(nav24_orb* ctx, const float* xy1, const float* xy2, int
             CK(cudaMemcpyAsync(dH12, H12, hb * 36, cudaMemcpyHostToDevice, s));
         }
         if (F21) CK(cudaMemcpyAsync(dF21, F21, hb * 36, cudaMemcpyHostToDevice, s));
+        const bool maskH = H21 && (all_h || kept_h), maskF = F21 && (all_f || kept_f);
         if (n_matches > 0) {
             ctx->launches += launch_two_view_score(dXy1, dXy2, n_matches, H21 ? dH21 : nullptr, H21 ? dH12 : nullptr, F21 ? dF21 : nullptr,
-                                                   n_hyp, sigma, th_h, th_f, th_score, dSH, dSF, inliers_h ? dIH : nullptr,
-                                                   inliers_f ? dIF : nullptr, s);
+                                                   n_hyp, sigma, th_h, th_f, th_score, dSH, dSF, maskH ? dIH : nullptr,
+                                                   maskF ? dIF : nullptr, s);
             CK(cudaGetLastError());
         } else {
             CK(cudaMemsetAsync(dSH, 0, 2 * hb * 4, s));      // no matches: every score is 0 (the reference's loops do not run)
         }
         if (H21) CK(cudaMemcpyAsync(score_h, dSH, hb * 4, cudaMemcpyDeviceToHost, s));
         if (F21) CK(cudaMemcpyAsync(score_f, dSF, hb * 4, cudaMemcpyDeviceToHost, s));
-        if (H21 && inliers_h && n_matches > 0) CK(cudaMemcpyAsync(inliers_h, dIH, hb * n_matches, cudaMemcpyDeviceToHost, s));
-        if (F21 && inliers_f && n_matches > 0) CK(cudaMemcpyAsync(inliers_f, dIF, hb * n_matches, cudaMemcpyDeviceToHost, s));
+        if (H21 && all_h && n_matches > 0) CK(cudaMemcpyAsync(all_h, dIH, hb * n_matches, cudaMemcpyDeviceToHost, s));
+        if (F21 && all_f && n_matches > 0) CK(cudaMemcpyAsync(all_f, dIF, hb * n_matches, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         // `if (currentScore > score) keep` over the iterations (:307-312, :358-363): the first hypothesis with the highest
         // score, and none when no score exceeds the initial 0
         auto pick = [&](const float* sc) { int b = -1; float best = 0.f; for (int i = 0; i < n_hyp; ++i) if (sc[i] > best) { best = sc[i]; b = i; } return b; };
-        if (H21 && best_h) *best_h = pick(score_h);
-        if (F21 && best_f) *best_f = pick(score_f);
+        const int bh = H21 ? pick(score_h) : -1, bf = F21 ? pick(score_f) : -1;
+        if (best_h) *best_h = bh;
+        if (best_f) *best_f = bf;
+        // the kept iteration's mask only: n_matches bytes per model instead of n_hyp x n_matches
+        bool more = false;
+        if (kept_h && bh >= 0 && n_matches > 0) { CK(cudaMemcpyAsync(kept_h, dIH + (size_t)bh * n_matches, (size_t)n_matches, cudaMemcpyDeviceToHost, s)); more = true; }
+        if (kept_f && bf >= 0 && n_matches > 0) { CK(cudaMemcpyAsync(kept_f, dIF + (size_t)bf * n_matches, (size_t)n_matches, cudaMemcpyDeviceToHost, s)); more = true; }
+        if (more) CK(cudaStreamSynchronize(s));
         return NAV24_OK;
     });
+}
+
+int nav24_two_view_score(nav24_orb* ctx, const float* xy1, const float* xy2, int n_matches, const float* H21, const float* H12,
+                         const float* F21, int n_hyp, float sigma, float th_h, float th_f, float th_score, float* score_h,
+                         float* score_f, uint8_t* inliers_h, uint8_t* inliers_f, int* best_h, int* best_f) {
+    return two_view_run(ctx, xy1, xy2, n_matches, H21, H12, F21, n_hyp, sigma, th_h, th_f, th_score, score_h, score_f, inliers_h,
+                        inliers_f, nullptr, nullptr, best_h, best_f);
+}
+
+int nav24_two_view_score_kept(nav24_orb* ctx, const float* xy1, const float* xy2, int n_matches, const float* H21, const float* H12,
+                              const float* F21, int n_hyp, float sigma, float th_h, float th_f, float th_score, float* score_h,
+                              float* score_f, uint8_t* kept_inliers_h, uint8_t* kept_inliers_f, int* best_h, int* best_f) {
+    return two_view_run(ctx, xy1, xy2, n_matches, H21, H12, F21, n_hyp, sigma, th_h, th_f, th_score, score_h, score_f, nullptr,
+                        nullptr, kept_inliers_h, kept_inliers_f, best_h, best_f);
 }
 
 }  // extern "C"

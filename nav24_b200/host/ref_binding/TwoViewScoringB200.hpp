@@ -21,9 +21,10 @@ namespace NAV24::OP {
 
 struct TwoViewScoresB200 {
     std::vector<float> SH, SF;                  // per iteration: CheckHomography / CheckFundamental scores
-    std::vector<uint8_t> inliersH, inliersF;    // per iteration x match: vbCurrentInliers
+    std::vector<uint8_t> inliersH, inliersF;    // allMasks: per iteration x match (vbCurrentInliers); else the kept iteration's only
     int bestH = -1, bestF = -1;                 // the iteration the reference's selection loop keeps (-1: no score above 0)
     int nMatches = 0;
+    bool allMasks = false;
 
     // what FindHomography / FindFundamental return through their reference parameters
     void keptHomography(const std::vector<cv::Mat>& H21s, std::vector<bool>& vbMatchesInliers, float& score, cv::Mat& H21) const {
@@ -41,16 +42,19 @@ private:
         if (best < 0) return;
         score = S[(size_t)best];
         M = Ms[(size_t)best].clone();                                  // :309, :360
-        for (int i = 0; i < nMatches; ++i) vbMatchesInliers[(size_t)i] = inl[(size_t)best * nMatches + i] != 0;
+        const size_t row = allMasks ? (size_t)best * (size_t)nMatches : 0;
+        for (int i = 0; i < nMatches; ++i) vbMatchesInliers[(size_t)i] = inl[row + (size_t)i] != 0;
     }
 };
 
 // H21s[i] / H12s[i] = T2inv*Hn*T1 and its inverse (:302-303), F21s[i] = T2t*Fn*T1 (:354): CV_32F 3 x 3, one per iteration.
-// Either model may be left out (empty vectors).  Returns NAV24_OK or a NAV24_E_* code (nav24_last_error_string explains).
+// Either model may be left out (empty vectors).  allMasks = false (the default) brings back only the kept iteration's inlier
+// mask, which is all FindHomography / FindFundamental return (nav24_two_view_score_kept: n_matches bytes per model over PCIe
+// instead of iterations x n_matches); true brings back every iteration's mask.  Returns NAV24_OK or a NAV24_E_* code.
 inline int scoreHypothesesB200(nav24_orb* ctx, const std::vector<cv::KeyPoint>& vKeys1, const std::vector<cv::KeyPoint>& vKeys2,
                                const std::vector<std::pair<int, int>>& vMatches12, const std::vector<cv::Mat>& H21s,
                                const std::vector<cv::Mat>& H12s, const std::vector<cv::Mat>& F21s, float sigma,
-                               const Params2VR& prm, TwoViewScoresB200& out) {
+                               const Params2VR& prm, TwoViewScoresB200& out, bool allMasks = false) {
     const int N = (int)vMatches12.size();
     const int nHyp = (int)(H21s.empty() ? F21s.size() : H21s.size());
     std::vector<float> xy1((size_t)2 * N), xy2((size_t)2 * N);
@@ -69,9 +73,11 @@ inline int scoreHypothesesB200(nav24_orb* ctx, const std::vector<cv::KeyPoint>& 
     const std::vector<float> h21 = flatten(H21s), h12 = flatten(H12s), f21 = flatten(F21s);
     out = TwoViewScoresB200();
     out.nMatches = N;
-    if (!H21s.empty()) { out.SH.resize((size_t)nHyp); out.inliersH.resize((size_t)nHyp * N); }
-    if (!F21s.empty()) { out.SF.resize((size_t)nHyp); out.inliersF.resize((size_t)nHyp * N); }
-    return nav24_two_view_score(ctx, xy1.data(), xy2.data(), N, h21.empty() ? nullptr : h21.data(), h12.empty() ? nullptr : h12.data(),
+    out.allMasks = allMasks;
+    const size_t rows = allMasks ? (size_t)nHyp : 1;
+    if (!H21s.empty()) { out.SH.resize((size_t)nHyp); out.inliersH.resize(rows * (size_t)N); }
+    if (!F21s.empty()) { out.SF.resize((size_t)nHyp); out.inliersF.resize(rows * (size_t)N); }
+    return (allMasks ? nav24_two_view_score : nav24_two_view_score_kept)(ctx, xy1.data(), xy2.data(), N, h21.empty() ? nullptr : h21.data(), h12.empty() ? nullptr : h12.data(),
                                 f21.empty() ? nullptr : f21.data(), nHyp, sigma, prm.mThChiSqScore, prm.mThChiSqF, prm.mThChiSqScore,
                                 out.SH.empty() ? nullptr : out.SH.data(), out.SF.empty() ? nullptr : out.SF.data(),
                                 out.inliersH.empty() ? nullptr : out.inliersH.data(), out.inliersF.empty() ? nullptr : out.inliersF.data(),

@@ -89,8 +89,9 @@ int two_view_main(const char* path) {
         cv::Mat Fn = (tvr.*get(CompF()))(a, b);
         F21s.push_back(cv::Mat(T2t * Fn * T1));
     }
-    OP::TwoViewScoresB200 sc;
-    const int rc = OP::scoreHypothesesB200(det->handle(), tvr.*get(Keys1()), tvr.*get(Keys2()), m, H21s, H12s, F21s, sigma, tvr.mParams2VR, sc);
+    OP::TwoViewScoresB200 sc, kept;      // sc: every iteration's mask (for the per-hypothesis check); kept: the default call
+    int rc = OP::scoreHypothesesB200(det->handle(), tvr.*get(Keys1()), tvr.*get(Keys2()), m, H21s, H12s, F21s, sigma, tvr.mParams2VR, sc, true);
+    if (rc == NAV24_OK) rc = OP::scoreHypothesesB200(det->handle(), tvr.*get(Keys1()), tvr.*get(Keys2()), m, H21s, H12s, F21s, sigma, tvr.mParams2VR, kept);
     if (rc != NAV24_OK) { printf("{\"error\": \"nav24_two_view_score: %d %s\"}\n", rc, nav24_last_error_string(det->handle())); return 1; }
 
     const int N = (int)m.size();
@@ -105,12 +106,13 @@ int two_view_main(const char* path) {
         for (int i = 0; i < N; ++i) inlBad += (inl[(size_t)i] ? 1 : 0) != sc.inliersF[(size_t)it * N + i];
     }
     // what FindHomography / FindFundamental return vs what the binding hands back in their place
-    for (int model = 0; model < 2; ++model) {
+    for (int model = 0; model < 4; ++model) {      // both result forms (all masks / kept mask only) x both models
         VB inlR, inlB;
         float sR = -1.f, sB = -1.f;
         cv::Mat MR, MB;
-        if (model == 0) { (tvr.*get(FindH()))(inlR, sR, MR); sc.keptHomography(H21s, inlB, sB, MB); }
-        else { (tvr.*get(FindF()))(inlR, sR, MR); sc.keptFundamental(F21s, inlB, sB, MB); }
+        const OP::TwoViewScoresB200& res = model < 2 ? sc : kept;
+        if (model % 2 == 0) { (tvr.*get(FindH()))(inlR, sR, MR); res.keptHomography(H21s, inlB, sB, MB); }
+        else { (tvr.*get(FindF()))(inlR, sR, MR); res.keptFundamental(F21s, inlB, sB, MB); }
         bool same = same_bits(sR, sB) && inlR == inlB && MR.empty() == MB.empty();
         if (same && !MR.empty()) for (int i = 0; i < 9; ++i) same = same && same_bits(MR.at<float>(i / 3, i % 3), MB.at<float>(i / 3, i % 3));
         keptBad += !same;

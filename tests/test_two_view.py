@@ -257,6 +257,36 @@ def test_cuda_scores_equal_oracle(seed, n, planar, cuda_required):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,planar", [(21, 400, False), (22, 1500, True), (23, 1, False), (24, 8, False)])
+def test_cuda_kept_only_call_equals_full_call(seed, n, planar, cuda_required):
+    """nav24_two_view_score_kept: the scores of all iterations, the kept iteration and only its inlier mask — identical to
+    the full call's row `best` (and to the oracle), for both models, one model at a time, and when nothing is kept."""
+    from nav24_b200 import capi
+    x1, x2, H21, H12, F21 = scene(seed, n, planar)
+    ctx = capi.OrbContext(1000)
+    try:
+        full = ctx.two_view_score(x1, x2, H21, H12, F21)
+        kept = ctx.two_view_score_kept(x1, x2, H21, H12, F21)
+        assert kept["score_h"].tobytes() == full["score_h"].tobytes() and kept["score_f"].tobytes() == full["score_f"].tobytes()
+        assert kept["best_h"] == full["best_h"] and kept["best_f"] == full["best_f"]
+        for tag, b in (("h", full["best_h"]), ("f", full["best_f"])):
+            want = full["inliers_" + tag][b] if b >= 0 else np.zeros(n, np.uint8)
+            assert np.array_equal(kept["kept_inliers_" + tag], want), tag
+        if full["best_h"] >= 0:
+            assert np.array_equal(kept["kept_inliers_h"], oo.check_homography(H21[full["best_h"]], H12[full["best_h"]], x1, x2)[1])
+        kf = ctx.two_view_score_kept(x1, x2, F21=F21)
+        assert kf["score_h"] is None and kf["best_f"] == full["best_f"] and np.array_equal(kf["kept_inliers_f"], kept["kept_inliers_f"])
+        # hypotheses that explain nothing: no iteration is kept, the masks come back all zero
+        far = np.tile(np.array([1, 0, 1e5, 0, 1, 1e5, 0, 0, 1], np.float32), (3, 1)); farI = np.tile(np.array([1, 0, -1e5, 0, 1, -1e5, 0, 0, 1], np.float32), (3, 1))
+        none = ctx.two_view_score_kept(x1, x2, far, farI, None)
+        assert none["best_h"] == -1 and not none["score_h"].any() and not none["kept_inliers_h"].any()
+        empty = ctx.two_view_score_kept(x1[:0], x2[:0], H21, H12, F21)
+        assert empty["best_h"] == -1 and empty["best_f"] == -1 and len(empty["kept_inliers_h"]) == 0
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
 def test_cuda_two_view_edge_cases(cuda_required):
     from nav24_b200 import capi
     x1, x2, H21, H12, F21 = scene(9, 50)
