@@ -21,7 +21,7 @@ def build(force=False):
     have_ref = os.path.exists(os.path.join(REF_ROOT, "core", "operators", "objDetection", "OP_FtDtOrbSlam.cpp"))
     if have_ref:
         oo.build()
-        src = [os.path.join(_HERE, f) for f in ("ref_driver.cpp", "ref_driver_2v.cpp", "ref_link_stubs.cpp", "Makefile.ref",
+        src = [os.path.join(_HERE, f) for f in ("ref_driver.cpp", "ref_driver_2v.cpp", "ref_access_2v.hpp", "ref_link_stubs.cpp", "Makefile.ref",
                                                 "ref_shim/opencv2/core.hpp", "ref_shim/opencv2/core_algebra.hpp",
                                                 "_build/liborb_oracle.so")]
         stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
