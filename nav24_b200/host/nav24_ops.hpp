@@ -468,6 +468,20 @@ public:
                                     &r.bestH, &r.bestF) == NAV24_OK;
     }
 
+    // What FindHomography / FindFundamental return: r.inliersH / r.inliersF hold ONLY the kept iteration's mask (n bytes each,
+    // all 0 when r.bestH / r.bestF is -1) — nav24_two_view_score_kept, n bytes per model over PCIe instead of nHyp x n.
+    bool scoreKept(const std::vector<float>& xy1, const std::vector<float>& xy2, const std::vector<float>& H21,
+                   const std::vector<float>& H12, const std::vector<float>& F21, Result& r) const {
+        const int n = (int)(xy1.size() / 2), nHyp = (int)(std::max(H21.size(), F21.size()) / 9);
+        r = Result();
+        if (!H21.empty()) { r.scoreH.resize(nHyp); r.inliersH.resize((size_t)n); }
+        if (!F21.empty()) { r.scoreF.resize(nHyp); r.inliersF.resize((size_t)n); }
+        return nav24_two_view_score_kept(mpDet->handle(), xy1.data(), xy2.data(), n, H21.empty() ? nullptr : H21.data(),
+                                         H12.empty() ? nullptr : H12.data(), F21.empty() ? nullptr : F21.data(), nHyp, mSigma,
+                                         mThChiSqScore, mThChiSqF, mThChiSqScore, r.scoreH.data(), r.scoreF.data(), r.inliersH.data(),
+                                         r.inliersF.data(), &r.bestH, &r.bestF) == NAV24_OK;
+    }
+
     float mThChiSqScore = 5.991f, mThChiSqF = 3.841f;      // DEF_TH_CHISQ_SCORE, DEF_TH_CHISQ_F
 
 private:

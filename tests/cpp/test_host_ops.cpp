@@ -167,6 +167,15 @@ int main(int argc, char** argv) {
         std::fwrite(r.scoreH.data(), 4, 2, fo); std::fwrite(r.scoreF.data(), 4, 2, fo);
         std::fwrite(&r.bestH, 4, 1, fo); std::fwrite(&r.bestF, 4, 1, fo);
         std::fwrite(r.inliersH.data(), 1, 2 * (size_t)nm, fo); std::fwrite(r.inliersF.data(), 1, 2 * (size_t)nm, fo);
+        // the kept-only form hands back the same scores, the same kept iteration and exactly its row of the masks
+        OP::TwoViewScorerB200::Result k;
+        int same = scorer.scoreKept(xy1, xy2, H21, H12, F21, k) && k.scoreH == r.scoreH && k.scoreF == r.scoreF && k.bestH == r.bestH &&
+                   k.bestF == r.bestF && (int)k.inliersH.size() == nm && (int)k.inliersF.size() == nm ? 1 : 0;
+        for (int i = 0; i < nm && same; ++i) {
+            if (k.inliersH[(size_t)i] != (r.bestH >= 0 ? r.inliersH[(size_t)r.bestH * nm + i] : 0)) same = 0;
+            if (k.inliersF[(size_t)i] != (r.bestF >= 0 ? r.inliersF[(size_t)r.bestF * nm + i] : 0)) same = 0;
+        }
+        std::fwrite(&same, 4, 1, fo);
     }
     std::fclose(fo);
     return 0;

@@ -114,3 +114,4 @@ def test_host_ops_match_oracle(tmp_path, cuda_required, H, W, nf, scale):
         s, inl = oo.check_fundamental(F21[hyp], xy1, xy2)
         assert np.float32(s).tobytes() == sF[hyp].tobytes() and np.array_equal(inl, inF[hyp])
     assert bestH == int(np.argmax(sH)) and inH[0].sum() > 0.8 * nm and bestF == int(np.argmax(sF))
+    assert int(take(np.int32, 1)[0]) == 1           # TwoViewScorerB200::scoreKept == score (scores, kept iteration, its mask)
